@@ -1,0 +1,169 @@
+"""Pin the CPU oracle: bit-for-bit against the reference's OWN operator classes.
+
+oracle/_ref/libsmilei_ref.so is built by oracle/ref_build/build_ref.sh from the sources
+under /root/reference/src (Interpolator3D{2,4}Order, Pusher{Boris,Vay,HigueraCary},
+Projector3D{2,4}Order, MA_Solver3D_norm, MF_Solver3D_Yee, ElectroMagn3D, SpeciesV,
+BoundaryConditionType, Field3D, Particles).  Both sides are compiled -O2 -ffp-contract=off,
+so the comparison is exact equality of every output double / int.
+
+These tests run wherever the reference build exists (this container; the library also
+travels to the GPU box).  tests/test_oracle_golden.py checks the same oracle against
+committed outputs of that reference build, so the pin holds where _ref is absent.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+
+CASES = [  # (n, cell, dt, pcoord, npatch)
+    ((8, 8, 8), (0.07, 0.07, 0.07), 0.038, (0, 0, 0), (1, 1, 1)),
+    ((8, 9, 10), (0.07, 0.08, 0.09), 0.03, (1, 0, 2), (3, 1, 4)),
+    ((6, 12, 7), (0.2, 3.0, 3.0), 0.19, (2, 1, 0), (4, 2, 1)),
+]
+
+
+@pytest.fixture(scope="module")
+def libs():
+    return ol.Oracle(), ol.Reference()
+
+
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_interp_bit_exact(libs, order, case):
+    orc, ref = libs
+    n, cell, dt, pc, npch = CASES[case]
+    g = ol.make_grid(n, order, cell, dt, pc, npch)
+    rng = np.random.default_rng(10 * case + order)
+    F = ol.random_fields(g, rng)
+    P = ol.random_particles(g, rng, 3000)
+    a = orc.interp(g, order, F, P["x"], P["y"], P["z"])
+    b = ref.interp(g, order, F, P["x"], P["y"], P["z"])
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("pusher", [0, 1, 2])
+@pytest.mark.parametrize("mass,charge", [(1.0, -1), (1836.0, 1)])
+def test_push_bit_exact(libs, pusher, mass, charge):
+    orc, ref = libs
+    n, cell, dt, pc, npch = CASES[1]
+    g = ol.make_grid(n, 2, cell, dt, pc, npch)
+    rng = np.random.default_rng(100 + pusher)
+    N = 4000
+    P = ol.random_particles(g, rng, N, p_scale=2.0, charge=charge)
+    E = rng.standard_normal(3 * N)
+    B = rng.standard_normal(3 * N)
+    Pa = {k: v.copy() for k, v in P.items()}
+    Pb = {k: v.copy() for k, v in P.items()}
+    ia = orc.push(g, pusher, mass, Pa["x"], Pa["y"], Pa["z"], Pa["px"], Pa["py"], Pa["pz"], Pa["q"], E, B)
+    ib = ref.push(g, pusher, mass, Pb["x"], Pb["y"], Pb["z"], Pb["px"], Pb["py"], Pb["pz"], Pb["q"], E, B)
+    assert np.array_equal(ia, ib)
+    for k in ("x", "y", "z", "px", "py", "pz"):
+        assert np.array_equal(Pa[k], Pb[k]), k
+    assert not np.array_equal(Pa["px"], P["px"])
+
+
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_project_bit_exact(libs, order, case):
+    """gather -> push -> deposit chain, J compared exactly (same serial summation order)."""
+    orc, ref = libs
+    n, cell, dt, pc, npch = CASES[case]
+    g = ol.make_grid(n, order, cell, dt, pc, npch)
+    rng = np.random.default_rng(1000 + 10 * case + order)
+    F = ol.random_fields(g, rng, scale=0.1)
+    N = 2500
+    P = ol.random_particles(g, rng, N, p_scale=1.0)
+    E, B, iold, delta = orc.interp(g, order, F, P["x"], P["y"], P["z"])
+    orc.push(g, 0, 1.0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["q"], E, B)
+    Ja = {k: F[k].copy() for k in ("Jx", "Jy", "Jz")}
+    Jb = {k: F[k].copy() for k in ("Jx", "Jy", "Jz")}
+    orc.project(g, order, Ja, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+    ref.project(g, order, Jb, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+    for k in Ja:
+        assert np.array_equal(Ja[k], Jb[k]), k
+        assert not np.array_equal(Ja[k], F[k])
+
+
+def test_project_rho_bit_exact(libs):
+    orc, ref = libs
+    n, cell, dt, pc, npch = CASES[1]
+    g = ol.make_grid(n, 2, cell, dt, pc, npch)
+    rng = np.random.default_rng(77)
+    F = ol.random_fields(g, rng, scale=0.1)
+    N = 1500
+    P = ol.random_particles(g, rng, N, p_scale=1.0)
+    E, B, iold, delta = orc.interp(g, 2, F, P["x"], P["y"], P["z"])
+    orc.push(g, 0, 1.0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["q"], E, B)
+    Ja = {k: np.zeros(ol.field_dims(g, k)) for k in ("Jx", "Jy", "Jz", "rho")}
+    Jb = {k: np.zeros(ol.field_dims(g, k)) for k in ("Jx", "Jy", "Jz", "rho")}
+    orc.project_rho_o2(g, Ja, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+    ref.project_rho_o2(g, Jb, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+    for k in Ja:
+        assert np.array_equal(Ja[k], Jb[k]), k
+
+
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_maxwell_bit_exact(libs, order, case):
+    orc, ref = libs
+    n, cell, dt, pc, npch = CASES[case]
+    g = ol.make_grid(n, order, cell, dt, pc, npch)
+    rng = np.random.default_rng(2000 + 10 * case + order)
+    F = ol.random_fields(g, rng)
+    Fa = {k: v.copy() for k, v in F.items()}
+    Fb = {k: v.copy() for k, v in F.items()}
+    for lib, X in ((orc, Fa), (ref, Fb)):
+        lib.save_B(g, X)
+        lib.maxwell_ampere(g, X)
+        lib.maxwell_faraday(g, X)
+        lib.center_B(g, X)
+    for k in F:
+        assert np.array_equal(Fa[k], Fb[k]), k
+    for k in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm"):
+        assert not np.array_equal(Fa[k], F[k]), k
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_keys_and_bc_bit_exact(libs, case):
+    orc, ref = libs
+    n, cell, dt, pc, npch = CASES[case]
+    g = ol.make_grid(n, 2, cell, dt, pc, npch)
+    rng = np.random.default_rng(3000 + case)
+    N = 20000
+    P = ol.random_particles(g, rng, N)
+    mn, mx = ol.patch_bounds(g)
+    # put particles exactly on node / half-cell boundaries, where round() decides
+    for i, c in enumerate("xyz"):
+        P[c][:200] = mn[i] + rng.integers(0, n[i], 200) * g.cell[i]
+        P[c][200:400] = mn[i] + (rng.integers(0, n[i], 200) + 0.5) * g.cell[i]
+    ncells = (n[0] + 1) * (n[1] + 1) * (n[2] + 1)
+    ca = np.zeros(ncells, dtype=np.int32)
+    cb = np.zeros(ncells, dtype=np.int32)
+    ka = orc.cell_keys(g, P["x"], P["y"], P["z"], count=ca)
+    kb = ref.cell_keys(g, P["x"], P["y"], P["z"], count=cb)
+    assert np.array_equal(ka, kb) and np.array_equal(ca, cb)
+    assert ka.min() >= 0 and ka.max() < ncells and ca.sum() == N
+    # leavers on every face
+    for i, c in enumerate("xyz"):
+        P[c][1000 + 100 * i:1050 + 100 * i] = mn[i] - 0.3 * g.cell[i]
+        P[c][1050 + 100 * i:1100 + 100 * i] = mx[i] + 0.3 * g.cell[i]
+    P["x"][5000] = mx[0]  # exactly on the upper bound leaves (>=)
+    P["y"][5001] = mn[1]  # exactly on the lower bound stays (<)
+    ta = orc.bc_tag(g, P["x"], P["y"], P["z"])
+    tb = ref.bc_tag(g, P["x"], P["y"], P["z"])
+    assert np.array_equal(ta, tb)
+    assert set(np.unique(ta)) == {0, -2, -3, -4, -5, -6, -7}
+    assert ta[5000] == -3 and ta[5001] == 0
+
+
+@pytest.mark.parametrize("pcoord,npatch", [((0, 0, 0), (1, 1, 1)), ((0, 1, 2), (2, 3, 3)), ((1, 2, 1), (3, 3, 3))])
+def test_norm2_bit_exact(libs, pcoord, npatch):
+    orc, ref = libs
+    g = ol.make_grid((8, 6, 7), 2, (0.1, 0.1, 0.1), 0.05, pcoord, npatch)
+    rng = np.random.default_rng(5)
+    for name in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "rho"):
+        f = np.ascontiguousarray(rng.standard_normal(ol.field_dims(g, name)))
+        assert orc.field_norm2(g, f, name) == ref.field_norm2(g, f, name)
