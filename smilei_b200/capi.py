@@ -1,0 +1,257 @@
+"""ctypes binding of the C ABI declared in include/smilei_b200.h.
+
+The shared library is built in-tree (smilei_b200/csrc/libsmilei_b200.so, see
+__graft_entry__.build()).  There is no fallback of any kind: if the library is missing, or a
+call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsmilei_b200.so")
+
+FIELDS = ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm", "Jx", "Jy", "Jz", "rho")
+FIELD_ID = {name: i for i, name in enumerate(FIELDS)}
+# namelist aliases (src/ElectroMagn/ElectroMagn.h:163-190)
+FIELD_ID.update({"Bx_m": FIELD_ID["Bxm"], "By_m": FIELD_ID["Bym"], "Bz_m": FIELD_ID["Bzm"], "Rho": FIELD_ID["rho"]})
+PUSHERS = {"boris": 0, "vay": 1, "higueracary": 2}
+DYN_KEEP_SCRATCH = 1
+DYN_DIAG_RHO = 2
+UNPACK_COPY, UNPACK_ADD = 0, 1
+RECORD_DOUBLES = 8
+
+# every symbol include/smilei_b200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = (
+    "sb200_last_error", "sb200_abi_version", "sb200_device_count", "sb200_patch_create", "sb200_patch_destroy",
+    "sb200_patch_set_stream", "sb200_patch_synchronize", "sb200_species_config", "sb200_species_set",
+    "sb200_species_get", "sb200_species_count", "sb200_species_device_ptr", "sb200_species_first_index",
+    "sb200_field_size", "sb200_field_set", "sb200_field_get", "sb200_field_device_ptr", "sb200_restart_rhoJ",
+    "sb200_dynamics", "sb200_scratch_get", "sb200_maxwell", "sb200_center_B", "sb200_sort", "sb200_energy",
+    "sb200_halo_plane_elems", "sb200_halo_pack", "sb200_halo_unpack", "sb200_halo_sum_self",
+    "sb200_halo_exchange_self", "sb200_leaving_count", "sb200_leaving_pack", "sb200_arriving_unpack",
+    "sb200_debug_flags", "sb200_species_init_thermal",
+)
+
+
+class SmileiB200Error(RuntimeError):
+    """Raised for every non-zero return of the C ABI (the reference's ERROR(), Tools.h:127-133)."""
+
+
+class Grid(C.Structure):
+    """sb200_grid."""
+    _fields_ = [("n", C.c_int * 3), ("oversize", C.c_int * 3), ("cell_length", C.c_double * 3), ("dt", C.c_double),
+                ("pcoord", C.c_int * 3), ("npatch", C.c_int * 3), ("interp_order", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SmileiB200Error(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C smilei_b200/csrc). There is no CPU fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.sb200_last_error.restype = C.c_char_p
+        for s in SYMBOLS:
+            getattr(_lib, s)  # AttributeError if the library and the header disagree
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise SmileiB200Error(f"{what}: {lib().sb200_last_error().decode()}")
+
+
+def _p(a, dtype):
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == dtype and a.flags["C_CONTIGUOUS"], (a.dtype, dtype)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(lib().sb200_device_count(C.byref(n)), "sb200_device_count")
+    return n.value
+
+
+class Patch:
+    """One patch on one GPU: owns the device fields and the per-species SoA (sb200_patch)."""
+
+    def __init__(self, n, cell_length, dt, interp_order=2, n_species=0, pcoord=(0, 0, 0), npatch=(1, 1, 1),
+                 oversize=None, device=0):
+        oversize = (interp_order,) * 3 if oversize is None else tuple(oversize)
+        self.grid = Grid((C.c_int * 3)(*n), (C.c_int * 3)(*oversize), (C.c_double * 3)(*cell_length), float(dt),
+                         (C.c_int * 3)(*pcoord), (C.c_int * 3)(*npatch), int(interp_order))
+        self.n = tuple(n)
+        self.oversize = oversize
+        self.order = interp_order
+        self.n_species = n_species
+        self.ncells = (n[0] + 1) * (n[1] + 1) * (n[2] + 1)
+        self._h = C.c_void_p()
+        _check(lib().sb200_patch_create(C.byref(self._h), C.byref(self.grid), n_species, device), "sb200_patch_create")
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().sb200_patch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        _check(lib().sb200_patch_set_stream(self._h, C.c_void_p(cuda_stream)), "sb200_patch_set_stream")
+
+    def synchronize(self):
+        _check(lib().sb200_patch_synchronize(self._h), "sb200_patch_synchronize")
+
+    # -- species
+    def species_config(self, ispec, mass, pusher, capacity):
+        pusher = PUSHERS[pusher] if isinstance(pusher, str) else int(pusher)
+        _check(lib().sb200_species_config(self._h, ispec, C.c_double(mass), pusher, C.c_size_t(capacity)),
+               "sb200_species_config")
+
+    def species_set(self, ispec, x, y, z, px, py, pz, w, q):
+        n = len(x)
+        cols = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, px, py, pz, w)]
+        q = np.ascontiguousarray(q, dtype=np.int16)
+        _check(lib().sb200_species_set(self._h, ispec, *[_p(a, np.float64) for a in cols], _p(q, np.int16),
+                                       C.c_size_t(n)), "sb200_species_set")
+
+    def species_init_thermal(self, ispec, ppc, density, charge, temperature, seed=0):
+        _check(lib().sb200_species_init_thermal(self._h, ispec, (C.c_int * 3)(*ppc), C.c_double(density), int(charge),
+                                                C.c_double(temperature), C.c_ulonglong(seed)),
+               "sb200_species_init_thermal")
+
+    def species_count(self, ispec):
+        n = C.c_size_t(0)
+        _check(lib().sb200_species_count(self._h, ispec, C.byref(n)), "sb200_species_count")
+        return n.value
+
+    def species_get(self, ispec):
+        n = self.species_count(ispec)
+        out = {k: np.empty(n) for k in ("x", "y", "z", "px", "py", "pz", "w")}
+        out["q"] = np.empty(n, dtype=np.int16)
+        out["key"] = np.empty(n, dtype=np.int32)
+        _check(lib().sb200_species_get(self._h, ispec, *[_p(out[k], np.float64) for k in
+                                                         ("x", "y", "z", "px", "py", "pz", "w")],
+                                       _p(out["q"], np.int16), _p(out["key"], np.int32), C.c_size_t(n)),
+               "sb200_species_get")
+        return out
+
+    def species_device_ptr(self, ispec, column):
+        ptr = C.c_void_p()
+        _check(lib().sb200_species_device_ptr(self._h, ispec, column, C.byref(ptr)), "sb200_species_device_ptr")
+        return ptr.value
+
+    def first_index(self, ispec):
+        first = np.empty(self.ncells + 1, dtype=np.int32)
+        _check(lib().sb200_species_first_index(self._h, ispec, _p(first, np.int32), C.c_size_t(len(first))),
+               "sb200_species_first_index")
+        return first
+
+    # -- fields
+    def field_dims(self, name):
+        dims = (C.c_int * 3)()
+        n = C.c_size_t(0)
+        _check(lib().sb200_field_size(self._h, FIELD_ID[name], C.byref(n), dims), "sb200_field_size")
+        return tuple(dims)
+
+    def field_set(self, name, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        _check(lib().sb200_field_set(self._h, FIELD_ID[name], _p(a, np.float64), C.c_size_t(a.size)),
+               "sb200_field_set")
+
+    def field_get(self, name):
+        a = np.empty(self.field_dims(name))
+        _check(lib().sb200_field_get(self._h, FIELD_ID[name], _p(a, np.float64), C.c_size_t(a.size)),
+               "sb200_field_get")
+        return a
+
+    def field_device_ptr(self, name):
+        ptr = C.c_void_p()
+        alloc = (C.c_int * 3)()
+        _check(lib().sb200_field_device_ptr(self._h, FIELD_ID[name], C.byref(ptr), alloc), "sb200_field_device_ptr")
+        return ptr.value, tuple(alloc)
+
+    # -- time step
+    def restart_rhoJ(self):
+        _check(lib().sb200_restart_rhoJ(self._h), "sb200_restart_rhoJ")
+
+    def dynamics(self, ispec, flags=0):
+        _check(lib().sb200_dynamics(self._h, ispec, flags), "sb200_dynamics")
+
+    def scratch_get(self, n):
+        E = np.empty(3 * n)
+        B = np.empty(3 * n)
+        invgf = np.empty(n)
+        iold = np.empty(3 * n, dtype=np.int32)
+        delta = np.empty(3 * n)
+        _check(lib().sb200_scratch_get(self._h, _p(E, np.float64), _p(B, np.float64), _p(invgf, np.float64),
+                                       _p(iold, np.int32), _p(delta, np.float64), C.c_size_t(n)), "sb200_scratch_get")
+        return E, B, invgf, iold, delta
+
+    def maxwell(self):
+        _check(lib().sb200_maxwell(self._h), "sb200_maxwell")
+
+    def center_B(self):
+        _check(lib().sb200_center_B(self._h), "sb200_center_B")
+
+    def sort(self, ispec):
+        _check(lib().sb200_sort(self._h, ispec), "sb200_sort")
+
+    def energy(self):
+        ukin = np.zeros(max(self.n_species, 1))
+        uelm = C.c_double(0.)
+        _check(lib().sb200_energy(self._h, _p(ukin, np.float64), C.byref(uelm)), "sb200_energy")
+        return ukin[:self.n_species], uelm.value
+
+    def debug_flags(self):
+        f = np.zeros(8, dtype=np.int32)
+        _check(lib().sb200_debug_flags(self._h, _p(f, np.int32)), "sb200_debug_flags")
+        return f
+
+    # -- halos (device buffers are raw pointers: torch tensors' data_ptr())
+    def halo_plane_elems(self, name, dim):
+        n = C.c_size_t(0)
+        _check(lib().sb200_halo_plane_elems(self._h, FIELD_ID[name], dim, C.byref(n)), "sb200_halo_plane_elems")
+        return n.value
+
+    def halo_pack(self, name, dim, first_plane, nplanes, dev_ptr):
+        _check(lib().sb200_halo_pack(self._h, FIELD_ID[name], dim, first_plane, nplanes, C.c_void_p(dev_ptr)),
+               "sb200_halo_pack")
+
+    def halo_unpack(self, name, dim, first_plane, nplanes, dev_ptr, mode):
+        _check(lib().sb200_halo_unpack(self._h, FIELD_ID[name], dim, first_plane, nplanes, C.c_void_p(dev_ptr), mode),
+               "sb200_halo_unpack")
+
+    def halo_sum_self(self, name, dim):
+        _check(lib().sb200_halo_sum_self(self._h, FIELD_ID[name], dim), "sb200_halo_sum_self")
+
+    def halo_exchange_self(self, name, dim):
+        _check(lib().sb200_halo_exchange_self(self._h, FIELD_ID[name], dim), "sb200_halo_exchange_self")
+
+    # -- particle migration
+    def leaving_count(self, ispec):
+        c = (C.c_int * 6)()
+        _check(lib().sb200_leaving_count(self._h, ispec, c), "sb200_leaving_count")
+        return list(c)
+
+    def leaving_pack(self, ispec, dim, side, wrap, dev_ptr, max_records):
+        n = C.c_size_t(0)
+        _check(lib().sb200_leaving_pack(self._h, ispec, dim, side, C.c_double(wrap), C.c_void_p(dev_ptr),
+                                        C.c_size_t(max_records), C.byref(n)), "sb200_leaving_pack")
+        return n.value
+
+    def arriving_unpack(self, ispec, dev_ptr, n):
+        _check(lib().sb200_arriving_unpack(self._h, ispec, C.c_void_p(dev_ptr), C.c_size_t(n)),
+               "sb200_arriving_unpack")

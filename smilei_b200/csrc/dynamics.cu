@@ -1,0 +1,480 @@
+// dynamics.cu — Species::dynamics as ONE kernel per species: gather + push + boundary tag +
+// next cell key + Esirkepov deposit, on cell-sorted SoA particles.
+//
+// Restates, per particle (file:line relative to the reference's src/):
+//   Interpolator3D2Order::coeffs/compute/fieldsWrapper   Interpolator/Interpolator3D2Order.h:54-158, .cpp:163-285
+//   Interpolator3D4Order::coeffs/compute/fieldsWrapper   Interpolator/Interpolator3D4Order.h:40-144, .cpp:159-217
+//   PusherBoris / PusherVay / PusherHigueraCary          Pusher/PusherBoris.cpp:82-127, PusherVay.cpp:92-170, PusherHigueraCary.cpp:93-162
+//   PartBoundCond::apply + internal_inf/internal_sup      ParticleBC/PartBoundCond.h:38-76, BoundaryConditionType.cpp:15-57
+//   SpeciesV::computeParticleCellKeys                     Species/SpeciesV.cpp:796-812
+//   Projector3D2Order::currents / Projector3D4Order       Projector/Projector3D2Order.cpp:55-343, Projector3D4Order.cpp:49-233
+//
+// Design: one CTA per tile of TX x TY x TZ primal-node cells.  Because the
+// particles are sorted by cell key (z fastest), the tile's particles are TX*TY contiguous
+// runs.  The CTA stages the E and B_m stencil box of the tile in shared memory once, keeps a
+// private J accumulation box in shared memory, walks its particles one per thread, and
+// flushes the J box to HBM once with red.global.add.f64.  Particle traffic is the
+// algorithmic 110 B: read 7 doubles + 1 short, write 6 doubles + 1 int; Epart/Bpart/iold/
+// deltaold/invgf never exist in HBM unless SB200_DYN_KEEP_SCRATCH asks for them.
+#include "common.cuh"
+
+namespace sb200 {
+
+constexpr int TX = 4, TY = 4, TZ = 8;
+constexpr int DYN_THREADS = 256;
+
+template<int ORDER> struct Shape;
+// Interpolator3D2Order.h:107-123
+template<> struct Shape<2> {
+    __device__ static __forceinline__ void w( double d, double *c )
+    {
+        const double d2 = d*d;
+        c[0] = 0.5*( d2 - d + 0.25 );
+        c[1] = 0.75 - d2;
+        c[2] = 0.5*( d2 + d + 0.25 );
+    }
+};
+// Interpolator3D4Order.h:69-73 with the constants of Interpolator3D4Order.cpp:24-34
+template<> struct Shape<4> {
+    __device__ static __forceinline__ void w( double d, double *c )
+    {
+        const double d2 = d*d, d3 = d2*d, d4 = d3*d;
+        c[0] = 1.0/384.0   - 1.0/48.0*d  + 1.0/16.0*d2 - 1.0/12.0*d3 + 1.0/24.0*d4;
+        c[1] = 19.0/96.0   - 11.0/24.0*d + 1.0/4.0*d2  + 1.0/6.0*d3  - 1.0/6.0*d4;
+        c[2] = 115.0/192.0 - 5.0/8.0*d2  + 1.0/4.0*d4;
+        c[3] = 19.0/96.0   + 11.0/24.0*d + 1.0/4.0*d2  - 1.0/6.0*d3  - 1.0/6.0*d4;
+        c[4] = 1.0/384.0   + 1.0/48.0*d  + 1.0/16.0*d2 + 1.0/12.0*d3 + 1.0/24.0*d4;
+    }
+};
+
+template<int ORDER> struct Tile {
+    static constexpr int H  = ORDER/2;
+    static constexpr int NW = ORDER+1;            // gather points per dim
+    static constexpr int WD = ORDER+3;            // Esirkepov window per dim (5 or 7)
+    static constexpr int FX = TX+2*H+1, FY = TY+2*H+1, FZ = TZ+2*H+1;   // staged field box
+    static constexpr int JX = TX+2*H+2, JY = TY+2*H+2, JZ = TZ+2*H+2;   // J accumulation box
+    static constexpr int FVOL = FX*FY*FZ, JVOL = JX*JY*JZ;
+    static constexpr size_t SMEM = ( size_t )( 6*FVOL + 3*JVOL )*sizeof( double );
+};
+
+struct DynArgs {
+    double *col[7];
+    short  *q;
+    int    *key;
+    const int *first;
+    const double *F[6];       // Ex Ey Ez Bxm Bym Bzm
+    double *J[3];
+    int    *leave_counts;
+    int    *iflags;
+    double *sc_E, *sc_B, *sc_invgf, *sc_delta;
+    int    *sc_iold;
+    size_t  n;
+    double  one_over_mass;
+    int     tiles[3];
+};
+
+// separable gather of one component from its staged box: sum_i cx[i] sum_j cy[j] sum_k cz[k] F
+template<int ORDER>
+__device__ __forceinline__ double gather( const double *__restrict__ sF, const double *cx, const double *cy, const double *cz,
+                                          int sx, int sy, int sz )
+{
+    using T = Tile<ORDER>;
+    double acc = 0.;
+#pragma unroll
+    for( int i=0; i<T::NW; i++ ) {
+        double ai = 0.;
+#pragma unroll
+        for( int j=0; j<T::NW; j++ ) {
+            const double *row = sF + ( ( sx - T::H + i )*T::FY + ( sy - T::H + j ) )*T::FZ + ( sz - T::H );
+            double aj = 0.;
+#pragma unroll
+            for( int k=0; k<T::NW; k++ ) aj += cz[k]*row[k];
+            ai += cy[j]*aj;
+        }
+        acc += cx[i]*ai;
+    }
+    return acc;
+}
+
+template<int PUSHER>
+__device__ __forceinline__ void push( double cmd, double dt, double &px, double &py, double &pz,
+                                      double Ex, double Ey, double Ez, double Bx, double By, double Bz,
+                                      double &dxp, double &dyp, double &dzp, double &invgf_out )
+{
+    if( PUSHER == SB200_PUSHER_BORIS ) {
+        double pxsm = cmd*Ex, pysm = cmd*Ey, pzsm = cmd*Ez;
+        const double umx = px + pxsm, umy = py + pysm, umz = pz + pzsm;
+        double local_invgf = cmd / sqrt( 1.0 + umx*umx + umy*umy + umz*umz );
+        const double Tx = local_invgf*Bx, Ty = local_invgf*By, Tz = local_invgf*Bz;
+        const double inv_det_T = 1.0/( 1.0 + Tx*Tx + Ty*Ty + Tz*Tz );
+        pxsm += ( ( 1.0+Tx*Tx-Ty*Ty-Tz*Tz )*umx + 2.0*( Tx*Ty+Tz )*umy + 2.0*( Tz*Tx-Ty )*umz )*inv_det_T;
+        pysm += ( 2.0*( Tx*Ty-Tz )*umx + ( 1.0-Tx*Tx+Ty*Ty-Tz*Tz )*umy + 2.0*( Ty*Tz+Tx )*umz )*inv_det_T;
+        pzsm += ( 2.0*( Tz*Tx+Ty )*umx + 2.0*( Ty*Tz-Tx )*umy + ( 1.0-Tx*Tx-Ty*Ty+Tz*Tz )*umz )*inv_det_T;
+        local_invgf = 1./sqrt( 1.0 + pxsm*pxsm + pysm*pysm + pzsm*pzsm );
+        invgf_out = local_invgf;
+        px = pxsm; py = pysm; pz = pzsm;
+        local_invgf *= dt;
+        dxp = pxsm*local_invgf; dyp = pysm*local_invgf; dzp = pzsm*local_invgf;
+    } else if( PUSHER == SB200_PUSHER_VAY ) {
+        double invgf = 1./sqrt( 1.0 + px*px + py*py + pz*pz );
+        double upx = px + 2.*cmd*Ex, upy = py + 2.*cmd*Ey, upz = pz + 2.*cmd*Ez;
+        double Tx = cmd*Bx, Ty = cmd*By, Tz = cmd*Bz;
+        upx += invgf*( py*Tz - pz*Ty );
+        upy += invgf*( pz*Tx - px*Tz );
+        upz += invgf*( px*Ty - py*Tx );
+        double alpha = 1.0 + upx*upx + upy*upy + upz*upz;
+        const double T2 = Tx*Tx + Ty*Ty + Tz*Tz;
+        double s = alpha - T2;
+        double us2 = upx*Tx + upy*Ty + upz*Tz;
+        us2 = us2*us2;
+        alpha = 1.0/sqrt( 0.5*( s + sqrt( s*s + 4.0*( T2 + us2 ) ) ) );
+        Tx *= alpha; Ty *= alpha; Tz *= alpha;
+        s = 1.0/( 1.0 + Tx*Tx + Ty*Ty + Tz*Tz );
+        alpha = upx*Tx + upy*Ty + upz*Tz;
+        const double pxsm = s*( upx + alpha*Tx + Tz*upy - Ty*upz );
+        const double pysm = s*( upy + alpha*Ty + Tx*upz - Tz*upx );
+        const double pzsm = s*( upz + alpha*Tz + Ty*upx - Tx*upy );
+        invgf = 1.0/sqrt( 1.0 + pxsm*pxsm + pysm*pysm + pzsm*pzsm );
+        invgf_out = invgf;
+        px = pxsm; py = pysm; pz = pzsm;
+        dxp = dt*pxsm*invgf; dyp = dt*pysm*invgf; dzp = dt*pzsm*invgf;
+    } else {
+        double pxsm = cmd*Ex, pysm = cmd*Ey, pzsm = cmd*Ez;
+        const double umx = px + pxsm, umy = py + pysm, umz = pz + pzsm;
+        const double gfm2 = 1.0 + umx*umx + umy*umy + umz*umz;
+        double Tx = cmd*Bx, Ty = cmd*By, Tz = cmd*Bz;
+        const double beta2 = Tx*Tx + Ty*Ty + Tz*Tz;
+        const double Tum = Tx*umx + Ty*umy + Tz*umz;
+        const double local_invgf = 1./sqrt( 0.5*( gfm2 - beta2 + sqrt( ( gfm2-beta2 )*( gfm2-beta2 ) + 4.0*( beta2 + Tum*Tum ) ) ) );
+        Tx *= local_invgf; Ty *= local_invgf; Tz *= local_invgf;
+        const double Tx2 = Tx*Tx, Ty2 = Ty*Ty, Tz2 = Tz*Tz, TxTy = Tx*Ty, TyTz = Ty*Tz, TzTx = Tz*Tx;
+        const double inv_det_T = 1.0/( 1.0 + Tx2 + Ty2 + Tz2 );
+        const double upx = ( ( 1.0+Tx2-Ty2-Tz2 )*umx + 2.0*( TxTy+Tz )*umy + 2.0*( TzTx-Ty )*umz )*inv_det_T;
+        const double upy = ( 2.0*( TxTy-Tz )*umx + ( 1.0-Tx2+Ty2-Tz2 )*umy + 2.0*( TyTz+Tx )*umz )*inv_det_T;
+        const double upz = ( 2.0*( TzTx+Ty )*umx + 2.0*( TyTz-Tx )*umy + ( 1.0-Tx2-Ty2+Tz2 )*umz )*inv_det_T;
+        pxsm += upx; pysm += upy; pzsm += upz;
+        const double invgf = 1./sqrt( 1.0 + pxsm*pxsm + pysm*pysm + pzsm*pzsm );
+        invgf_out = invgf;
+        px = pxsm; py = pysm; pz = pzsm;
+        dxp = dt*pxsm*invgf; dyp = dt*pysm*invgf; dzp = dt*pzsm*invgf;
+    }
+}
+
+// S1 on the WD-point window from the NW weights `w` at shift s = ip - ipo in {-1,0,1}
+// (Projector3D2Order.cpp:124-152: Sx1[ip_m_ipo+1 .. +3] = weights)
+template<int ORDER>
+__device__ __forceinline__ void place_S1( const double *w, int shift, double *S1 )
+{
+    using T = Tile<ORDER>;
+#pragma unroll
+    for( int s=0; s<T::WD; s++ ) {
+        const double a = ( s-1 >= 0 && s-1 < T::NW ) ? w[( s-1 >= 0 && s-1 < T::NW ) ? s-1 : 0] : 0.;   // shift  0
+        const double b = ( s-2 >= 0 && s-2 < T::NW ) ? w[( s-2 >= 0 && s-2 < T::NW ) ? s-2 : 0] : 0.;   // shift +1
+        const double c = ( s   >= 0 && s   < T::NW ) ? w[( s   >= 0 && s   < T::NW ) ? s   : 0] : 0.;   // shift -1
+        S1[s] = shift == 0 ? a : ( shift > 0 ? b : c );
+    }
+}
+
+template<int ORDER, int PUSHER, bool SCRATCH>
+__global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, const DynArgs a )
+{
+    using T = Tile<ORDER>;
+    extern __shared__ double smem[];
+    double *sF = smem;                    // 6 boxes of FVOL
+    double *sJ = smem + 6*T::FVOL;        // 3 boxes of JVOL
+    __shared__ int row_off[TX*TY+1];
+    __shared__ int row_base[TX*TY];
+
+    const int tid = threadIdx.x;
+    int b = blockIdx.x;
+    const int tz = b % a.tiles[2]; b /= a.tiles[2];
+    const int ty = b % a.tiles[1];
+    const int tx = b / a.tiles[1];
+    const int c0[3] = { tx*TX, ty*TY, tz*TZ };
+
+    // particle runs of the tile
+    if( tid < TX*TY ) {
+        const int ix = c0[0] + tid/TY, iy = c0[1] + tid%TY;
+        int beg = 0, end = 0;
+        if( ix < g.ncell[0] && iy < g.ncell[1] ) {
+            const int kz1 = min( c0[2]+TZ, g.ncell[2] );
+            const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + c0[2];
+            beg = a.first[cell];
+            end = a.first[cell + ( kz1 - c0[2] )];
+        }
+        row_base[tid] = beg;
+        row_off[tid+1] = end - beg;
+    }
+    __syncthreads();
+    if( tid == 0 ) {
+        int s = 0;
+        row_off[0] = 0;
+        for( int r=0; r<TX*TY; r++ ) { s += row_off[r+1]; row_off[r+1] = s; }
+    }
+    __syncthreads();
+    const int total = row_off[TX*TY];
+    if( total == 0 ) return;
+
+    // stage the field boxes: box index s <-> array index gs + s, gs = c0 + o - H
+    const int gs[3] = { c0[0] + g.o[0] - T::H, c0[1] + g.o[1] - T::H, c0[2] + g.o[2] - T::H };
+    for( int t = tid; t < 6*T::FVOL; t += DYN_THREADS ) {
+        const int c = t / T::FVOL;
+        int r = t - c*T::FVOL;
+        const int k = r % T::FZ; r /= T::FZ;
+        const int j = r % T::FY;
+        const int i = r / T::FY;
+        const int gi = gs[0]+i, gj = gs[1]+j, gk = gs[2]+k;
+        double v = 0.;
+        if( gi < g.ax && gj < g.ay && gk < g.az ) v = a.F[c][gi*g.sx + gj*g.sy + gk];
+        sF[t] = v;
+    }
+    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0.;
+    __syncthreads();
+
+    const double third = 1./3.;
+    for( int wi = tid; wi < total; wi += DYN_THREADS ) {
+        // row of this work item (binary search in row_off)
+        int lo = 0, hi = TX*TY;
+        while( hi - lo > 1 ) { const int mid = ( lo+hi ) >> 1; if( row_off[mid] <= wi ) lo = mid; else hi = mid; }
+        const size_t ip = ( size_t )row_base[lo] + ( size_t )( wi - row_off[lo] );
+
+        double pos[3] = { a.col[0][ip], a.col[1][ip], a.col[2][ip] };
+        double px = a.col[3][ip], py = a.col[4][ip], pz = a.col[5][ip];
+        const double weight = a.col[6][ip];
+        const short charge = a.q[ip];
+
+        // ---- coefficients at the old position (Interpolator3D{2,4}Order::coeffs)
+        double cp[3][T::NW], cd[3][T::NW], delta_p[3];
+        int sp[3], sd[3], cl[3];   // box indices (primal, dual) and cell offset in the tile
+        bool bad = false;
+#pragma unroll
+        for( int d=0; d<3; d++ ) {
+            const double pn = pos[d]*g.dxi[d];
+            const int ipn = ( int )round( pn );
+            delta_p[d] = pn - ( double )ipn;
+            Shape<ORDER>::w( delta_p[d], cp[d] );
+            const int idn = ( int )round( pn + 0.5 );
+            const double dd = pn - ( double )idn + 0.5;
+            Shape<ORDER>::w( dd, cd[d] );
+            int c = ipn - g.begin[d] - g.o[d] - c0[d];       // cell offset inside the tile
+            const int tdim = d==0 ? TX : d==1 ? TY : TZ;
+            if( c < 0 || c >= tdim ) { bad = true; c = c < 0 ? 0 : tdim-1; }
+            cl[d] = c;
+            sp[d] = c + T::H;
+            sd[d] = sp[d] + ( idn - ipn );
+        }
+        if( bad ) atomicAdd( &a.iflags[1], 1 );   // particle not in the cell its sort key says
+
+        // ---- gather (fieldsWrapper): Ex(d,p,p) Ey(p,d,p) Ez(p,p,d) Bx(p,d,d) By(d,p,d) Bz(d,d,p)
+        const double Ex = gather<ORDER>( sF+0*T::FVOL, cd[0], cp[1], cp[2], sd[0], sp[1], sp[2] );
+        const double Ey = gather<ORDER>( sF+1*T::FVOL, cp[0], cd[1], cp[2], sp[0], sd[1], sp[2] );
+        const double Ez = gather<ORDER>( sF+2*T::FVOL, cp[0], cp[1], cd[2], sp[0], sp[1], sd[2] );
+        const double Bx = gather<ORDER>( sF+3*T::FVOL, cp[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+        const double By = gather<ORDER>( sF+4*T::FVOL, cd[0], cp[1], cd[2], sd[0], sp[1], sd[2] );
+        const double Bz = gather<ORDER>( sF+5*T::FVOL, cd[0], cd[1], cp[2], sd[0], sd[1], sp[2] );
+
+        // ---- push
+        const double cmd = ( double )charge*a.one_over_mass*g.dts2;
+        double dxp, dyp, dzp, invgf;
+        push<PUSHER>( cmd, g.dt, px, py, pz, Ex, Ey, Ez, Bx, By, Bz, dxp, dyp, dzp, invgf );
+        double npos[3] = { pos[0] + dxp, pos[1] + dyp, pos[2] + dzp };
+
+        a.col[0][ip] = npos[0]; a.col[1][ip] = npos[1]; a.col[2][ip] = npos[2];
+        a.col[3][ip] = px; a.col[4][ip] = py; a.col[5][ip] = pz;
+
+        if( SCRATCH ) {
+            a.sc_E[0*a.n+ip] = Ex; a.sc_E[1*a.n+ip] = Ey; a.sc_E[2*a.n+ip] = Ez;
+            a.sc_B[0*a.n+ip] = Bx; a.sc_B[1*a.n+ip] = By; a.sc_B[2*a.n+ip] = Bz;
+            a.sc_invgf[ip] = invgf;
+#pragma unroll
+            for( int d=0; d<3; d++ ) {
+                a.sc_iold[d*a.n+ip] = cl[d] + c0[d] + g.o[d];
+                a.sc_delta[d*a.n+ip] = delta_p[d];
+            }
+        }
+
+        // ---- S0 / S1 / DS on the Esirkepov window (Projector3D2Order.cpp:99-159)
+        double S0[3][T::WD], DS[3][T::WD];
+        int    nkey[3];
+        int    tag = 0;
+#pragma unroll
+        for( int d=0; d<3; d++ ) {
+            const double pn = npos[d]*g.dxi[d];
+            const int ipn = ( int )round( pn );
+            const double dl = pn - ( double )ipn;
+            double w1[T::NW], S1[T::WD];
+            Shape<ORDER>::w( dl, w1 );
+            const int shift = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );    // ip - ipo - i_domain_begin
+            place_S1<ORDER>( w1, shift, S1 );
+            S0[d][0] = 0.; S0[d][T::WD-1] = 0.;
+#pragma unroll
+            for( int s=0; s<T::NW; s++ ) S0[d][s+1] = cp[d][s];
+#pragma unroll
+            for( int s=0; s<T::WD; s++ ) DS[d][s] = S1[s] - S0[d][s];
+            nkey[d] = ( int )( ( double )ipn - g.min_loc_round[d] );
+            // PartBoundCond::apply: x first, then y, then z; first hit wins
+            if( tag == 0 ) {
+                if( npos[d] < g.xmin[d] ) tag = -2 - 2*d;
+                else if( npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
+            }
+        }
+        int key = tag;
+        if( tag == 0 ) key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2];
+        else atomicAdd( &a.leave_counts[-tag-2], 1 );
+        a.key[ip] = key;
+
+        // ---- currents (Esirkepov), accumulated in the tile's J box
+        const double charge_weight = g.inv_cell_volume*( double )charge*weight;
+        const double cr[3] = { charge_weight*g.d_ov_dt[0], charge_weight*g.d_ov_dt[1], charge_weight*g.d_ov_dt[2] };
+        double *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
+        // Jx: flux along x, weights over (y,z)
+        {
+            double C[T::WD];
+            double run = 0.;
+            C[0] = 0.;
+#pragma unroll
+            for( int i=1; i<T::WD; i++ ) { run -= cr[0]*DS[0][i-1]; C[i] = run; }
+#pragma unroll
+            for( int j=0; j<T::WD; j++ ) {
+#pragma unroll
+                for( int k=0; k<T::WD; k++ ) {
+                    const double W = S0[1][j]*S0[2][k] + 0.5*DS[1][j]*S0[2][k] + 0.5*DS[2][k]*S0[1][j] + third*DS[1][j]*DS[2][k];
+                    if( W != 0. ) {
+#pragma unroll
+                        for( int i=1; i<T::WD; i++ ) {
+                            const double v = C[i]*W;
+                            if( v != 0. ) atomicAdd( jb + 0*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
+                        }
+                    }
+                }
+            }
+        }
+        // Jy: flux along y, weights over (z,x)
+        {
+            double C[T::WD];
+            double run = 0.;
+            C[0] = 0.;
+#pragma unroll
+            for( int j=1; j<T::WD; j++ ) { run -= cr[1]*DS[1][j-1]; C[j] = run; }
+#pragma unroll
+            for( int i=0; i<T::WD; i++ ) {
+#pragma unroll
+                for( int k=0; k<T::WD; k++ ) {
+                    const double W = S0[2][k]*S0[0][i] + 0.5*DS[2][k]*S0[0][i] + 0.5*DS[0][i]*S0[2][k] + third*DS[2][k]*DS[0][i];
+                    if( W != 0. ) {
+#pragma unroll
+                        for( int j=1; j<T::WD; j++ ) {
+                            const double v = C[j]*W;
+                            if( v != 0. ) atomicAdd( jb + 1*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
+                        }
+                    }
+                }
+            }
+        }
+        // Jz: flux along z, weights over (x,y)
+        {
+            double C[T::WD];
+            double run = 0.;
+            C[0] = 0.;
+#pragma unroll
+            for( int k=1; k<T::WD; k++ ) { run -= cr[2]*DS[2][k-1]; C[k] = run; }
+#pragma unroll
+            for( int i=0; i<T::WD; i++ ) {
+#pragma unroll
+                for( int j=0; j<T::WD; j++ ) {
+                    const double W = S0[0][i]*S0[1][j] + 0.5*DS[0][i]*S0[1][j] + 0.5*DS[1][j]*S0[0][i] + third*DS[0][i]*DS[1][j];
+                    if( W != 0. ) {
+#pragma unroll
+                        for( int k=1; k<T::WD; k++ ) {
+                            const double v = C[k]*W;
+                            if( v != 0. ) atomicAdd( jb + 2*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // flush the J box: box index s <-> array index c0 + o - H - 1 + s
+    const int js[3] = { c0[0] + g.o[0] - T::H - 1, c0[1] + g.o[1] - T::H - 1, c0[2] + g.o[2] - T::H - 1 };
+    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) {
+        const double v = sJ[t];
+        if( v == 0. ) continue;
+        const int c = t / T::JVOL;
+        int r = t - c*T::JVOL;
+        const int k = r % T::JZ; r /= T::JZ;
+        const int j = r % T::JY;
+        const int i = r / T::JY;
+        const int gi = js[0]+i, gj = js[1]+j, gk = js[2]+k;
+        if( gi >= 0 && gj >= 0 && gk >= 0 && gi < g.ax && gj < g.ay && gk < g.az )
+            atomicAdd( a.J[c] + gi*g.sx + gj*g.sy + gk, v );
+    }
+}
+
+template<int ORDER, int PUSHER, bool SCRATCH>
+static int launch_one( sb200_patch *p, const DynArgs &a, int ntiles )
+{
+    using T = Tile<ORDER>;
+    auto kern = k_dynamics<ORDER, PUSHER, SCRATCH>;
+    SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )T::SMEM ) );
+    kern<<<ntiles, DYN_THREADS, T::SMEM, p->stream>>>( p->gd, a );
+    SB200_CUDA( cudaGetLastError() );
+    return 0;
+}
+
+template<int ORDER, int PUSHER>
+static int launch_scratch( sb200_patch *p, const DynArgs &a, int ntiles, bool scratch )
+{
+    return scratch ? launch_one<ORDER, PUSHER, true>( p, a, ntiles ) : launch_one<ORDER, PUSHER, false>( p, a, ntiles );
+}
+
+template<int ORDER>
+static int launch_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int pusher, bool scratch )
+{
+    switch( pusher ) {
+        case SB200_PUSHER_BORIS: return launch_scratch<ORDER, SB200_PUSHER_BORIS>( p, a, ntiles, scratch );
+        case SB200_PUSHER_VAY: return launch_scratch<ORDER, SB200_PUSHER_VAY>( p, a, ntiles, scratch );
+        default: return launch_scratch<ORDER, SB200_PUSHER_HIGUERACARY>( p, a, ntiles, scratch );
+    }
+}
+
+int launch_dynamics( sb200_patch *p, int ispec, int flags )
+{
+    SpeciesDev &s = p->sp[ispec];
+    SB200_CHECK( !( flags & SB200_DYN_DIAG_RHO ), "sb200_dynamics: SB200_DYN_DIAG_RHO is not built yet (diag-step rho deposit)" );
+    SB200_CUDA( cudaMemsetAsync( p->leave_counts + 8*ispec, 0, 8*sizeof( int ), p->stream ) );
+    if( s.n == 0 ) return 0;
+    const GridDev &g = p->gd;
+    const bool scratch = ( flags & SB200_DYN_KEEP_SCRATCH ) != 0;
+    if( scratch && p->sc_cap < s.n ) {
+        void *old[] = { p->sc_E, p->sc_B, p->sc_invgf, p->sc_delta, p->sc_iold };
+        for( void *m : old ) if( m ) cudaFree( m );
+        p->sc_cap = 0;
+        SB200_CUDA( cudaMalloc( &p->sc_E, 3*s.n*sizeof( double ) ) );
+        SB200_CUDA( cudaMalloc( &p->sc_B, 3*s.n*sizeof( double ) ) );
+        SB200_CUDA( cudaMalloc( &p->sc_invgf, s.n*sizeof( double ) ) );
+        SB200_CUDA( cudaMalloc( &p->sc_delta, 3*s.n*sizeof( double ) ) );
+        SB200_CUDA( cudaMalloc( &p->sc_iold, 3*s.n*sizeof( int ) ) );
+        p->sc_cap = s.n;
+    }
+    DynArgs a;
+    for( int c=0; c<7; c++ ) a.col[c] = s.col[c];
+    a.q = s.q; a.key = s.key; a.first = s.first;
+    const int fid[6] = { SB200_EX, SB200_EY, SB200_EZ, SB200_BXM, SB200_BYM, SB200_BZM };
+    for( int c=0; c<6; c++ ) a.F[c] = p->f[fid[c]];
+    a.J[0] = p->f[SB200_JX]; a.J[1] = p->f[SB200_JY]; a.J[2] = p->f[SB200_JZ];
+    a.leave_counts = p->leave_counts + 8*ispec;
+    a.iflags = p->iflags;
+    a.sc_E = p->sc_E; a.sc_B = p->sc_B; a.sc_invgf = p->sc_invgf; a.sc_delta = p->sc_delta; a.sc_iold = p->sc_iold;
+    a.n = s.n;
+    a.one_over_mass = 1.0/s.mass;                      // Pusher.cpp:20
+    a.tiles[0] = ( g.ncell[0] + TX - 1 )/TX;
+    a.tiles[1] = ( g.ncell[1] + TY - 1 )/TY;
+    a.tiles[2] = ( g.ncell[2] + TZ - 1 )/TZ;
+    const int ntiles = a.tiles[0]*a.tiles[1]*a.tiles[2];
+    if( g.order == 2 ) return launch_pusher<2>( p, a, ntiles, s.pusher, scratch );
+    return launch_pusher<4>( p, a, ntiles, s.pusher, scratch );
+}
+
+} // namespace sb200

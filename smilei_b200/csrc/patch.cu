@@ -1,0 +1,414 @@
+// patch.cu — patch handle, device memory, host<->device import/export of the
+// reference-layout field and particle arrays.
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace sb200 {
+
+static thread_local std::string g_err;
+void set_error( const std::string &s ) { g_err = s; }
+
+static void fill_grid( const sb200_grid &g, GridDev &d )
+{
+    d.order = g.interp_order;
+    for( int i=0; i<3; i++ ) {
+        d.n[i] = g.n[i];
+        d.o[i] = g.oversize[i];
+        d.p[i] = g.n[i] + 2*g.oversize[i] + 1;            // ElectroMagn.cpp:47
+        d.d[i] = g.n[i] + 2*g.oversize[i] + 2;            // ElectroMagn.cpp:48
+        d.ncell[i] = g.n[i] + 1;                          // SpeciesV.cpp:72-77
+        d.begin[i] = g.pcoord[i]*g.n[i] - g.oversize[i];  // Patch.cpp:148-150
+        d.cell[i] = g.cell_length[i];
+        d.dxi[i] = 1.0/g.cell_length[i];                  // Interpolator3D2Order.cpp:18-20
+        d.d_ov_dt[i] = g.cell_length[i]/g.dt;             // Projector3D2Order.cpp:21-25
+        d.dt_ov_d[i] = g.dt/g.cell_length[i];             // Solver3D.h:20-22
+        d.xmin[i] = ( g.pcoord[i]   )*( g.n[i]*g.cell_length[i] );   // Patch.cpp:146
+        d.xmax[i] = ( g.pcoord[i]+1 )*( g.n[i]*g.cell_length[i] );   // Patch.cpp:147
+        d.min_loc_round[i] = std::round( d.xmin[i]*d.dxi[i] );       // SpeciesV.cpp:800-802
+        d.pcoord[i] = g.pcoord[i];
+        d.npatch[i] = g.npatch[i];
+    }
+    d.dt = g.dt;
+    d.dts2 = g.dt/2.;                                     // Pusher.cpp:23
+    d.cell_volume = 1.0;
+    for( int i=0; i<3; i++ ) d.cell_volume *= g.cell_length[i];      // Params.cpp:1172-1186
+    d.inv_cell_volume = 1./d.cell_volume;                 // Projector.cpp:7
+    d.ax = d.d[0];
+    d.ay = d.d[1];
+    d.az = ( d.d[2] + 15 )/16*16;
+    d.sy = d.az;
+    d.sx = ( long long )d.ay*d.az;
+}
+
+int ensure_stage( sb200_patch *p, size_t elems )
+{
+    if( elems <= p->stage_cap ) return 0;
+    if( p->stage ) SB200_CUDA( cudaFree( p->stage ) );
+    p->stage = nullptr; p->stage_cap = 0;
+    SB200_CUDA( cudaMalloc( &p->stage, elems*sizeof( double ) ) );
+    p->stage_cap = elems;
+    return 0;
+}
+
+static int alloc_particle_cols( double **col, short **q, int **key, size_t cap )
+{
+    for( int c=0; c<7; c++ ) SB200_CUDA( cudaMalloc( &col[c], cap*sizeof( double ) ) );
+    SB200_CUDA( cudaMalloc( q, cap*sizeof( short ) ) );
+    SB200_CUDA( cudaMalloc( key, cap*sizeof( int ) ) );
+    return 0;
+}
+static void free_particle_cols( double **col, short **q, int **key )
+{
+    for( int c=0; c<7; c++ ) { if( col[c] ) cudaFree( col[c] ); col[c] = nullptr; }
+    if( *q ) cudaFree( *q ); *q = nullptr;
+    if( *key ) cudaFree( *key ); *key = nullptr;
+}
+
+int ensure_spare( sb200_patch *p, size_t cap )
+{
+    if( cap <= p->spare.cap ) return 0;
+    free_particle_cols( p->spare.col, &p->spare.q, &p->spare.key );
+    p->spare.cap = 0;
+    if( alloc_particle_cols( p->spare.col, &p->spare.q, &p->spare.key, cap ) ) return 1;
+    p->spare.cap = cap;
+    return 0;
+}
+
+int ensure_perm( sb200_patch *p, size_t cap )
+{
+    if( cap <= p->perm_cap ) return 0;
+    if( p->perm ) cudaFree( p->perm );
+    p->perm = nullptr; p->perm_cap = 0;
+    SB200_CUDA( cudaMalloc( &p->perm, cap*sizeof( int ) ) );
+    p->perm_cap = cap;
+    return 0;
+}
+
+// compact (reference) <-> padded (device) field conversion through the staging buffer
+__global__ void k_field_pad( const double *__restrict__ compact, double *__restrict__ padded,
+                             int nx, int ny, int nz, long long sx, long long sy, int to_padded )
+{
+    long long total = ( long long )nx*ny*nz;
+    for( long long t = blockIdx.x*( long long )blockDim.x + threadIdx.x; t < total; t += ( long long )gridDim.x*blockDim.x ) {
+        int k = ( int )( t % nz );
+        long long r = t / nz;
+        int j = ( int )( r % ny );
+        int i = ( int )( r / ny );
+        long long pi = i*sx + j*sy + k;
+        if( to_padded ) padded[pi] = compact[t];
+        else ( ( double * )compact )[t] = padded[pi];
+    }
+}
+
+static void field_dims( const GridDev &g, int id, int dims[3] )
+{
+    for( int i=0; i<3; i++ ) dims[i] = field_dual( id, i ) ? g.d[i] : g.p[i];
+}
+
+} // namespace sb200
+
+using namespace sb200;
+
+extern "C" {
+
+const char *sb200_last_error( void ) { return g_err.c_str(); }
+int sb200_abi_version( void ) { return SB200_ABI_VERSION; }
+
+int sb200_device_count( int *count )
+{
+    SB200_CHECK( count, "sb200_device_count: null pointer" );
+    SB200_CUDA( cudaGetDeviceCount( count ) );
+    return 0;
+}
+
+int sb200_patch_create( sb200_patch **out, const sb200_grid *grid, int n_species, int device )
+{
+    SB200_CHECK( out && grid, "sb200_patch_create: null pointer" );
+    SB200_CHECK( grid->interp_order==2 || grid->interp_order==4, "sb200_patch_create: interpolation_order must be 2 or 4" );
+    for( int i=0; i<3; i++ ) {
+        SB200_CHECK( grid->n[i] >= 2*grid->oversize[i]+2, "sb200_patch_create: patch_size must be >= 2*oversize+2 cells" );
+        SB200_CHECK( grid->oversize[i] >= grid->interp_order, "sb200_patch_create: oversize must be >= interpolation_order" );
+        SB200_CHECK( grid->cell_length[i] > 0., "sb200_patch_create: cell_length must be > 0" );
+        SB200_CHECK( grid->npatch[i] >= 1 && grid->pcoord[i] >= 0 && grid->pcoord[i] < grid->npatch[i], "sb200_patch_create: bad patch coordinates" );
+    }
+    SB200_CHECK( grid->dt > 0., "sb200_patch_create: timestep must be > 0" );
+    SB200_CHECK( n_species >= 0 && n_species <= 64, "sb200_patch_create: bad species count" );
+    int ndev = 0;
+    SB200_CUDA( cudaGetDeviceCount( &ndev ) );
+    SB200_CHECK( ndev > 0, "sb200_patch_create: no CUDA device (there is no CPU fallback)" );
+    SB200_CHECK( device >= 0 && device < ndev, "sb200_patch_create: bad device index" );
+    SB200_CUDA( cudaSetDevice( device ) );
+    cudaDeviceProp prop;
+    SB200_CUDA( cudaGetDeviceProperties( &prop, device ) );
+    SB200_CHECK( prop.major >= 10, "sb200_patch_create: kernels are built for sm_100a only" );
+
+    sb200_patch *p = new sb200_patch();
+    p->grid = *grid;
+    fill_grid( *grid, p->gd );
+    p->device = device;
+    p->nspec = n_species;
+    p->sp = new SpeciesDev[n_species > 0 ? n_species : 1];
+    const GridDev &g = p->gd;
+    SB200_CHECK( ( double )g.ncell[0]*g.ncell[1]*g.ncell[2] < 2.0e9, "sb200_patch_create: too many cells for int keys" );
+    p->ncells = ( size_t )g.ncell[0]*g.ncell[1]*g.ncell[2];
+    p->falloc = ( size_t )g.ax*g.ay*g.az;
+    for( int f=0; f<SB200_NFIELDS; f++ ) {
+        SB200_CUDA( cudaMalloc( &p->f[f], p->falloc*sizeof( double ) ) );
+        SB200_CUDA( cudaMemset( p->f[f], 0, p->falloc*sizeof( double ) ) );
+    }
+    SB200_CUDA( cudaMalloc( &p->count, ( p->ncells+1 )*sizeof( int ) ) );
+    SB200_CUDA( cudaMalloc( &p->cursor, ( p->ncells+1 )*sizeof( int ) ) );
+    SB200_CUDA( cudaMalloc( &p->red, 4096*sizeof( double ) ) );
+    SB200_CUDA( cudaMalloc( &p->leave_counts, 8*( n_species+1 )*sizeof( int ) ) );
+    SB200_CUDA( cudaMalloc( &p->iflags, 8*sizeof( int ) ) );
+    SB200_CUDA( cudaMemset( p->leave_counts, 0, 8*( n_species+1 )*sizeof( int ) ) );
+    SB200_CUDA( cudaMemset( p->iflags, 0, 8*sizeof( int ) ) );
+    *out = p;
+    return 0;
+}
+
+int sb200_patch_destroy( sb200_patch *p )
+{
+    if( !p ) return 0;
+    cudaSetDevice( p->device );
+    cudaDeviceSynchronize();
+    for( int f=0; f<SB200_NFIELDS; f++ ) if( p->f[f] ) cudaFree( p->f[f] );
+    for( int s=0; s<p->nspec; s++ ) {
+        free_particle_cols( p->sp[s].col, &p->sp[s].q, &p->sp[s].key );
+        if( p->sp[s].first ) cudaFree( p->sp[s].first );
+    }
+    free_particle_cols( p->spare.col, &p->spare.q, &p->spare.key );
+    void *misc[] = { p->count, p->cursor, p->perm, p->blocksums, p->stage, p->red, p->leave_counts, p->iflags,
+                     p->sc_E, p->sc_B, p->sc_invgf, p->sc_delta, p->sc_iold };
+    for( void *m : misc ) if( m ) cudaFree( m );
+    delete[] p->sp;
+    delete p;
+    return 0;
+}
+
+int sb200_patch_set_stream( sb200_patch *p, void *cuda_stream )
+{
+    SB200_CHECK( p, "sb200_patch_set_stream: null patch" );
+    p->stream = ( cudaStream_t )cuda_stream;
+    return 0;
+}
+
+int sb200_patch_synchronize( sb200_patch *p )
+{
+    SB200_CHECK( p, "sb200_patch_synchronize: null patch" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    return 0;
+}
+
+int sb200_species_config( sb200_patch *p, int ispec, double mass, int pusher, size_t capacity )
+{
+    SB200_CHECK( p && ispec >= 0 && ispec < p->nspec, "sb200_species_config: bad species index" );
+    SB200_CHECK( pusher >= 0 && pusher <= 2, "sb200_species_config: pusher must be boris(0), vay(1) or higueracary(2)" );
+    SB200_CHECK( mass > 0., "sb200_species_config: only massive species are on this path (mass > 0)" );
+    SB200_CHECK( capacity < ( size_t )2000000000u, "sb200_species_config: capacity must fit int indices" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    SpeciesDev &s = p->sp[ispec];
+    s.mass = mass;
+    s.pusher = pusher;
+    if( capacity > s.cap ) {
+        SB200_CHECK( s.n == 0, "sb200_species_config: cannot grow a populated species" );
+        free_particle_cols( s.col, &s.q, &s.key );
+        if( alloc_particle_cols( s.col, &s.q, &s.key, capacity ) ) return 1;
+        s.cap = capacity;
+    }
+    if( !s.first ) {
+        SB200_CUDA( cudaMalloc( &s.first, ( p->ncells+1 )*sizeof( int ) ) );
+        SB200_CUDA( cudaMemset( s.first, 0, ( p->ncells+1 )*sizeof( int ) ) );
+    }
+    return 0;
+}
+
+int sb200_species_set( sb200_patch *p, int ispec,
+                       const double *x, const double *y, const double *z,
+                       const double *px, const double *py, const double *pz,
+                       const double *w, const short *q, size_t n )
+{
+    SB200_CHECK( p && ispec >= 0 && ispec < p->nspec, "sb200_species_set: bad species index" );
+    SpeciesDev &s = p->sp[ispec];
+    SB200_CHECK( n <= s.cap, "sb200_species_set: more particles than the configured capacity" );
+    SB200_CHECK( n == 0 || ( x && y && z && px && py && pz && w && q ), "sb200_species_set: null column" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    const double *src[7] = { x, y, z, px, py, pz, w };
+    for( int c=0; c<7; c++ ) SB200_CUDA( cudaMemcpyAsync( s.col[c], src[c], n*sizeof( double ), cudaMemcpyHostToDevice, p->stream ) );
+    SB200_CUDA( cudaMemcpyAsync( s.q, q, n*sizeof( short ), cudaMemcpyHostToDevice, p->stream ) );
+    SB200_CUDA( cudaMemsetAsync( s.key, 0, n*sizeof( int ), p->stream ) );
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    s.n = n;
+    s.sorted = false;
+    return 0;
+}
+
+int sb200_species_get( sb200_patch *p, int ispec,
+                       double *x, double *y, double *z, double *px, double *py, double *pz,
+                       double *w, short *q, int *keys, size_t n )
+{
+    SB200_CHECK( p && ispec >= 0 && ispec < p->nspec, "sb200_species_get: bad species index" );
+    SpeciesDev &s = p->sp[ispec];
+    SB200_CHECK( n <= s.n, "sb200_species_get: asking for more particles than the species holds" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    double *dst[7] = { x, y, z, px, py, pz, w };
+    for( int c=0; c<7; c++ ) if( dst[c] ) SB200_CUDA( cudaMemcpyAsync( dst[c], s.col[c], n*sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
+    if( q ) SB200_CUDA( cudaMemcpyAsync( q, s.q, n*sizeof( short ), cudaMemcpyDeviceToHost, p->stream ) );
+    if( keys ) SB200_CUDA( cudaMemcpyAsync( keys, s.key, n*sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    return 0;
+}
+
+int sb200_species_count( sb200_patch *p, int ispec, size_t *n )
+{
+    SB200_CHECK( p && n && ispec >= 0 && ispec < p->nspec, "sb200_species_count: bad arguments" );
+    *n = p->sp[ispec].n;
+    return 0;
+}
+
+int sb200_species_device_ptr( sb200_patch *p, int ispec, int column, void **dev_ptr )
+{
+    SB200_CHECK( p && dev_ptr && ispec >= 0 && ispec < p->nspec, "sb200_species_device_ptr: bad arguments" );
+    SpeciesDev &s = p->sp[ispec];
+    if( column >= 0 && column < 7 ) *dev_ptr = s.col[column];
+    else if( column == 7 ) *dev_ptr = s.q;
+    else if( column == 8 ) *dev_ptr = s.key;
+    else SB200_CHECK( false, "sb200_species_device_ptr: column must be 0..8" );
+    return 0;
+}
+
+int sb200_species_first_index( sb200_patch *p, int ispec, int *first, size_t n )
+{
+    SB200_CHECK( p && first && ispec >= 0 && ispec < p->nspec, "sb200_species_first_index: bad arguments" );
+    SB200_CHECK( n == p->ncells+1, "sb200_species_first_index: n must be ncells+1" );
+    SB200_CHECK( p->sp[ispec].sorted, "sb200_species_first_index: species is not sorted" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    SB200_CUDA( cudaMemcpyAsync( first, p->sp[ispec].first, n*sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    return 0;
+}
+
+int sb200_field_size( sb200_patch *p, int field_id, size_t *n, int dims[3] )
+{
+    SB200_CHECK( p && field_id >= 0 && field_id < SB200_NFIELDS, "sb200_field_size: bad field id" );
+    int d[3];
+    field_dims( p->gd, field_id, d );
+    if( n ) *n = ( size_t )d[0]*d[1]*d[2];
+    if( dims ) { dims[0] = d[0]; dims[1] = d[1]; dims[2] = d[2]; }
+    return 0;
+}
+
+int sb200_field_set( sb200_patch *p, int field_id, const double *host, size_t n )
+{
+    SB200_CHECK( p && host && field_id >= 0 && field_id < SB200_NFIELDS, "sb200_field_set: bad arguments" );
+    int d[3];
+    field_dims( p->gd, field_id, d );
+    size_t total = ( size_t )d[0]*d[1]*d[2];
+    SB200_CHECK( n == total, "sb200_field_set: size does not match the field dims" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    if( ensure_stage( p, total ) ) return 1;
+    SB200_CUDA( cudaMemcpyAsync( p->stage, host, total*sizeof( double ), cudaMemcpyHostToDevice, p->stream ) );
+    SB200_CUDA( cudaMemsetAsync( p->f[field_id], 0, p->falloc*sizeof( double ), p->stream ) );
+    k_field_pad<<<1184, 256, 0, p->stream>>>( p->stage, p->f[field_id], d[0], d[1], d[2], p->gd.sx, p->gd.sy, 1 );
+    SB200_CUDA( cudaGetLastError() );
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    return 0;
+}
+
+int sb200_field_get( sb200_patch *p, int field_id, double *host, size_t n )
+{
+    SB200_CHECK( p && host && field_id >= 0 && field_id < SB200_NFIELDS, "sb200_field_get: bad arguments" );
+    int d[3];
+    field_dims( p->gd, field_id, d );
+    size_t total = ( size_t )d[0]*d[1]*d[2];
+    SB200_CHECK( n == total, "sb200_field_get: size does not match the field dims" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    if( ensure_stage( p, total ) ) return 1;
+    k_field_pad<<<1184, 256, 0, p->stream>>>( p->stage, p->f[field_id], d[0], d[1], d[2], p->gd.sx, p->gd.sy, 0 );
+    SB200_CUDA( cudaGetLastError() );
+    SB200_CUDA( cudaMemcpyAsync( host, p->stage, total*sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    return 0;
+}
+
+int sb200_field_device_ptr( sb200_patch *p, int field_id, void **dev_ptr, int alloc[3] )
+{
+    SB200_CHECK( p && dev_ptr && field_id >= 0 && field_id < SB200_NFIELDS, "sb200_field_device_ptr: bad arguments" );
+    *dev_ptr = p->f[field_id];
+    if( alloc ) { alloc[0] = p->gd.ax; alloc[1] = p->gd.ay; alloc[2] = p->gd.az; }
+    return 0;
+}
+
+int sb200_debug_flags( sb200_patch *p, int flags[8] )
+{
+    SB200_CHECK( p && flags, "sb200_debug_flags: bad arguments" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    SB200_CUDA( cudaMemcpyAsync( flags, p->iflags, 8*sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    return 0;
+}
+
+int sb200_restart_rhoJ( sb200_patch *p )
+{
+    SB200_CHECK( p, "sb200_restart_rhoJ: null patch" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    for( int f=SB200_JX; f<=SB200_RHO; f++ ) SB200_CUDA( cudaMemsetAsync( p->f[f], 0, p->falloc*sizeof( double ), p->stream ) );
+    return 0;
+}
+
+int sb200_dynamics( sb200_patch *p, int ispec, int flags )
+{
+    SB200_CHECK( p && ispec >= 0 && ispec < p->nspec, "sb200_dynamics: bad species index" );
+    SB200_CHECK( p->sp[ispec].sorted || p->sp[ispec].n == 0, "sb200_dynamics: species must be cell-sorted (call sb200_sort)" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    return launch_dynamics( p, ispec, flags );
+}
+
+int sb200_scratch_get( sb200_patch *p, double *Epart, double *Bpart, double *invgf, int *iold, double *deltaold, size_t n )
+{
+    SB200_CHECK( p, "sb200_scratch_get: null patch" );
+    SB200_CHECK( n <= p->sc_cap && p->sc_E, "sb200_scratch_get: no scratch of that size (run sb200_dynamics with SB200_DYN_KEEP_SCRATCH)" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    // device scratch is component-major with stride sc_n == n of the last dynamics call
+    if( Epart ) SB200_CUDA( cudaMemcpyAsync( Epart, p->sc_E, 3*n*sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
+    if( Bpart ) SB200_CUDA( cudaMemcpyAsync( Bpart, p->sc_B, 3*n*sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
+    if( invgf ) SB200_CUDA( cudaMemcpyAsync( invgf, p->sc_invgf, n*sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
+    if( iold ) SB200_CUDA( cudaMemcpyAsync( iold, p->sc_iold, 3*n*sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+    if( deltaold ) SB200_CUDA( cudaMemcpyAsync( deltaold, p->sc_delta, 3*n*sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    return 0;
+}
+
+int sb200_maxwell( sb200_patch *p )
+{
+    SB200_CHECK( p, "sb200_maxwell: null patch" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    return launch_maxwell( p );
+}
+
+int sb200_center_B( sb200_patch *p )
+{
+    SB200_CHECK( p, "sb200_center_B: null patch" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    return launch_center_shell( p );
+}
+
+int sb200_sort( sb200_patch *p, int ispec )
+{
+    SB200_CHECK( p && ispec >= 0 && ispec < p->nspec, "sb200_sort: bad species index" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    return launch_sort( p, ispec );
+}
+
+int sb200_energy( sb200_patch *p, double *ukin_per_species, double *uelm )
+{
+    SB200_CHECK( p, "sb200_energy: null patch" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    return launch_energy( p, ukin_per_species, uelm );
+}
+
+} // extern "C"

@@ -1,0 +1,208 @@
+// sort.cu — cell keys, histogram, exclusive scan and the stable counting sort of the SoA.
+//
+// Restates SpeciesV::computeParticleCellKeys (src/Species/SpeciesV.cpp:766-855) and the
+// result of SpeciesV::sortParticles (:599-762): particles with key<0 (tagged leavers) are
+// dropped, the others are ordered by cell key; first_index/last_index are the prefix sum of
+// the per-cell counts (:645-652).  Within a cell the order is the STABLE one (ascending
+// original index) — the canonical order of this build; the reference's in-place cycle sort
+// leaves an algorithm-dependent order within a cell.
+//
+// Pipeline (all on p->stream):
+//   k_keys_hist   key (if not already valid) + count[key]++                 4(+24) B/particle read
+//   scan          first = exclusive_scan(count)                             ncells ints
+//   k_scatter_idx slot = first[key] + atomicAdd(cursor[key]) ; perm[slot]=i  8 B/particle
+//   k_cell_sort   ascending insertion sort of each cell's run of perm        (restores stability)
+//   k_gather      out[c][j] = in[c][perm[j]] for the 9 columns               124 B/particle
+#include "common.cuh"
+
+namespace sb200 {
+
+__device__ __forceinline__ int cell_key_of( const GridDev &g, double x, double y, double z )
+{
+    // SpeciesV.cpp:806-812 — same int arithmetic, round() = half away from zero
+    int key = ( int )( round( x*g.dxi[0] ) - g.min_loc_round[0] );
+    key *= g.ncell[1];
+    key += ( int )( round( y*g.dxi[1] ) - g.min_loc_round[1] );
+    key *= g.ncell[2];
+    key += ( int )( round( z*g.dxi[2] ) - g.min_loc_round[2] );
+    return key;
+}
+
+__global__ void __launch_bounds__( 256 ) k_keys_hist( GridDev g, const double *__restrict__ x, const double *__restrict__ y,
+        const double *__restrict__ z, int *__restrict__ key, int *__restrict__ count, size_t n, int recompute, int ncells, int *__restrict__ iflags )
+{
+    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < n; i += ( size_t )gridDim.x*blockDim.x ) {
+        int k = key[i];
+        if( k < 0 ) continue;
+        if( recompute ) {
+            k = cell_key_of( g, x[i], y[i], z[i] );
+            if( k < 0 || k >= ncells ) {       // a particle outside the patch that nobody tagged
+                atomicAdd( &iflags[0], 1 );
+                k = -1;
+            }
+            key[i] = k;
+            if( k < 0 ) continue;
+        }
+        atomicAdd( &count[k], 1 );
+    }
+}
+
+// ---------------------------------------------------------------- exclusive scan (int)
+constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_B = SCAN_T*SCAN_E;
+
+__global__ void __launch_bounds__( SCAN_T ) k_scan_block( int *__restrict__ data, int *__restrict__ sums, size_t n )
+{
+    __shared__ int warp_tot[SCAN_T/32];
+    const size_t base = ( size_t )blockIdx.x*SCAN_B + ( size_t )threadIdx.x*SCAN_E;
+    int v[SCAN_E], t = 0;
+#pragma unroll
+    for( int e=0; e<SCAN_E; e++ ) { v[e] = base+e < n ? data[base+e] : 0; t += v[e]; }
+    // inclusive warp scan of the thread totals
+    int inc = t;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for( int d=1; d<32; d<<=1 ) { int u = __shfl_up_sync( 0xffffffffu, inc, d ); if( lane >= d ) inc += u; }
+    if( lane == 31 ) warp_tot[w] = inc;
+    __syncthreads();
+    int woff = 0;
+    for( int i=0; i<w; i++ ) woff += warp_tot[i];
+    int run = woff + inc - t;
+#pragma unroll
+    for( int e=0; e<SCAN_E; e++ ) { if( base+e < n ) data[base+e] = run; run += v[e]; }
+    if( threadIdx.x == SCAN_T-1 && sums ) sums[blockIdx.x] = run;
+}
+
+__global__ void __launch_bounds__( SCAN_T ) k_scan_add( int *__restrict__ data, const int *__restrict__ sums, size_t n )
+{
+    const int off = sums[blockIdx.x];
+    const size_t base = ( size_t )blockIdx.x*SCAN_B + ( size_t )threadIdx.x*SCAN_E;
+#pragma unroll
+    for( int e=0; e<SCAN_E; e++ ) if( base+e < n ) data[base+e] += off;
+}
+
+static int scan_rec( sb200_patch *p, int *data, size_t n, int *ws )
+{
+    const size_t nb = ( n + SCAN_B - 1 )/SCAN_B;
+    if( nb == 1 ) {
+        k_scan_block<<<1, SCAN_T, 0, p->stream>>>( data, nullptr, n );
+        SB200_CUDA( cudaGetLastError() );
+        return 0;
+    }
+    k_scan_block<<<( unsigned )nb, SCAN_T, 0, p->stream>>>( data, ws, n );
+    SB200_CUDA( cudaGetLastError() );
+    if( scan_rec( p, ws, nb, ws+nb ) ) return 1;
+    k_scan_add<<<( unsigned )nb, SCAN_T, 0, p->stream>>>( data, ws, n );
+    SB200_CUDA( cudaGetLastError() );
+    return 0;
+}
+
+int exclusive_scan_int( sb200_patch *p, int *data, size_t n )
+{
+    if( n == 0 ) return 0;
+    size_t need = 0, m = n;
+    while( m > 1 ) { m = ( m + SCAN_B - 1 )/SCAN_B; need += m; if( m == 1 ) break; }
+    need += 16;
+    if( need > p->blocksums_cap ) {
+        if( p->blocksums ) cudaFree( p->blocksums );
+        p->blocksums = nullptr; p->blocksums_cap = 0;
+        SB200_CUDA( cudaMalloc( &p->blocksums, need*sizeof( int ) ) );
+        p->blocksums_cap = need;
+    }
+    return scan_rec( p, data, n, p->blocksums );
+}
+
+// ---------------------------------------------------------------- scatter / per-cell order / gather
+__global__ void __launch_bounds__( 256 ) k_scatter_idx( const int *__restrict__ key, const int *__restrict__ first,
+        int *__restrict__ cursor, int *__restrict__ perm, size_t n )
+{
+    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < n; i += ( size_t )gridDim.x*blockDim.x ) {
+        const int k = key[i];
+        if( k < 0 ) continue;
+        const int slot = first[k] + atomicAdd( &cursor[k], 1 );
+        perm[slot] = ( int )i;
+    }
+}
+
+__global__ void __launch_bounds__( 128 ) k_cell_sort( const int *__restrict__ first, int *__restrict__ perm, int ncells )
+{
+    for( int c = blockIdx.x*blockDim.x + threadIdx.x; c < ncells; c += gridDim.x*blockDim.x ) {
+        const int b = first[c], e = first[c+1];
+        for( int i = b+1; i < e; i++ ) {
+            const int v = perm[i];
+            int j = i-1;
+            while( j >= b ) {
+                const int u = perm[j];
+                if( u <= v ) break;
+                perm[j+1] = u;
+                j--;
+            }
+            perm[j+1] = v;
+        }
+    }
+}
+
+struct Cols { double *c[7]; short *q; int *key; };
+
+__global__ void __launch_bounds__( 256 ) k_gather( Cols in, Cols out, const int *__restrict__ perm, size_t n )
+{
+    for( size_t j = blockIdx.x*( size_t )blockDim.x + threadIdx.x; j < n; j += ( size_t )gridDim.x*blockDim.x ) {
+        const int s = perm[j];
+#pragma unroll
+        for( int c=0; c<7; c++ ) out.c[c][j] = in.c[c][s];
+        out.q[j] = in.q[s];
+        out.key[j] = in.key[s];
+    }
+}
+
+int launch_sort( sb200_patch *p, int ispec )
+{
+    SpeciesDev &s = p->sp[ispec];
+    const size_t n = s.n;
+    const int ncells = ( int )p->ncells;
+    SB200_CUDA( cudaMemsetAsync( p->count, 0, ( p->ncells+1 )*sizeof( int ), p->stream ) );
+    SB200_CUDA( cudaMemsetAsync( p->cursor, 0, ( p->ncells+1 )*sizeof( int ), p->stream ) );
+    SB200_CUDA( cudaMemsetAsync( p->iflags, 0, 8*sizeof( int ), p->stream ) );
+    if( n > 0 ) {
+        if( ensure_spare( p, s.cap ) ) return 1;
+        if( ensure_perm( p, s.cap ) ) return 1;
+        const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*16 ? ( n + 255 )/256 : 148*16 );
+        // keys written by the fused dynamics kernel / arriving_unpack are already final; a
+        // freshly imported species (keys all 0, unsorted) gets them computed here
+        const int recompute = s.sorted ? 0 : 1;
+        k_keys_hist<<<blocks, 256, 0, p->stream>>>( p->gd, s.col[0], s.col[1], s.col[2], s.key, p->count, n, recompute, ncells, p->iflags );
+        SB200_CUDA( cudaGetLastError() );
+    }
+    // first = exclusive scan(count) over ncells+1 entries (last = total kept)
+    if( exclusive_scan_int( p, p->count, p->ncells+1 ) ) return 1;
+    SB200_CUDA( cudaMemcpyAsync( s.first, p->count, ( p->ncells+1 )*sizeof( int ), cudaMemcpyDeviceToDevice, p->stream ) );
+    int kept = 0, flags[8];
+    SB200_CUDA( cudaMemcpyAsync( &kept, s.first + p->ncells, sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+    SB200_CUDA( cudaMemcpyAsync( flags, p->iflags, 8*sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+    if( n > 0 ) {
+        const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*16 ? ( n + 255 )/256 : 148*16 );
+        k_scatter_idx<<<blocks, 256, 0, p->stream>>>( s.key, s.first, p->cursor, p->perm, n );
+        SB200_CUDA( cudaGetLastError() );
+        k_cell_sort<<<148*16, 128, 0, p->stream>>>( s.first, p->perm, ncells );
+        SB200_CUDA( cudaGetLastError() );
+    }
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    SB200_CHECK( flags[0] == 0, "sb200_sort: particles outside the patch without a leaving tag (positions must lie in [min,max) of the patch)" );
+    if( kept > 0 ) {
+        Cols in, out;
+        for( int c=0; c<7; c++ ) { in.c[c] = s.col[c]; out.c[c] = p->spare.col[c]; }
+        in.q = s.q; in.key = s.key; out.q = p->spare.q; out.key = p->spare.key;
+        const unsigned blocks = ( unsigned )( ( ( size_t )kept + 255 )/256 < 148*16 ? ( ( size_t )kept + 255 )/256 : 148*16 );
+        k_gather<<<blocks, 256, 0, p->stream>>>( in, out, p->perm, ( size_t )kept );
+        SB200_CUDA( cudaGetLastError() );
+        // swap the species storage with the spare set
+        for( int c=0; c<7; c++ ) { double *t = s.col[c]; s.col[c] = p->spare.col[c]; p->spare.col[c] = t; }
+        { short *t = s.q; s.q = p->spare.q; p->spare.q = t; }
+        { int *t = s.key; s.key = p->spare.key; p->spare.key = t; }
+        const size_t tc = s.cap; s.cap = p->spare.cap; p->spare.cap = tc;
+    }
+    s.n = ( size_t )kept;
+    s.sorted = true;
+    return 0;
+}
+
+} // namespace sb200

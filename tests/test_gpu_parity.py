@@ -1,0 +1,398 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (smilei_b200.capi), against
+the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * cell keys, sort permutation, particle counts, first_index .......... bit-exact
+  * Yee update (E, B, B_m) .............................................. bit-exact (<= 1e-12 required)
+  * gather + push (Epart, Bpart, x, p) .................................. <= 1e-12 relative
+  * Esirkepov deposit (J) ............................................... <= 1e-10 relative (summation order)
+Relative means: max |a-b| / max |b| over the array (fields and currents have cancelling
+terms, so a per-element ratio is meaningless where the value is ~0).
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+TOL_PUSH = 1e-12
+TOL_DEPOSIT = 1e-10
+
+
+def rel(a, b):
+    s = np.max(np.abs(b))
+    return np.max(np.abs(a - b)) / (s if s > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import smilei_b200
+    from smilei_b200 import capi
+    assert capi.device_count() >= 1
+    return smilei_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return ol.Oracle()
+
+
+def make_patch(sb, n, order, cell, dt, nspec=1, pcoord=(0, 0, 0), npatch=(1, 1, 1)):
+    return sb.Patch(n, cell, dt, interp_order=order, n_species=nspec, pcoord=pcoord, npatch=npatch)
+
+
+GEOMS = [((8, 8, 8), (0.07, 0.07, 0.07), 0.038, (0, 0, 0), (1, 1, 1)),
+         ((12, 9, 17), (0.07, 0.08, 0.09), 0.03, (1, 0, 2), (3, 1, 4))]
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_field_roundtrip(sb, order):
+    n = (12, 10, 14)
+    p = make_patch(sb, n, order, (0.1, 0.1, 0.1), 0.05, nspec=0)
+    g = ol.make_grid(n, order, (0.1, 0.1, 0.1), 0.05)
+    rng = np.random.default_rng(0)
+    for name in sb.FIELDS:
+        assert p.field_dims(name) == ol.field_dims(g, name)
+        a = rng.standard_normal(ol.field_dims(g, name))
+        p.field_set(name, a)
+        assert np.array_equal(p.field_get(name), a)
+    p.close()
+
+
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("geom", range(len(GEOMS)))
+def test_maxwell_bit_exact(sb, orc, order, geom):
+    n, cell, dt, pc, npch = GEOMS[geom]
+    if order == 4:
+        n = tuple(max(v, 10) for v in n)
+    g = ol.make_grid(n, order, cell, dt, pc, npch)
+    p = make_patch(sb, n, order, cell, dt, 0, pc, npch)
+    rng = np.random.default_rng(20 + order + geom)
+    F = ol.random_fields(g, rng)
+    for k, v in F.items():
+        p.field_set(k, v)
+    X = {k: v.copy() for k, v in F.items()}
+    orc.save_B(g, X)
+    orc.maxwell_ampere(g, X)
+    orc.maxwell_faraday(g, X)
+    p.maxwell()
+    for k in ("Ex", "Ey", "Ez", "Bx", "By", "Bz"):
+        assert np.array_equal(p.field_get(k), X[k]), k
+    orc.center_B(g, X)
+    p.center_B()
+    for k in ("Bxm", "Bym", "Bzm"):
+        assert np.array_equal(p.field_get(k), X[k]), k
+    # two more steps: the padded layout must stay clean
+    for _ in range(2):
+        orc.save_B(g, X)
+        orc.maxwell_ampere(g, X)
+        orc.maxwell_faraday(g, X)
+        orc.center_B(g, X)
+        p.maxwell()
+        p.center_B()
+    for k in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm"):
+        assert np.array_equal(p.field_get(k), X[k]), k
+    p.close()
+
+
+@pytest.mark.parametrize("geom", range(len(GEOMS)))
+def test_sort_bit_exact(sb, orc, geom):
+    n, cell, dt, pc, npch = GEOMS[geom]
+    g = ol.make_grid(n, 2, cell, dt, pc, npch)
+    p = make_patch(sb, n, 2, cell, dt, 1, pc, npch)
+    rng = np.random.default_rng(30 + geom)
+    N = 40000
+    P = ol.random_particles(g, rng, N)
+    mn, mx = ol.patch_bounds(g)
+    for i, c in enumerate("xyz"):   # particles exactly on nodes and half-cell boundaries
+        P[c][:300] = mn[i] + rng.integers(0, n[i], 300) * g.cell[i]
+        P[c][300:600] = mn[i] + (rng.integers(0, n[i], 300) + 0.5) * g.cell[i]
+    p.species_config(0, 1.0, "boris", N + 100)
+    p.species_set(0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+    p.sort(0)
+    ncells = (n[0] + 1) * (n[1] + 1) * (n[2] + 1)
+    keys = orc.cell_keys(g, P["x"], P["y"], P["z"])
+    first, perm = orc.counting_sort_perm(keys, ncells)
+    out = p.species_get(0)
+    assert p.species_count(0) == N
+    assert np.array_equal(p.first_index(0), first)
+    assert np.array_equal(out["key"], keys[perm])
+    for k in ("x", "y", "z", "px", "py", "pz", "w", "q"):
+        assert np.array_equal(out[k], P[k][perm]), k
+    # idempotence: sorting a sorted species changes nothing
+    p.sort(0)
+    out2 = p.species_get(0)
+    for k in out:
+        assert np.array_equal(out[k], out2[k]), k
+    p.close()
+
+
+def test_sort_empty_and_single(sb):
+    p = make_patch(sb, (8, 8, 8), 2, (0.1, 0.1, 0.1), 0.05, 1)
+    p.species_config(0, 1.0, "boris", 16)
+    p.sort(0)
+    assert p.species_count(0) == 0 and p.first_index(0).sum() == 0
+    p.dynamics(0)
+    one = [np.array([0.33]), np.array([0.41]), np.array([0.79])]
+    p.species_set(0, *one, np.zeros(1), np.zeros(1), np.zeros(1), np.ones(1), np.array([-1], dtype=np.int16))
+    p.sort(0)
+    f = p.first_index(0)
+    assert p.species_count(0) == 1 and f[-1] == 1
+    key = (3 * 9 + 4) * 9 + 8
+    assert f[key] == 0 and f[key + 1] == 1
+    p.close()
+
+
+def test_sort_rejects_untagged_outsiders(sb):
+    p = make_patch(sb, (8, 8, 8), 2, (0.1, 0.1, 0.1), 0.05, 1)
+    p.species_config(0, 1.0, "boris", 16)
+    x = np.array([0.1, 5.0])
+    p.species_set(0, x, x * 0 + 0.1, x * 0 + 0.1, x * 0, x * 0, x * 0, x * 0 + 1, np.array([-1, -1], dtype=np.int16))
+    with pytest.raises(sb.SmileiB200Error):
+        p.sort(0)
+    p.close()
+
+
+def oracle_dynamics(orc, g, order, pusher, mass, F, P):
+    """Species::dynamics order (Species.cpp:591,727,757,782) + computeParticleCellKeys."""
+    E, B, iold, delta = orc.interp(g, order, F, P["x"], P["y"], P["z"])
+    invgf = orc.push(g, pusher, mass, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["q"], E, B)
+    tags = orc.bc_tag(g, P["x"], P["y"], P["z"])
+    J = {k: F[k].copy() for k in ("Jx", "Jy", "Jz")}
+    orc.project(g, order, J, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+    keys = tags.copy()
+    orc.cell_keys(g, P["x"], P["y"], P["z"], keys=keys)
+    return E, B, invgf, iold, delta, J, keys
+
+
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("pusher", [0, 1, 2])
+@pytest.mark.parametrize("geom", range(len(GEOMS)))
+def test_dynamics_parity(sb, orc, order, pusher, geom):
+    n, cell, dt, pc, npch = GEOMS[geom]
+    if order == 4:
+        n = tuple(max(v, 10) for v in n)
+    g = ol.make_grid(n, order, cell, dt, pc, npch)
+    p = make_patch(sb, n, order, cell, dt, 1, pc, npch)
+    rng = np.random.default_rng(40 + 10 * order + pusher + 100 * geom)
+    F = ol.random_fields(g, rng, scale=0.3)
+    mass, charge = (1.0, -1) if pusher != 1 else (3.0, 2)
+    N = 30000
+    P = ol.random_particles(g, rng, N, p_scale=1.5, charge=charge)   # fast: many cross cells, some leave
+    for k, v in F.items():
+        p.field_set(k, v)
+    p.species_config(0, mass, pusher, N)
+    p.species_set(0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+    p.sort(0)
+    S = p.species_get(0)                       # sorted order = what the kernel walks
+    p.dynamics(0, flags=1)
+    assert p.debug_flags()[1] == 0
+    out = p.species_get(0)
+    gE, gB, ginvgf, giold, gdelta = p.scratch_get(N)
+    E, B, invgf, iold, delta, J, keys = oracle_dynamics(orc, g, order, pusher, mass, F, S)
+    assert np.array_equal(giold, iold)
+    assert np.array_equal(gdelta, delta)
+    assert rel(gE, E) <= TOL_PUSH and rel(gB, B) <= TOL_PUSH
+    assert rel(ginvgf, invgf) <= TOL_PUSH
+    for k in ("px", "py", "pz"):
+        assert rel(out[k], S[k]) <= TOL_PUSH, k
+    mn, mx = ol.patch_bounds(g)
+    for i, k in enumerate("xyz"):
+        assert np.max(np.abs(out[k] - S[k])) <= TOL_PUSH * max(abs(mx[i]), g.cell[i]), k
+    # keys: bit-exact given identical positions -> recompute the oracle's keys from the GPU's positions
+    tags = orc.bc_tag(g, out["x"], out["y"], out["z"])
+    k2 = tags.copy()
+    orc.cell_keys(g, out["x"], out["y"], out["z"], keys=k2)
+    assert np.array_equal(out["key"], k2)
+    assert (out["key"] < 0).sum() > 0                       # the case does exercise leavers
+    assert np.mean(out["key"] != keys) < 1e-3               # and agrees with the oracle's own trajectory
+    cnt = p.leaving_count(0)
+    assert cnt == [int((k2 == -2 - t).sum()) for t in range(6)]
+    for k in ("Jx", "Jy", "Jz"):
+        assert rel(p.field_get(k), J[k]) <= TOL_DEPOSIT, k
+    p.close()
+
+
+def test_dynamics_slow_particles_and_two_species(sb, orc):
+    """Thermal-plasma-like case: nobody crosses more than one cell, most cross none; two species
+    deposit into the same J."""
+    n, cell, dt = (16, 16, 16), (0.07, 0.07, 0.07), 0.038
+    g = ol.make_grid(n, 2, cell, dt)
+    p = make_patch(sb, n, 2, cell, dt, 2)
+    rng = np.random.default_rng(7)
+    F = ol.random_fields(g, rng, scale=0.01)
+    for k in ("Jx", "Jy", "Jz"):
+        F[k][:] = 0.
+    for k, v in F.items():
+        p.field_set(k, v)
+    J = {k: F[k].copy() for k in ("Jx", "Jy", "Jz")}
+    for ispec, (mass, charge, ps) in enumerate([(1836.0, 1, 0.14 * 1836 ** 0.5 / 1836), (1.0, -1, 0.14)]):
+        N = 16 * 16 * 16 * 8
+        P = ol.random_particles(g, rng, N, p_scale=ps, charge=charge)
+        p.species_config(ispec, mass, "boris", N)
+        p.species_set(ispec, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+        p.sort(ispec)
+        S = p.species_get(ispec)
+        p.dynamics(ispec)
+        out = p.species_get(ispec)
+        E, B, iold, delta = orc.interp(g, 2, F, S["x"], S["y"], S["z"])
+        orc.push(g, 0, mass, S["x"], S["y"], S["z"], S["px"], S["py"], S["pz"], S["q"], E, B)
+        orc.project(g, 2, J, S["x"], S["y"], S["z"], S["q"], S["w"], iold, delta)
+        for k in ("px", "py", "pz"):
+            assert rel(out[k], S[k]) <= TOL_PUSH, k
+    for k in ("Jx", "Jy", "Jz"):
+        assert rel(p.field_get(k), J[k]) <= TOL_DEPOSIT, k
+    p.close()
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_halo_self_matches_oracle(sb, orc, order):
+    n = (12, 10, 14)
+    g = ol.make_grid(n, order, (0.1, 0.1, 0.1), 0.05)
+    p = make_patch(sb, n, order, (0.1, 0.1, 0.1), 0.05, 0)
+    rng = np.random.default_rng(50 + order)
+    F = ol.random_fields(g, rng)
+    for k, v in F.items():
+        p.field_set(k, v)
+    # SyncVectorPatch::sumAllComponents order: x, then y, then z, on Jx, Jy, Jz
+    for dim in range(3):
+        for k in ("Jx", "Jy", "Jz"):
+            orc.sum_pair(g, dim, k, F[k], F[k])
+            p.halo_sum_self(k, dim)
+    for k in ("Jx", "Jy", "Jz"):
+        assert np.array_equal(p.field_get(k), F[k]), k
+    # SyncVectorPatch::exchangeB: along x By,Bz; along y Bx,Bz; along z Bx,By
+    for dim, comps in ((0, ("By", "Bz")), (1, ("Bx", "Bz")), (2, ("Bx", "By"))):
+        for k in comps:
+            orc.exchange_pair(g, dim, k, F[k], F[k])
+            p.halo_exchange_self(k, dim)
+    for k in ("Bx", "By", "Bz"):
+        assert np.array_equal(p.field_get(k), F[k]), k
+    p.close()
+
+
+def test_halo_pack_unpack_roundtrip(sb):
+    import torch
+    n = (12, 10, 14)
+    p = make_patch(sb, n, 2, (0.1, 0.1, 0.1), 0.05, 0)
+    rng = np.random.default_rng(60)
+    for name in ("Jx", "By", "Ez"):
+        a = rng.standard_normal(p.field_dims(name))
+        for dim in range(3):
+            p.field_set(name, a)
+            first, npl = 3, 4
+            elems = p.halo_plane_elems(name, dim)
+            buf = torch.zeros(npl * elems, dtype=torch.float64, device="cuda")
+            p.halo_pack(name, dim, first, npl, buf.data_ptr())
+            p.synchronize()
+            sl = [slice(None)] * 3
+            sl[dim] = slice(first, first + npl)
+            expect = np.moveaxis(a[tuple(sl)], dim, 0).reshape(-1)
+            assert np.array_equal(buf.cpu().numpy(), expect)
+            p.halo_unpack(name, dim, first + 2, npl, buf.data_ptr(), 1)
+            b = a.copy()
+            sl2 = [slice(None)] * 3
+            sl2[dim] = slice(first + 2, first + 2 + npl)
+            b[tuple(sl2)] += a[tuple(sl)]
+            assert np.array_equal(p.field_get(name), b)
+    p.close()
+
+
+def test_energy_matches_oracle(sb, orc):
+    n = (12, 10, 14)
+    for pc, npch in (((0, 0, 0), (1, 1, 1)), ((1, 0, 2), (3, 2, 3))):
+        g = ol.make_grid(n, 2, (0.1, 0.11, 0.12), 0.05, pc, npch)
+        p = make_patch(sb, n, 2, (0.1, 0.11, 0.12), 0.05, 2, pc, npch)
+        rng = np.random.default_rng(70)
+        F = ol.random_fields(g, rng)
+        for k, v in F.items():
+            p.field_set(k, v)
+        uk = []
+        for ispec, mass in enumerate((1836.0, 1.0)):
+            P = ol.random_particles(g, rng, 5000 + ispec)
+            p.species_config(ispec, mass, "boris", 6000)
+            p.species_set(ispec, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+            uk.append(orc.ukin(mass, P["px"], P["py"], P["pz"], P["w"]))
+        ukin, uelm = p.energy()
+        assert np.allclose(ukin, uk, rtol=1e-13, atol=0)
+        assert abs(uelm - orc.uelm(g, F)) <= 1e-13 * abs(uelm)
+        p.close()
+
+
+def test_particle_exchange_self_periodic(sb, orc):
+    """Leavers of a single periodic patch come back through pack -> unpack with the wrap of
+    Patch::prepareParticles, x then y then z (corner particles are forwarded)."""
+    import torch
+    n, cell, dt = (8, 8, 8), (0.1, 0.1, 0.1), 0.05
+    g = ol.make_grid(n, 2, cell, dt)
+    p = make_patch(sb, n, 2, cell, dt, 1)
+    rng = np.random.default_rng(80)
+    N = 20000
+    P = ol.random_particles(g, rng, N, p_scale=3.0)   # relativistic: ~half a cell per step
+    for k in ("Ex", "Ey", "Ez", "Bxm", "Bym", "Bzm"):
+        p.field_set(k, np.zeros(ol.field_dims(g, k)))
+    p.species_config(0, 1.0, "boris", 2 * N)
+    p.species_set(0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+    p.sort(0)
+    p.dynamics(0)
+    before = p.species_get(0)
+    L = [n[i] * cell[i] for i in range(3)]
+    buf = torch.zeros(8 * N, dtype=torch.float64, device="cuda")
+    moved = 0
+    for dim in range(3):
+        for side in (0, 1):
+            wrap = L[dim] if side == 0 else -L[dim]
+            k = p.leaving_pack(0, dim, side, wrap, buf.data_ptr(), N)
+            p.arriving_unpack(0, buf.data_ptr(), k)
+            moved += k
+    assert moved > 0
+    p.sort(0)
+    after = p.species_get(0)
+    assert len(after["x"]) == N                      # nobody lost, nobody duplicated
+    for i, c in enumerate("xyz"):
+        assert after[c].min() >= 0. and after[c].max() < L[i]
+    # expected: wrap every coordinate like prepareParticles does, then the canonical sort
+    exp = {k: v.copy() for k, v in before.items()}
+    order = []
+    # resident particles keep their slots; forwarded ones are appended in (dim, side, index) order
+    alive = before["key"] >= 0
+    idx_res = np.flatnonzero(alive)
+    pos = {c: before[c].copy() for c in "xyz"}
+    appended = []
+    tagged = {t: list(np.flatnonzero(before["key"] == t)) for t in range(-7, -1)}
+    for dim in range(3):
+        c = "xyz"[dim]
+        for side in (0, 1):
+            tag = -2 - 2 * dim - side
+            lst = tagged[tag]
+            tagged[tag] = []
+            for i in lst:
+                if side == 0 and pos[c][i] < 0.:
+                    pos[c][i] += L[dim]
+                if side == 1 and pos[c][i] >= L[dim]:
+                    pos[c][i] -= L[dim]
+                # re-tag in the remaining dims (cornersParticles)
+                t2 = 0
+                for d2 in range(3):
+                    v = pos["xyz"[d2]][i]
+                    if v < 0.:
+                        t2 = -2 - 2 * d2
+                        break
+                    if v >= L[d2]:
+                        t2 = -3 - 2 * d2
+                        break
+                if t2 == 0:
+                    appended.append(i)
+                else:
+                    tagged[t2].append(i)
+    final = list(idx_res) + appended
+    fx, fy, fz = (np.ascontiguousarray(pos[c][final]) for c in "xyz")
+    keys = orc.cell_keys(g, fx, fy, fz)
+    first, perm = orc.counting_sort_perm(keys, 9 * 9 * 9)
+    final = np.array(final)[perm]
+    for c in "xyz":
+        assert np.array_equal(after[c], pos[c][final]), c
+    for k in ("px", "py", "pz", "w", "q"):
+        assert np.array_equal(after[k], before[k][final]), k
+    p.close()
