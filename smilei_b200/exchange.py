@@ -1,0 +1,229 @@
+"""Neighbour exchange between patches held by different GPUs: the NCCL replacement of
+SmileiMPI / SyncVectorPatch for the hot path.
+
+One patch per process per GPU on a Cartesian grid of ranks (`npatch`), periodic box.  Three
+exchanges per step, each x -> y -> z sequential so that edges and corners propagate exactly
+as in the reference:
+
+  * sum_J       SyncVectorPatch::sumAllComponents          (src/Patch/SyncVectorPatch.cpp:203-…)
+  * exchange_B  SyncVectorPatch::exchangeB                  (:667-699, :1441-1527)
+  * particles   SyncVectorPatch::initExchParticles / finalizeExchParticlesAndSort (:27-113),
+                Patch::exchNbrOfParticles / prepareParticles / exchParticles / cornersParticles
+                (src/Patch/Patch.cpp:560-800)
+
+Transport is torch.distributed point-to-point (`batch_isend_irecv`): NCCL over NVLink on
+GPUs, gloo in the CPU tests.  NCCL has no tags; when the -dim and +dim neighbour are the
+same peer (2 ranks along a periodic dimension) both payloads travel in ONE message with a
+fixed layout, which replaces the MPI tags of Patch.cpp:573,587.  A dimension held by a
+single rank wraps on the device without any message (the reference's same-rank pointer
+copies, SyncVectorPatch.cpp:288-311).
+
+The patch object only has to provide the halo / migration hooks of include/smilei_b200.h
+(smilei_b200.capi.Patch does; the CPU tests plug an oracle-backed stand-in).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+UNPACK_COPY, UNPACK_ADD = 0, 1
+RECORD = 8  # doubles per migrating particle (SB200_PARTICLE_RECORD_DOUBLES)
+
+J_FIELDS = ("Jx", "Jy", "Jz")
+# components exchanged per direction = the two that are dual in it (SyncVectorPatch.cpp:690-695)
+B_EXCHANGE = ((0, ("By", "Bz")), (1, ("Bx", "Bz")), (2, ("Bx", "By")))
+_DUAL = {"Jx": (1, 0, 0), "Jy": (0, 1, 0), "Jz": (0, 0, 1), "Bx": (0, 1, 1), "By": (1, 0, 1), "Bz": (1, 1, 0),
+         "rho": (0, 0, 0)}
+
+
+def rank_to_pcoord(rank, npatch):
+    """Row-major rank <-> patch coordinates (x slowest).  Inside one NVSwitch box every peer is
+    equidistant, so the Hilbert ordering of the reference brings nothing."""
+    return tuple(int(v) for v in np.unravel_index(rank, npatch))
+
+
+def pcoord_to_rank(pcoord, npatch):
+    return int(np.ravel_multi_index(tuple(c % n for c, n in zip(pcoord, npatch)), npatch))
+
+
+class Exchanger:
+    """Halo and particle exchange for ONE patch (this rank's) on a periodic Cartesian rank grid."""
+
+    def __init__(self, patch, n, oversize, cell_length, npatch, pcoord, device, group=None, particle_buffer=1 << 16):
+        self.patch = patch
+        self.n = tuple(n)
+        self.o = tuple(oversize)
+        self.cell = tuple(cell_length)
+        self.npatch = tuple(npatch)
+        self.pcoord = tuple(pcoord)
+        self.device = torch.device(device)
+        self.group = group
+        self.world = int(np.prod(self.npatch))
+        if self.world > 1:
+            assert dist.is_initialized(), "torch.distributed must be initialised for more than one patch"
+            assert dist.get_world_size(group) == self.world
+            assert pcoord_to_rank(self.pcoord, self.npatch) == dist.get_rank(group)
+        self.nbr = []
+        for d in range(3):
+            lo = list(self.pcoord)
+            hi = list(self.pcoord)
+            lo[d] -= 1
+            hi[d] += 1
+            self.nbr.append((pcoord_to_rank(lo, self.npatch), pcoord_to_rank(hi, self.npatch)))
+        self._bufs = {}
+        self._pcap = int(particle_buffer)
+        self.bytes_sent = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, key, numel):
+        b = self._bufs.get(key)
+        if b is None or b.numel() < numel:
+            b = torch.empty(max(numel, 1), dtype=torch.float64, device=self.device)
+            self._bufs[key] = b
+        return b
+
+    def _sendrecv(self, ops):
+        """ops: list of (peer, send_tensor, recv_tensor).  One batch = one NCCL group."""
+        p2p = []
+        for peer, s, r in ops:
+            p2p.append(dist.P2POp(dist.isend, s, peer, self.group))
+            p2p.append(dist.P2POp(dist.irecv, r, peer, self.group))
+            self.bytes_sent += s.numel() * s.element_size()
+        for w in dist.batch_isend_irecv(p2p):
+            w.wait()
+
+    def _exchange_slabs(self, dim, to_lo, to_hi):
+        """Send `to_lo` to the -dim neighbour and `to_hi` to the +dim one; returns
+        (from_lo, from_hi) = what those neighbours sent to me."""
+        lo, hi = self.nbr[dim]
+        n_lo, n_hi = to_lo.numel(), to_hi.numel()
+        if lo == hi:
+            # one peer on both sides: [payload for its +side | payload for its -side] in one message
+            send = self._buf(("s2", dim), n_lo + n_hi)[:n_lo + n_hi]
+            send[:n_lo].copy_(to_lo)
+            send[n_lo:].copy_(to_hi)
+            recv = self._buf(("r2", dim), n_lo + n_hi)[:n_lo + n_hi]
+            self._sendrecv([(lo, send, recv)])
+            # the peer's first block was meant for its -dim neighbour's +side = my +side
+            return recv[n_lo:], recv[:n_lo]
+        from_lo = self._buf(("rl", dim), n_hi)[:n_hi]   # the -dim neighbour sends me its to_hi block
+        from_hi = self._buf(("rh", dim), n_lo)[:n_lo]
+        self._sendrecv([(lo, to_lo, from_lo), (hi, to_hi, from_hi)])
+        return from_lo, from_hi
+
+    # ------------------------------------------------------------------ J
+    def sum_J(self, fields=J_FIELDS):
+        """Both sides of every shared plane end up holding the sum (SyncVectorPatch.cpp:296-311)."""
+        p = self.patch
+        for dim in range(3):
+            if self.npatch[dim] == 1:
+                for f in fields:
+                    p.halo_sum_self(f, dim)
+                continue
+            sizes, gsp = [], []
+            for f in fields:
+                g = 1 + 2 * self.o[dim] + _DUAL[f][dim]            # SyncVectorPatch.cpp:235-237,284
+                gsp.append(g)
+                sizes.append(g * p.halo_plane_elems(f, dim))
+            tot = sum(sizes)
+            to_lo = self._buf(("jl", dim), tot)[:tot]
+            to_hi = self._buf(("jh", dim), tot)[:tot]
+            off = 0
+            for f, g, s in zip(fields, gsp, sizes):
+                p.halo_pack(f, dim, 0, g, to_lo[off:off + s].data_ptr())            # my planes [0,gsp)
+                p.halo_pack(f, dim, self.n[dim], g, to_hi[off:off + s].data_ptr())  # my planes [n,n+gsp)
+                off += s
+            self._sync_patch_stream()
+            from_lo, from_hi = self._exchange_slabs(dim, to_lo, to_hi)
+            off = 0
+            for f, g, s in zip(fields, gsp, sizes):
+                # the -dim neighbour's [n,n+gsp) planes are my [0,gsp); the +dim one's [0,gsp) are my [n,n+gsp)
+                p.halo_unpack(f, dim, 0, g, from_lo[off:off + s].data_ptr(), UNPACK_ADD)
+                p.halo_unpack(f, dim, self.n[dim], g, from_hi[off:off + s].data_ptr(), UNPACK_ADD)
+                off += s
+
+    # ------------------------------------------------------------------ B
+    def exchange_B(self):
+        """R[0,o) <- L[n,n+o) ; L[n+gsp,n+gsp+o) <- R[gsp,gsp+o), gsp = o+2 (SyncVectorPatch.cpp:1501-1527)."""
+        p = self.patch
+        for dim, comps in B_EXCHANGE:
+            o = self.o[dim]
+            gsp = o + 2
+            if self.npatch[dim] == 1:
+                for f in comps:
+                    p.halo_exchange_self(f, dim)
+                continue
+            sizes = [o * p.halo_plane_elems(f, dim) for f in comps]
+            tot = sum(sizes)
+            to_lo = self._buf(("bl", dim), tot)[:tot]
+            to_hi = self._buf(("bh", dim), tot)[:tot]
+            off = 0
+            for f, s in zip(comps, sizes):
+                p.halo_pack(f, dim, gsp, o, to_lo[off:off + s].data_ptr())           # I am R of my -dim neighbour
+                p.halo_pack(f, dim, self.n[dim], o, to_hi[off:off + s].data_ptr())   # I am L of my +dim neighbour
+                off += s
+            self._sync_patch_stream()
+            from_lo, from_hi = self._exchange_slabs(dim, to_lo, to_hi)
+            off = 0
+            for f, s in zip(comps, sizes):
+                p.halo_unpack(f, dim, 0, o, from_lo[off:off + s].data_ptr(), UNPACK_COPY)
+                p.halo_unpack(f, dim, self.n[dim] + gsp, o, from_hi[off:off + s].data_ptr(), UNPACK_COPY)
+                off += s
+
+    # ------------------------------------------------------------------ particles
+    def exchange_particles(self, n_species):
+        """x, then y, then z; arrivals are re-tagged on unpack so corner particles are forwarded in
+        the next dimension (Patch::cornersParticles)."""
+        p = self.patch
+        for dim in range(3):
+            L = self.cell[dim] * float(self.n[dim] * self.npatch[dim])      # Patch.cpp:626
+            wrap_lo = L if self.pcoord[dim] == 0 else 0.                     # Patch.cpp:636-642
+            wrap_hi = -L if self.pcoord[dim] == self.npatch[dim] - 1 else 0.  # Patch.cpp:643-649
+            for s in range(n_species):
+                counts = p.leaving_count(s)                       # Patch::exchNbrOfParticles: sizes first
+                c_lo, c_hi = counts[2 * dim], counts[2 * dim + 1]
+                if self.npatch[dim] == 1:
+                    self._ensure_pcap(max(c_lo, c_hi))
+                    to_lo = self._buf(("pl", dim), RECORD * self._pcap)
+                    to_hi = self._buf(("ph", dim), RECORD * self._pcap)
+                    k_lo = p.leaving_pack(s, dim, 0, wrap_lo, to_lo.data_ptr(), self._pcap)
+                    k_hi = p.leaving_pack(s, dim, 1, wrap_hi, to_hi.data_ptr(), self._pcap)
+                    assert (k_lo, k_hi) == (c_lo, c_hi), ("leaving counts disagree", k_lo, k_hi, c_lo, c_hi)
+                    p.arriving_unpack(s, to_lo.data_ptr(), k_lo)
+                    p.arriving_unpack(s, to_hi.data_ptr(), k_hi)
+                    continue
+                cnt_lo = torch.tensor([float(c_lo)], dtype=torch.float64, device=self.device)
+                cnt_hi = torch.tensor([float(c_hi)], dtype=torch.float64, device=self.device)
+                r_lo, r_hi = self._exchange_slabs(dim, cnt_lo, cnt_hi)
+                n_from_lo, n_from_hi = int(r_lo.item()), int(r_hi.item())
+                # every message of this (dim, species) round is padded to one size known to both ends
+                pad = max(c_lo, c_hi, n_from_lo, n_from_hi, 1)
+                self._ensure_pcap(pad)
+                to_lo = self._buf(("pl", dim), RECORD * self._pcap)
+                to_hi = self._buf(("ph", dim), RECORD * self._pcap)
+                k_lo = p.leaving_pack(s, dim, 0, wrap_lo, to_lo.data_ptr(), self._pcap)
+                k_hi = p.leaving_pack(s, dim, 1, wrap_hi, to_hi.data_ptr(), self._pcap)
+                assert (k_lo, k_hi) == (c_lo, c_hi), ("leaving counts disagree", k_lo, k_hi, c_lo, c_hi)
+                self._sync_patch_stream()
+                lo, hi = self.nbr[dim]
+                if lo == hi:
+                    from_lo, from_hi = self._exchange_slabs(dim, to_lo[:RECORD * pad], to_hi[:RECORD * pad])
+                else:
+                    # sizes differ per neighbour pair: send what I have, receive what was announced
+                    from_lo = self._buf(("prl", dim), RECORD * max(n_from_lo, 1))[:RECORD * max(n_from_lo, 1)]
+                    from_hi = self._buf(("prh", dim), RECORD * max(n_from_hi, 1))[:RECORD * max(n_from_hi, 1)]
+                    self._sendrecv([(lo, to_lo[:RECORD * max(c_lo, 1)], from_lo),
+                                    (hi, to_hi[:RECORD * max(c_hi, 1)], from_hi)])
+                # arrivals from the -dim neighbour first, then from the +dim one (deterministic order)
+                p.arriving_unpack(s, from_lo.data_ptr(), n_from_lo)
+                p.arriving_unpack(s, from_hi.data_ptr(), n_from_hi)
+                self._sync_patch_stream()
+
+    def _ensure_pcap(self, need):
+        if need > self._pcap:
+            self._pcap = int(need * 1.5) + 16
+
+    def _sync_patch_stream(self):
+        # pack kernels run on the patch's stream; the collective runs on torch's: order them
+        sync = getattr(self.patch, "synchronize", None)
+        if sync is not None:
+            sync()

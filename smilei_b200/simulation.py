@@ -1,0 +1,197 @@
+"""The time loop of the hot path: one patch per GPU, neighbours exchanged through
+smilei_b200.exchange.  Mirrors the call order of the reference driver,
+
+    main loop                     src/Smilei.cpp:483-749
+    VectorPatch::dynamics         src/Patch/VectorPatch.cpp:325-374, 4763-4834
+    VectorPatch::sumDensities     :819
+    VectorPatch::solveMaxwell     :965-1085
+    finalizeExchParticlesAndSort  :435,  SyncVectorPatch.cpp:44-60
+    finalizeSyncAndBCFields       :1144-1180
+
+with the reference's vocabulary (Species, ElectroMagn, patch, smpi).  Everything numerical runs
+in the CUDA library behind the C ABI; this file only sequences calls.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import particles_init
+from .exchange import Exchanger, rank_to_pcoord
+from .operators import InterpolatorFactory, PusherFactory, ProjectorFactory, SolverFactory
+
+
+class Particles:
+    """Handle on the device SoA of one species (the reference's Particles, src/Particles/Particles.h)."""
+
+    def __init__(self, patch, ispec):
+        self.patch = patch
+        self.ispec = ispec
+        self._stage = None
+
+    def numberOfParticles(self):
+        return self.patch.species_count(self.ispec)
+
+
+class Species:
+    """src/Species/Species.h — owns Particles and the three operators (Species::initOperators, Species.cpp:260-307)."""
+
+    def __init__(self, params, sparams, patch, ispec):
+        self.params = params
+        self.name = sparams.name
+        self.mass_ = sparams.mass
+        self.pusher = sparams.pusher
+        self.sparams = sparams
+        self.patch = patch
+        self.ispec = ispec
+        self.particles = Particles(patch, ispec)
+        self.Interp = InterpolatorFactory.create(params, patch)
+        self.Push = PusherFactory.create(params, self)
+        self.Proj = ProjectorFactory.create(params, patch)
+
+    def dynamics(self, EMfields, smpi, diag_flag=False):
+        """Species::dynamics (Species.cpp:524-875): interpolate, push, boundary conditions, project."""
+        n = self.particles.numberOfParticles()
+        istart, iend = 0, n
+        self.Interp.fieldsWrapper(EMfields, self.particles, smpi, istart, iend, 0)          # Species.cpp:591
+        self.Push(self.particles, smpi, 0, n, 0)                                             # Species.cpp:727
+        # partBoundCond->apply (Species.cpp:757) is fused in the kernel
+        self.Proj.currentsAndDensityWrapper(EMfields, self.particles, smpi, istart, iend, 0, diag_flag, False,
+                                            self.ispec)                                      # Species.cpp:782
+
+
+class ElectroMagn:
+    """src/ElectroMagn/ElectroMagn.h — field container of the patch + the two Maxwell solvers."""
+
+    def __init__(self, params, patch):
+        self.patch = patch
+        self.MaxwellAmpereSolver_ = SolverFactory.createMA(params, patch)        # ElectroMagn.cpp:54
+        self.MaxwellFaradaySolver_ = SolverFactory.createMF(params, patch)       # ElectroMagn.cpp:55
+
+    def restartRhoJ(self):
+        self.patch.restart_rhoJ()
+
+    def centerMagneticFields(self):
+        self.patch.center_B()
+
+
+class _Smpi:
+    keep_scratch = False
+
+
+class Simulation:
+    """One rank's share of the run.  `rank_grid` = ranks per dimension (the GPU grid); the global box
+    of the namelist is split evenly, one patch per rank, periodic."""
+
+    def __init__(self, params, rank_grid=(1, 1, 1), rank=0, patch_factory=None, device=None, group=None,
+                 capacity_factor=1.25):
+        params.check_hot_path()
+        self.params = params
+        self.rank_grid = tuple(int(v) for v in rank_grid)
+        self.world = int(np.prod(self.rank_grid))
+        self.rank = rank
+        self.group = group
+        self.pcoord = rank_to_pcoord(rank, self.rank_grid)
+        for d in range(3):
+            if params.global_size[d] % self.rank_grid[d]:
+                raise ValueError(f"global size {params.global_size[d]} not divisible by {self.rank_grid[d]} ranks along dim {d}")
+        self.n = tuple(params.global_size[d] // self.rank_grid[d] for d in range(3))
+        self.capacity_factor = capacity_factor
+        if patch_factory is None:
+            from .capi import Patch
+            dev_index = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+            self.device = torch.device("cuda", dev_index)
+
+            def patch_factory(**kw):
+                return Patch(device=dev_index, **kw)
+        else:
+            self.device = torch.device("cpu") if device is None else torch.device(device)
+        self.patch = patch_factory(n=self.n, cell_length=tuple(params.cell_length), dt=params.timestep,
+                                   interp_order=params.interpolation_order, n_species=len(params.species),
+                                   pcoord=self.pcoord, npatch=self.rank_grid, oversize=tuple(params.oversize))
+        self.EMfields = ElectroMagn(params, self.patch)
+        self.vecSpecies = [Species(params, sp, self.patch, i) for i, sp in enumerate(params.species)]
+        self.smpi = _Smpi()
+        self.exchanger = Exchanger(self.patch, self.n, params.oversize, params.cell_length, self.rank_grid,
+                                   self.pcoord, self.device, group)
+        self.itime = 0
+
+    # ------------------------------------------------------------------ initial state
+    def create_particles(self, seed=None):
+        """ParticleCreator for the species of the namelist (host-side, init time only)."""
+        seed = self.params.random_seed if seed is None else seed
+        created = {}
+        for sp in self.vecSpecies:
+            src = created.get(sp.sparams.position_initialization)
+            arrays = particles_init.create(self.params, sp.sparams, self.n, self.pcoord, seed, self.rank,
+                                           positions=None if src is None else (src["x"], src["y"], src["z"]))
+            created[sp.name] = arrays
+            self.set_particles(sp.ispec, **arrays)
+
+    def set_particles(self, ispec, x, y, z, px, py, pz, w, q, capacity=None):
+        n = len(x)
+        cap = int(max(n * self.capacity_factor, n + 4096)) if capacity is None else capacity
+        self.patch.species_config(ispec, self.vecSpecies[ispec].mass_, self.vecSpecies[ispec].pusher, cap)
+        self.patch.species_set(ispec, x, y, z, px, py, pz, w, q)
+        self.patch.sort(ispec)                       # VectorPatch::initialParticleSorting (VectorPatch.cpp:300-320)
+
+    def init_thermal(self, ppc, density=1.0, temperature=None, seed=0):
+        """Synthetic uniform thermal plasma created on the device (bench / smoke)."""
+        ncell = self.n[0] * self.n[1] * self.n[2]
+        nppc = ppc[0] * ppc[1] * ppc[2]
+        for sp in self.vecSpecies:
+            T = sp.sparams.temperature[0] if temperature is None else temperature
+            self.patch.species_config(sp.ispec, sp.mass_, sp.pusher, int(ncell * nppc * self.capacity_factor) + 4096)
+            q = int(sp.sparams.charge)
+            # same seed for every species: identical positions => rho = 0 at t = 0, no Poisson solve needed
+            self.patch.species_init_thermal(sp.ispec, ppc, density, q, T, seed)
+            self.patch.sort(sp.ispec)
+
+    # ------------------------------------------------------------------ one time step
+    def step(self, diag_flag=False):
+        p = self.patch
+        # ---- VectorPatch::dynamics
+        self.EMfields.restartRhoJ()                                   # VectorPatch.cpp:4779
+        for sp in self.vecSpecies:
+            sp.dynamics(self.EMfields, self.smpi, diag_flag)          # VectorPatch.cpp:4821
+        # ---- initExchParticles .. finalizeExchParticles (Smilei.cpp:528,637)
+        self.exchanger.exchange_particles(len(self.vecSpecies))
+        # ---- sumDensities (Smilei.cpp:531)
+        self.exchanger.sum_J()
+        # ---- solveMaxwell (Smilei.cpp:547): saveMagneticFields, Ampere, Faraday, exchangeB
+        self.EMfields.MaxwellAmpereSolver_(self.EMfields)
+        self.EMfields.MaxwellFaradaySolver_(self.EMfields)
+        self.exchanger.exchange_B()
+        # ---- importAndSortParticles (Smilei.cpp:637)
+        for sp in self.vecSpecies:
+            p.sort(sp.ispec)
+        # ---- finalizeSyncAndBCFields (Smilei.cpp:649): periodic => no BC, centre B
+        self.EMfields.centerMagneticFields()
+        self.itime += 1
+
+    def run(self, n_steps, scalars_every=None):
+        out = []
+        for _ in range(n_steps):
+            self.step()
+            if scalars_every and self.itime % scalars_every == 0:
+                out.append((self.itime,) + self.scalars())
+        return out
+
+    # ------------------------------------------------------------------ diagnostics (parity observable)
+    def scalars(self):
+        """DiagnosticScalar Ukin (per species), Uelm, summed over ranks (SmileiMPI::computeGlobalDiags)."""
+        ukin, uelm = self.patch.energy()
+        v = torch.tensor(list(ukin) + [uelm], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(v, group=self.group)
+        v = v.cpu().numpy()
+        return v[:-1].copy(), float(v[-1])
+
+    def n_particles(self):
+        c = torch.tensor([float(self.patch.species_count(s.ispec)) for s in self.vecSpecies], dtype=torch.float64,
+                         device=self.device)
+        if self.world > 1:
+            dist.all_reduce(c, group=self.group)
+        return [int(x) for x in c.cpu().numpy()]
+
+    def close(self):
+        self.patch.close()

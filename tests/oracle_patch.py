@@ -1,0 +1,194 @@
+"""OraclePatch: the smilei_b200.capi.Patch interface implemented on the CPU with the oracle.
+
+TEST INFRASTRUCTURE ONLY.  It lets the product's host logic (smilei_b200.simulation /
+smilei_b200.exchange: call order, neighbour plan, message layout) run without a GPU — in
+particular under torch.distributed/gloo with several processes — and provides the multi-step
+oracle trajectory the GPU runs are compared with.  Buffers are torch CPU tensors addressed
+by data_ptr(), exactly like the CUDA library addresses device memory.
+"""
+import ctypes as C
+
+import numpy as np
+
+import oracle_lib as ol
+
+RECORD = 8
+
+
+def _view(ptr, n):
+    if n == 0:
+        return np.zeros(0)
+    return np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+
+
+class OraclePatch:
+    def __init__(self, n, cell_length, dt, interp_order=2, n_species=0, pcoord=(0, 0, 0), npatch=(1, 1, 1),
+                 oversize=None, device=0):
+        self.g = ol.make_grid(n, interp_order, cell_length, dt, pcoord, npatch)
+        self.n = tuple(n)
+        self.order = interp_order
+        self.n_species = n_species
+        self.orc = ol.Oracle()
+        self.F = {k: np.zeros(ol.field_dims(self.g, k)) for k in
+                  ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm", "Jx", "Jy", "Jz", "rho")}
+        self.sp = [dict(mass=1., pusher=0, P=None, first=None) for _ in range(n_species)]
+        self.ncells = (n[0] + 1) * (n[1] + 1) * (n[2] + 1)
+        self.mn, self.mx = ol.patch_bounds(self.g)
+
+    def close(self):
+        pass
+
+    def synchronize(self):
+        pass
+
+    # -- species
+    def species_config(self, ispec, mass, pusher, capacity):
+        from smilei_b200.capi import PUSHERS
+        self.sp[ispec]["mass"] = mass
+        self.sp[ispec]["pusher"] = PUSHERS[pusher] if isinstance(pusher, str) else int(pusher)
+
+    def species_set(self, ispec, x, y, z, px, py, pz, w, q):
+        P = dict(x=x, y=y, z=z, px=px, py=py, pz=pz, w=w)
+        P = {k: np.ascontiguousarray(v, dtype=np.float64).copy() for k, v in P.items()}
+        P["q"] = np.ascontiguousarray(q, dtype=np.int16).copy()
+        P["key"] = np.zeros(len(x), dtype=np.int32)
+        self.sp[ispec]["P"] = P
+        self.sp[ispec]["sorted"] = False
+
+    def species_count(self, ispec):
+        P = self.sp[ispec]["P"]
+        return 0 if P is None else len(P["x"])
+
+    def species_get(self, ispec):
+        return {k: v.copy() for k, v in self.sp[ispec]["P"].items()}
+
+    def first_index(self, ispec):
+        return self.sp[ispec]["first"].copy()
+
+    # -- fields
+    def field_dims(self, name):
+        return self.F[name].shape
+
+    def field_set(self, name, a):
+        self.F[name][...] = a
+
+    def field_get(self, name):
+        return self.F[name].copy()
+
+    # -- time step
+    def restart_rhoJ(self):
+        for k in ("Jx", "Jy", "Jz", "rho"):
+            self.F[k][...] = 0.
+
+    def dynamics(self, ispec, flags=0):
+        s = self.sp[ispec]
+        P = s["P"]
+        if P is None or len(P["x"]) == 0:
+            return
+        g, o = self.g, self.orc
+        E, B, iold, delta = o.interp(g, self.order, self.F, P["x"], P["y"], P["z"])
+        o.push(g, s["pusher"], s["mass"], P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["q"], E, B)
+        tags = o.bc_tag(g, P["x"], P["y"], P["z"])
+        o.project(g, self.order, self.F, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+        keys = tags.copy()
+        o.cell_keys(g, P["x"], P["y"], P["z"], keys=keys)
+        P["key"] = keys
+
+    def maxwell(self):
+        self.orc.save_B(self.g, self.F)
+        self.orc.maxwell_ampere(self.g, self.F)
+        self.orc.maxwell_faraday(self.g, self.F)
+
+    def center_B(self):
+        self.orc.center_B(self.g, self.F)
+
+    def sort(self, ispec):
+        s = self.sp[ispec]
+        P = s["P"]
+        if P is None:
+            s["first"] = np.zeros(self.ncells + 1, dtype=np.int32)
+            return
+        if not s.get("sorted", False):
+            keys = P["key"].copy()
+            keys[keys >= 0] = 0
+            self.orc.cell_keys(self.g, P["x"], P["y"], P["z"], keys=keys)
+            P["key"] = keys
+        first, perm = self.orc.counting_sort_perm(P["key"], self.ncells)
+        s["P"] = {k: np.ascontiguousarray(v[perm]) for k, v in P.items()}
+        s["first"] = first
+        s["sorted"] = True
+
+    def energy(self):
+        uk = np.array([0. if s["P"] is None else self.orc.ukin(s["mass"], s["P"]["px"], s["P"]["py"], s["P"]["pz"],
+                                                                 s["P"]["w"]) for s in self.sp])
+        return uk, self.orc.uelm(self.g, self.F)
+
+    # -- halos
+    def halo_plane_elems(self, name, dim):
+        d = self.F[name].shape
+        return int(np.prod([d[i] for i in range(3) if i != dim]))
+
+    def _slab(self, name, dim, first, npl):
+        sl = [slice(None)] * 3
+        sl[dim] = slice(first, first + npl)
+        return tuple(sl)
+
+    def halo_pack(self, name, dim, first_plane, nplanes, ptr):
+        a = np.moveaxis(self.F[name][self._slab(name, dim, first_plane, nplanes)], dim, 0)
+        _view(ptr, a.size)[:] = a.reshape(-1)
+
+    def halo_unpack(self, name, dim, first_plane, nplanes, ptr, mode):
+        sl = self._slab(name, dim, first_plane, nplanes)
+        shape = np.moveaxis(self.F[name][sl], dim, 0).shape
+        a = np.moveaxis(_view(ptr, int(np.prod(shape))).reshape(shape), 0, dim)
+        if mode == 1:
+            self.F[name][sl] += a
+        else:
+            self.F[name][sl] = a
+
+    def halo_sum_self(self, name, dim):
+        self.orc.sum_pair(self.g, dim, name, self.F[name], self.F[name])
+
+    def halo_exchange_self(self, name, dim):
+        self.orc.exchange_pair(self.g, dim, name, self.F[name], self.F[name])
+
+    # -- particles
+    def leaving_count(self, ispec):
+        P = self.sp[ispec]["P"]
+        if P is None:
+            return [0] * 6
+        return [int((P["key"] == -2 - t).sum()) for t in range(6)]
+
+    def leaving_pack(self, ispec, dim, side, wrap, ptr, max_records):
+        P = self.sp[ispec]["P"]
+        if P is None:
+            return 0
+        idx = np.flatnonzero(P["key"] == -2 - 2 * dim - side)
+        k = len(idx)
+        assert k <= max_records
+        rec = np.empty((k, RECORD))
+        for c, name in enumerate(("x", "y", "z", "px", "py", "pz", "w")):
+            rec[:, c] = P[name][idx]
+        rec[:, 7] = P["q"][idx]
+        hi = self.g.cell[dim] * float(self.g.n[dim] * self.g.npatch[dim])
+        if wrap > 0:
+            m = rec[:, dim] < 0.
+            rec[m, dim] += wrap
+        elif wrap < 0:
+            m = rec[:, dim] >= hi
+            rec[m, dim] += wrap
+        _view(ptr, k * RECORD)[:] = rec.reshape(-1)
+        return k
+
+    def arriving_unpack(self, ispec, ptr, n):
+        if n == 0:
+            return
+        rec = _view(ptr, n * RECORD).reshape(n, RECORD).copy()
+        P = self.sp[ispec]["P"]
+        x, y, z = (np.ascontiguousarray(rec[:, c]) for c in range(3))
+        keys = self.orc.bc_tag(self.g, x, y, z)
+        self.orc.cell_keys(self.g, x, y, z, keys=keys)
+        for c, name in enumerate(("x", "y", "z", "px", "py", "pz", "w")):
+            P[name] = np.concatenate([P[name], rec[:, c]])
+        P["q"] = np.concatenate([P["q"], rec[:, 7].astype(np.int16)])
+        P["key"] = np.concatenate([P["key"], keys])

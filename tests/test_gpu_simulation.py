@@ -1,0 +1,128 @@
+"""Multi-step parity on the GPU: the product's Simulation on the CUDA library against the same
+Simulation on the oracle-backed patch, same namelist, same initial arrays.
+
+Per-step energy diagnostics (DiagnosticScalar Ukin, Uelm) must agree to the north_star's
+tolerances: <= 1e-12 relative per step for push/FDTD, <= 1e-10 for deposition (J, hence E).
+Over several steps the two trajectories accumulate rounding differences (FMA contraction and
+atomic summation order on the GPU), so the bound applied to step k is k times the per-step one.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from oracle_patch import OraclePatch
+from test_host_logic import make_params, _global_state
+
+pytestmark = pytest.mark.gpu
+
+
+def run(params, patch_factory, n, steps, seed):
+    from smilei_b200.simulation import Simulation
+    sim = Simulation(params, patch_factory=patch_factory)
+    state = _global_state(n, seed)
+    for sp in sim.vecSpecies:
+        sim.set_particles(sp.ispec, **state[sp.name])
+    hist = [(0,) + sim.scalars()]
+    hist += sim.run(steps, scalars_every=1)
+    parts = [sim.patch.species_get(s.ispec) for s in sim.vecSpecies]
+    fields = {k: sim.patch.field_get(k) for k in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Jx", "Jy", "Jz")}
+    counts = sim.n_particles()
+    sim.close()
+    return hist, parts, fields, counts
+
+
+@pytest.mark.parametrize("order,pusher", [(2, "boris"), (2, "vay"), (4, "higueracary"), (4, "boris")])
+def test_periodic_box_steps_match_oracle(order, pusher):
+    n = (12, 12, 12)
+    steps = 8
+    params = make_params(order=order, n=n, pusher=pusher)
+    hg, pg, fg, cg = run(params, None, n, steps, 11)
+    ho, po, fo, co = run(params, OraclePatch, n, steps, 11)
+    assert cg == co == [12 ** 3 * 6] * 2
+    for k, (a, b) in enumerate(zip(hg, ho)):
+        assert a[0] == b[0]
+        scale = max(k, 1)
+        assert np.allclose(a[1], b[1], rtol=1e-12 * scale, atol=0), (k, a[1], b[1])          # Ukin per species
+        assert abs(a[2] - b[2]) <= 1e-10 * scale * max(abs(b[2]), 1e-300), (k, a[2], b[2])  # Uelm
+    for name in fg:
+        s = np.max(np.abs(fo[name]))
+        assert np.max(np.abs(fg[name] - fo[name])) <= 1e-10 * steps * s, name
+    # same particles in the same canonical order (sort permutation bit-exact unless a 1-ulp position
+    # difference moved a particle across a cell boundary; compare as sets then)
+    for a, b in zip(pg, po):
+        ia = np.lexsort((a["pz"], a["py"], a["px"]))
+        ib = np.lexsort((b["pz"], b["py"], b["px"]))
+        for k in ("x", "y", "z", "px", "py", "pz"):
+            assert np.allclose(a[k][ia], b[k][ib], rtol=0, atol=1e-11), k
+        assert np.mean(a["key"] != b["key"]) < 1e-3
+
+
+def test_energy_conservation_thermal_plasma():
+    """tst3d-like thermal plasma for 60 steps: Utot drifts by less than the reference's validation
+    tolerance on Utot/avg(Utot) (validate_tst3d_v_o2_thermal_plasma_short.py: 1e-3)."""
+    from smilei_b200.simulation import Simulation
+    n = (16, 16, 16)
+    params = make_params(order=2, n=n)
+    sim = Simulation(params)
+    sim.create_particles(seed=3)
+    uk, ue = sim.scalars()
+    tot0 = uk.sum() + ue
+    hist = sim.run(60, scalars_every=10)
+    tot = np.array([h[1].sum() + h[2] for h in hist])
+    assert np.all(np.abs(tot / tot0 - 1.) < 1e-3), tot / tot0
+    assert sim.n_particles() == [16 ** 3 * 8] * 2
+    sim.close()
+
+
+def _nccl_rank(rank, world, rank_grid, n, steps, port, ret):
+    import torch
+    import torch.distributed as dist
+    from smilei_b200.simulation import Simulation
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    params = make_params(n=n)
+    sim = Simulation(params, rank_grid=rank_grid, rank=rank)
+    state = _global_state(n, 5)
+    g = ol.make_grid(sim.n, 2, params.cell_length, params.timestep, sim.pcoord, rank_grid)
+    mn, mx = ol.patch_bounds(g)
+    for sp in sim.vecSpecies:
+        a = state[sp.name]
+        inside = np.ones(len(a["x"]), bool)
+        for d, c in enumerate("xyz"):
+            inside &= (a[c] >= mn[d]) & (a[c] < mx[d])
+        sim.set_particles(sp.ispec, **{k: v[inside] for k, v in a.items()})
+    hist = sim.run(steps, scalars_every=1)
+    parts = [sim.patch.species_get(s.ispec) for s in sim.vecSpecies]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, parts)
+    if rank == 0:
+        ret["hist"] = [(h[0], h[1].tolist(), h[2]) for h in hist]
+        ret["parts"] = gathered
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rank_grid", [(2, 1, 1), (1, 1, 2)])
+def test_two_gpus_nccl_match_oracle_single_rank(rank_grid):
+    import torch
+    import torch.multiprocessing as mp
+    from test_host_logic import _launch, _free_port, _canonical
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, steps = (12, 12, 12), 6
+    ref = _launch((1, 1, 1), n, steps)                  # oracle, one rank
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_nccl_rank, args=(2, rank_grid, n, steps, _free_port(), ret), nprocs=2, join=True)
+    two = dict(ret)
+    for k, ((it_a, uk_a, ue_a), (it_b, uk_b, ue_b)) in enumerate(zip(ref["hist"], two["hist"])):
+        assert it_a == it_b
+        assert np.allclose(uk_a, uk_b, rtol=1e-12 * (k + 1), atol=0)
+        assert abs(ue_a - ue_b) <= 1e-10 * (k + 1) * abs(ue_a)
+    for ispec in range(2):
+        a = _canonical(ref["parts"], ispec)
+        b = _canonical(two["parts"], ispec)
+        assert len(a["x"]) == len(b["x"])
+        for k in a:
+            assert np.allclose(a[k], b[k], rtol=0, atol=1e-11), k

@@ -1,0 +1,206 @@
+"""CPU tests of the host logic: namelist layer, operator factories, time-loop ordering and the
+exchange layer under torch.distributed/gloo with 2 processes.  The numerical back end is the
+oracle-backed OraclePatch (tests/oracle_patch.py) — the same Patch interface the CUDA library
+implements — so what is tested here is the PRODUCT's sequencing and message plan."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_lib as ol
+from oracle_patch import OraclePatch
+from smilei_b200 import namelist, operators
+from smilei_b200.capi import SmileiB200Error
+from smilei_b200.simulation import Simulation
+
+NAMELIST = """
+import math
+T = 10./511.
+dx = 0.5*math.sqrt(T)
+Main(geometry="3Dcartesian", interpolation_order={order}, timestep=0.95*dx/math.sqrt(3.),
+     simulation_time=20*0.95*dx/math.sqrt(3.), cell_length=[dx,dx,dx], grid_length=[{nx}*dx,{ny}*dx,{nz}*dx],
+     number_of_patches=[1,1,1], EM_boundary_conditions=[["periodic"]], print_every=1)
+Species(name="proton", position_initialization="regular", momentum_initialization="mj", particles_per_cell=8,
+        mass=1836.0, charge=1.0, charge_density=1., temperature=[T], pusher="{pusher}",
+        boundary_conditions=[["periodic","periodic"]]*3)
+Species(name="electron", position_initialization="proton", momentum_initialization="mj", particles_per_cell=8,
+        mass=1.0, charge=-1.0, charge_density=1., temperature=[T], pusher="{pusher}",
+        boundary_conditions=[["periodic","periodic"]]*3)
+DiagScalar(every=1)
+LoadBalancing(every=20)
+"""
+
+
+def make_params(order=2, n=(12, 12, 12), pusher="boris"):
+    return namelist.load_namelist(NAMELIST.format(order=order, nx=n[0], ny=n[1], nz=n[2], pusher=pusher), is_source=True)
+
+
+def test_namelist_derived_quantities():
+    p = make_params()
+    T = 10. / 511.
+    dx = 0.5 * T ** 0.5
+    assert p.global_size == [12, 12, 12] and p.oversize == [2, 2, 2]
+    assert p.timestep == 0.95 * dx / 3 ** 0.5
+    assert p.n_time == int((20 * 0.95 * dx / 3 ** 0.5) / p.timestep)
+    assert [s.name for s in p.species] == ["proton", "electron"]
+    assert p.species[0].mass == 1836. and p.species[1].pusher == "boris"
+    assert p.cell_volume == 1.0 * dx * dx * dx
+    assert make_params(order=4).oversize == [4, 4, 4]
+    p.check_hot_path()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/benchmarks"), reason="reference namelists not present")
+@pytest.mark.parametrize("path,order,nspec,n_time,size", [
+    ("benchmarks/tst3d_01_thermal_plasma.py", 2, 2, 163, 32),
+    ("benchmarks/gpu/tst3d_v_o2_thermal_plasma_short.py", 2, 2, 2001, 32),
+    ("benchmarks/tst3d_v_o4_thermal_plasma.py", 4, 2, None, 40),
+])
+def test_reference_namelists_load_unmodified(path, order, nspec, n_time, size):
+    p = namelist.load_namelist(os.path.join("/root/reference", path))
+    assert p.interpolation_order == order and len(p.species) == nspec
+    assert p.global_size == [size] * 3 and p.number_of_patches == [4, 4, 4]
+    if n_time is not None:
+        assert p.n_time == n_time          # 163 steps for tst3d_01
+    p.check_hot_path()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/benchmarks"), reason="reference namelists not present")
+def test_out_of_scope_namelist_is_rejected_loudly():
+    p = namelist.load_namelist("/root/reference/benchmarks/tst3d_s_o2_laser_wake_yee_vay.py")
+    with pytest.raises(namelist.NamelistError):
+        p.check_hot_path()         # moving window / lasers / Silver-Muller are 'next' rows, not silently ignored
+
+
+def test_factories_follow_the_reference_surface():
+    p = make_params(order=4, pusher="vay")
+    sim = Simulation(p, patch_factory=OraclePatch)
+    sp = sim.vecSpecies[0]
+    assert isinstance(sp.Interp, operators.Interpolator3D4Order)
+    assert isinstance(sp.Push, operators.PusherVay)
+    assert isinstance(sp.Proj, operators.Projector3D4Order)
+    assert isinstance(sim.EMfields.MaxwellAmpereSolver_, operators.MA_Solver3D_norm)
+    assert isinstance(sim.EMfields.MaxwellFaradaySolver_, operators.MF_Solver3D_Yee)
+    # call-order contract of the fused operators
+    with pytest.raises(SmileiB200Error):
+        sp.Push(sp.particles, sim.smpi, 0, 0, 0)
+    with pytest.raises(SmileiB200Error):
+        sim.EMfields.MaxwellFaradaySolver_(sim.EMfields)
+    p.species[0].pusher = "borisnr"
+    with pytest.raises(SmileiB200Error):
+        operators.PusherFactory.create(p, p.species[0])
+
+
+def test_single_rank_loop_conserves_particles_and_energy():
+    p = make_params(n=(12, 12, 12))
+    sim = Simulation(p, patch_factory=OraclePatch)
+    sim.create_particles(seed=1)
+    n0 = sim.n_particles()
+    assert n0 == [12 ** 3 * 8] * 2
+    uk0, ue0 = sim.scalars()
+    assert ue0 == 0.0                      # electrons sit on the protons: rho = 0, no field at t = 0
+    hist = sim.run(10, scalars_every=1)
+    assert sim.n_particles() == n0
+    tot0 = uk0.sum() + ue0
+    tot = np.array([h[1].sum() + h[2] for h in hist])
+    assert np.all(np.abs(tot / tot0 - 1) < 2e-3)      # the reference's own Utot tolerance (validate_tst3d_v_o2_*: 1e-3 on ratios)
+    assert hist[-1][2] > 0
+
+
+def _global_state(n, seed, nper=6):
+    """Explicit arrays (the reference's numpy position/momentum initialisation) for the whole box."""
+    T = 10. / 511.
+    dx = 0.5 * T ** 0.5
+    rng = np.random.default_rng(seed)
+    N = n[0] * n[1] * n[2] * nper
+    pos = [rng.random(N) * n[d] * dx for d in range(3)]
+    out = {}
+    for name, mass, q in (("proton", 1836., 1), ("electron", 1., -1)):
+        s = (T / mass) ** 0.5 * 3.0      # hot: plenty of particles cross patch faces, edges and corners
+        out[name] = dict(x=pos[0].copy(), y=pos[1].copy(), z=pos[2].copy(), px=s * rng.standard_normal(N),
+                         py=s * rng.standard_normal(N), pz=s * rng.standard_normal(N), w=np.full(N, dx ** 3 / nper),
+                         q=np.full(N, q, dtype=np.int16))
+    return out
+
+
+def _run_rank(rank, world, rank_grid, n, steps, port, ret):
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p = make_params(n=n)
+    sim = Simulation(p, rank_grid=rank_grid, rank=rank, patch_factory=OraclePatch)
+    state = _global_state(n, 5)
+    mn, mx = sim.patch.mn, sim.patch.mx
+    for sp in sim.vecSpecies:
+        a = state[sp.name]
+        inside = np.ones(len(a["x"]), bool)
+        for d, c in enumerate("xyz"):
+            inside &= (a[c] >= mn[d]) & (a[c] < mx[d])
+        sim.set_particles(sp.ispec, **{k: v[inside] for k, v in a.items()})
+    hist = sim.run(steps, scalars_every=1)
+    parts = [sim.patch.species_get(s.ispec) for s in sim.vecSpecies]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, parts)
+        sent = sim.exchanger.bytes_sent
+        dist.barrier()
+        dist.destroy_process_group()
+    else:
+        gathered, sent = [parts], 0
+    if rank == 0:
+        ret["hist"] = [(h[0], h[1].tolist(), h[2]) for h in hist]
+        ret["parts"] = gathered
+        ret["sent"] = sent
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _launch(rank_grid, n, steps):
+    world = int(np.prod(rank_grid))
+    if world == 1:
+        ret = {}
+        _run_rank(0, 1, rank_grid, n, steps, 0, ret)
+        return ret
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_run_rank, args=(world, rank_grid, n, steps, _free_port(), ret), nprocs=world, join=True)
+    return dict(ret)
+
+
+def _canonical(parts_per_rank, ispec):
+    cols = {k: np.concatenate([r[ispec][k] for r in parts_per_rank]) for k in ("x", "y", "z", "px", "py", "pz", "w")}
+    order = np.lexsort((cols["pz"], cols["py"], cols["px"]))     # momenta are unique identifiers
+    return {k: v[order] for k, v in cols.items()}
+
+
+@pytest.fixture(scope="module")
+def single_rank_reference():
+    return _launch((1, 1, 1), (12, 12, 12), 6)
+
+
+@pytest.mark.parametrize("rank_grid", [(2, 1, 1), (1, 2, 1), (1, 1, 2)])
+def test_two_ranks_gloo_match_single_rank(single_rank_reference, rank_grid):
+    """world_size-2 run of the product's Simulation + Exchanger == the 1-rank run: same particles
+    (every one of them, wherever it migrated), same energies, up to the rounding of the different J
+    summation order at the shared planes."""
+    ref = single_rank_reference
+    two = _launch(rank_grid, (12, 12, 12), 6)
+    assert two["sent"] > 0
+    for (it_a, uk_a, ue_a), (it_b, uk_b, ue_b) in zip(ref["hist"], two["hist"]):
+        assert it_a == it_b
+        assert np.allclose(uk_a, uk_b, rtol=1e-11, atol=0)
+        assert abs(ue_a - ue_b) <= 1e-9 * abs(ue_a)
+    for ispec in range(2):
+        a = _canonical(ref["parts"], ispec)
+        b = _canonical(two["parts"], ispec)
+        assert len(a["x"]) == len(b["x"]) == 12 ** 3 * 6
+        for k in a:
+            assert np.allclose(a[k], b[k], rtol=0, atol=1e-11), k
