@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — the hot-path benchmark (contract in the task statement, §④).
+
+    python bench.py --gpus N --steps K --warmup W            # this build, N GPUs of one node
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU operators
+
+A "step" is one full PIC time step of the hot path on synthetic uniform thermal plasma:
+restartRhoJ, gather+push+BC+deposit for both species, particle migration, J halo sum, Yee
+(Ampere, Faraday, B centring), B halo, cell sort.  Workload at N=1 = BASELINE.json configs[1]:
+256^3 cells, 16 ppc, 2 species, order 2, Boris, periodic; at N>1 the same box PER GPU on a
+2x1x1 / 2x2x1 / 2x2x2 grid (configs[4], weak scaling).  Inputs are resident in HBM before the
+timed region for `value`; `e2e` repeats the metric through the C ABI with host buffers.
+
+metric = particle pushes/s over the WHOLE step (all species, all ranks); the Yee cell-updates/s
+(the second half of BASELINE.json's metric) and the kernel-only pushes/s are reported beside it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle pushes/s (gather+push+deposit, whole PIC step incl. Yee + sort + exchange)"
+UNIT = "pushes/s"
+T_KEV = 10.
+PPC = (4, 2, 2)
+
+
+def plasma_constants():
+    T = T_KEV / 511.
+    dx = 0.5 * T ** 0.5
+    dt = 0.95 * dx / 3 ** 0.5
+    return T, dx, dt
+
+
+def rank_grid_for(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+def namelist_source(ncell, order, pusher):
+    T, dx, dt = plasma_constants()
+    return f"""
+Main(geometry="3Dcartesian", interpolation_order={order}, timestep={dt!r}, number_of_timesteps=1,
+     cell_length=[{dx!r}]*3, number_of_cells={list(ncell)!r}, number_of_patches=[1,1,1],
+     EM_boundary_conditions=[["periodic"]], gpu_computing=True)
+Species(name="proton", position_initialization="regular", regular_number=[4,2,2], momentum_initialization="mj",
+        particles_per_cell=16, mass=1836.0, charge=1.0, charge_density=1., temperature=[{T!r}], pusher="{pusher}",
+        boundary_conditions=[["periodic","periodic"]]*3)
+Species(name="electron", position_initialization="proton", momentum_initialization="mj",
+        particles_per_cell=16, mass=1.0, charge=-1.0, charge_density=1., temperature=[{T!r}], pusher="{pusher}",
+        boundary_conditions=[["periodic","periodic"]]*3)
+"""
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's OWN operator classes on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(order, pusher_id, steps, warmup, target_seconds=12.):
+    """Times Species::dynamics' operator chain (Interpolator3D2Order, PusherBoris, internal_inf/sup,
+    Projector3D2Order) + solveMaxwell (saveMagneticFields, MA_Solver3D_norm, MF_Solver3D_Yee,
+    centerMagneticFields) from oracle/_ref on patches of 16^3 cells x 16 ppc x 2 species, one OpenMP thread
+    per patch (the reference's own patch parallelism), all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib as ol
+    if not ol.have_ref():
+        return None
+    ref = ol.Reference(fast=True)
+    T, dx, dt = plasma_constants()
+    n = (16, 16, 16)
+    g = ol.make_grid(n, order, (dx, dx, dx), dt)
+    rng = np.random.default_rng(0)
+    F = ol.random_fields(g, rng, scale=1e-3)
+    cores = os.cpu_count() or 1
+    npatch = cores
+    nper = 16 ** 3 * 16
+    parts = []
+    for mass, q in ((1836., 1), (1., -1)):
+        P = ol.random_particles(g, rng, nper, p_scale=(T / mass) ** 0.5, charge=q)
+        P["w"][:] = dx ** 3 / 16.
+        parts.append((mass, P))
+
+    def one(nsteps):
+        t = 0.
+        for mass, P in parts:
+            tt, _ = ref.time_dynamics(g, order, pusher_id, mass, F, P, npatch, nsteps, cores)
+            t += tt
+        t += ref.time_maxwell(g, npatch, nsteps, cores)
+        return t
+    one(1)                                   # warm-up (page faults, OpenMP team)
+    t1 = one(1)
+    per_call = max(1, min(50, int(target_seconds / max(t1, 1e-3) / max(steps, 1))))
+    for _ in range(max(warmup - 1, 0)):
+        one(1)
+    times = [one(per_call) / per_call for _ in range(steps)]
+    t_step = sum(times) / len(times)
+    pushes = 2 * nper * npatch
+    return {"value": pushes / t_step, "t_step": t_step, "cores": cores, "kind": "reference",
+            "lib": os.path.basename(ref.path),
+            "sample": f"{npatch} patches of 16^3 cells x 16 ppc x 2 species ({pushes} particles/step), reference "
+                      f"operators (oracle/_ref, -O3 -march=native) over gather+push+BC+deposit+Yee, {per_call} "
+                      f"steps per timing, sort and exchange not included"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(2, 0, args.steps, args.warmup)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsmilei_ref.so not built"}))
+        return
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["t_step"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic 3D thermal plasma, 16 ppc, 2 species, order 2, Boris (bounded CPU sample of configs[1])",
+                       "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ncell", type=int, default=256, help="cells per dimension PER GPU")
+    ap.add_argument("--order", type=int, default=2)
+    ap.add_argument("--pusher", default="boris")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from smilei_b200 import capi, namelist
+    from smilei_b200.simulation import Simulation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    grid = rank_grid_for(world)
+    nloc = args.ncell
+    gsize = [nloc * g for g in grid]
+    params = namelist.load_namelist(namelist_source(gsize, args.order, args.pusher), is_source=True)
+    sim = Simulation(params, rank_grid=grid, rank=rank, device=f"cuda:{local}", capacity_factor=1.08)
+    T, dx, dt = plasma_constants()
+    sim.init_thermal(PPC, density=1.0, temperature=T, seed=0)
+    torch.cuda.synchronize()
+    npart_local = sum(sim.patch.species_count(s) for s in range(2))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sim.step()
+    barrier()
+
+    # ---- timed region: EXACTLY K steps, device events, phase events for the roofline of the top kernel
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
+    dyn_ev, mw_ev = [], []
+    p = sim.patch
+    launches0 = capi.launch_count()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        # the same call sequence as Simulation.step(), with events around the two hot kernels
+        sim.EMfields.restartRhoJ()
+        for sp in sim.vecSpecies:
+            a, b = ev(), ev()
+            a.record()
+            sp.dynamics(sim.EMfields, sim.smpi)
+            b.record()
+            dyn_ev.append((a, b))
+        sim.exchanger.exchange_particles(2)
+        sim.exchanger.sum_J()
+        a, b = ev(), ev()
+        a.record()
+        sim.EMfields.MaxwellAmpereSolver_(sim.EMfields)
+        sim.EMfields.MaxwellFaradaySolver_(sim.EMfields)
+        b.record()
+        mw_ev.append((a, b))
+        sim.exchanger.exchange_B()
+        for sp in sim.vecSpecies:
+            p.sort(sp.ispec)
+        sim.EMfields.centerMagneticFields()
+        sim.itime += 1
+    e1.record()
+    barrier()
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(npart_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms = float(t.item())
+    npart = float(tot.item())
+    ms_per_step = ms / args.steps
+    value = npart * args.steps / (ms * 1e-3)
+    dyn_ms = sum(a.elapsed_time(b) for a, b in dyn_ev) / len(dyn_ev)          # per launch (one species)
+    mw_ms = sum(a.elapsed_time(b) for a, b in mw_ev) / len(mw_ev)
+    ncell_local = nloc ** 3
+    # algorithmic bytes of one k_dynamics launch: 110 B per particle
+    # (read 7 doubles + 1 short, write 6 doubles + 1 int) + 96 B per cell (6 field reads + 3 J read-modify-writes)
+    dyn_bytes = 110. * (npart_local / 2.) + 96. * ncell_local
+    peak, peak_src = measured_peak()
+    achieved = dyn_bytes / (dyn_ms * 1e-3) / 1e9
+    uk, ue = sim.scalars()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic 3D thermal plasma {nloc}^3 cells per GPU, 16 ppc, 2 species, order {args.order}, "
+                               f"{args.pusher}, periodic, rank grid {grid[0]}x{grid[1]}x{grid[2]} (BASELINE.json configs[1]/[4])",
+                   "cells_per_gpu": ncell_local, "particles_total": int(npart), "T_keV": T_KEV, "dx": dx, "dt": dt,
+                   "l2": "inputs larger than L2 (SoA columns of 2.1 GB each, fields 150 MB each; no flush needed)"},
+        "pushes_per_s_dynamics_kernel": (npart_local / 2.) / (dyn_ms * 1e-3) * world,
+        "yee_cell_updates_per_s": ncell_local / (mw_ms * 1e-3) * world,
+        "yee_roofline_frac": (192. * ncell_local / (mw_ms * 1e-3) / 1e9) / peak,
+        "roofline": {"bound": "hbm", "kernel": "k_dynamics (gather+push+BC+deposit, one species)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dyn_bytes, "ms_per_launch": dyn_ms,
+                     "note": "FP64-pipe / shared-memory bound, not HBM bound: see DESIGN.md §6 and profiles/"},
+        "energies": {"Ukin": [float(v) for v in uk], "Uelm": ue},
+        "gpu_launches": int(launches),
+    }
+    if clocks is not None:
+        line["clocks"] = clocks
+
+    # ---- e2e: the same step through the C ABI with HOST buffers, H2D of the inputs and D2H of the
+    #      step's result (energy scalars) inside the timed region
+    if not args.no_e2e:
+        line["e2e"] = e2e_run(sim, args, world, rank, npart, barrier)
+    # ---- CPU baseline on rank 0 at N=1
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args.order, capi.PUSHERS[args.pusher], 3, 1, target_seconds=10.)
+        if r is not None:
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                    "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def e2e_run(sim, args, world, rank, npart, barrier):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    p = sim.patch
+    host = []
+    pinned = True
+    for s in range(2):
+        cols = p.species_get(s)                      # D2H once, outside the timed region
+        cols.pop("key")
+        if pinned:
+            try:
+                pin = {}
+                for k, v in cols.items():
+                    t = torch.empty(v.shape, dtype=torch.float64 if v.dtype == np.float64 else torch.int16, pin_memory=True)
+                    t.numpy()[...] = v
+                    pin[k] = t
+                cols = {k: t.numpy() for k, t in pin.items()}
+                host.append((cols, pin))
+                continue
+            except Exception:
+                pinned = False
+        host.append((cols, None))
+    h2d = sum(v.nbytes for cols, _ in host for v in cols.values())
+    d2h = 8 * 3
+
+    def step():
+        for s, (c, _) in enumerate(host):
+            p.species_set(s, c["x"], c["y"], c["z"], c["px"], c["py"], c["pz"], c["w"], c["q"])    # H2D (host buffers)
+            p.sort(s)
+        sim.step()
+        return sim.patch.energy()                                                                   # D2H of the step's result
+    step()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)   # host-side copies count: the slower of device and wall clock
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"value": npart * args.e2e_steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "pinned_host_memory": pinned,
+            "what": "per step: sb200_species_set of every SoA column from host memory (H2D), sb200_sort, the full "
+                    "PIC step, sb200_energy (D2H)"}
+
+
+if __name__ == "__main__":
+    main()

@@ -181,6 +181,8 @@ int  sb200_species_init_thermal( sb200_patch *p, int ispec, const int ppc[3], do
 /* HOST int[8] counters, cleared by sb200_sort: [0] particles outside the patch without a tag at
  * sort time, [1] particles found outside the cell their sort key says during sb200_dynamics. */
 int  sb200_debug_flags( sb200_patch *p, int flags[8] );
+/* number of CUDA kernels this library has launched since it was loaded (HOST output). */
+int  sb200_launch_count( unsigned long long *n );
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ SYMBOLS = (
     "sb200_dynamics", "sb200_scratch_get", "sb200_maxwell", "sb200_center_B", "sb200_sort", "sb200_energy",
     "sb200_halo_plane_elems", "sb200_halo_pack", "sb200_halo_unpack", "sb200_halo_sum_self",
     "sb200_halo_exchange_self", "sb200_leaving_count", "sb200_leaving_pack", "sb200_arriving_unpack",
-    "sb200_debug_flags", "sb200_species_init_thermal",
+    "sb200_debug_flags", "sb200_species_init_thermal", "sb200_launch_count",
 )
 
 
@@ -77,6 +77,12 @@ def _p(a, dtype):
 def device_count():
     n = C.c_int(0)
     _check(lib().sb200_device_count(C.byref(n)), "sb200_device_count")
+    return n.value
+
+
+def launch_count():
+    n = C.c_ulonglong(0)
+    _check(lib().sb200_launch_count(C.byref(n)), "sb200_launch_count")
     return n.value
 
 

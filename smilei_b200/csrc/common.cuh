@@ -72,6 +72,7 @@ struct ParticleBuf {               // spare SoA set the sort scatters into, then
 };
 
 void set_error( const std::string &s );
+extern unsigned long long g_launches;   // kernels launched by this library (bench.py: gpu_launches)
 
 #define SB200_CUDA( call ) do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) { \
         sb200::set_error( std::string( #call ) + ": " + cudaGetErrorString( e_ ) + " (" + __FILE__ + ":" + std::to_string( __LINE__ ) + ")" ); \

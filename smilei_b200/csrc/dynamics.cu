@@ -419,6 +419,7 @@ static int launch_one( sb200_patch *p, const DynArgs &a, int ntiles )
     auto kern = k_dynamics<ORDER, PUSHER, SCRATCH>;
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )T::SMEM ) );
     kern<<<ntiles, DYN_THREADS, T::SMEM, p->stream>>>( p->gd, a );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }

@@ -74,8 +74,10 @@ int launch_energy( sb200_patch *p, double *ukin, double *uelm )
         for( int s=0; s<p->nspec; s++ ) {
             SpeciesDev &S = p->sp[s];
             k_ukin<<<RED_BLOCKS, RED_T, 0, p->stream>>>( S.col[3], S.col[4], S.col[5], S.col[6], S.n, partial );
+            sb200::g_launches++;
             SB200_CUDA( cudaGetLastError() );
             k_final<<<1, RED_T, 0, p->stream>>>( partial, RED_BLOCKS, S.mass, res+s );
+            sb200::g_launches++;
             SB200_CUDA( cudaGetLastError() );
         }
     }
@@ -97,8 +99,10 @@ int launch_energy( sb200_patch *p, double *ukin, double *uelm )
                 w.s[i] = istart; w.e[i] = istart+bufsize;
             }
             k_norm2<<<RED_BLOCKS, RED_T, 0, p->stream>>>( p->f[ids[f]], w, g.sx, g.sy, partial );
+            sb200::g_launches++;
             SB200_CUDA( cudaGetLastError() );
             k_final<<<1, RED_T, 0, p->stream>>>( partial, RED_BLOCKS, 0.5*g.cell_volume, res+p->nspec+f );
+            sb200::g_launches++;
             SB200_CUDA( cudaGetLastError() );
         }
     }

@@ -185,6 +185,7 @@ int sb200_halo_pack( sb200_patch *p, int field_id, int dim, int first_plane, int
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( total == 0 ) return 0;
     k_slab_pack<<<nblocks( total ), 256, 0, p->stream>>>( s, p->f[field_id], dev_buf, total );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }
@@ -198,6 +199,7 @@ int sb200_halo_unpack( sb200_patch *p, int field_id, int dim, int first_plane, i
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( total == 0 ) return 0;
     k_slab_unpack<<<nblocks( total ), 256, 0, p->stream>>>( s, p->f[field_id], dev_buf, total, mode == SB200_UNPACK_ADD );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }
@@ -213,6 +215,7 @@ int sb200_halo_sum_self( sb200_patch *p, int field_id, int dim )
     SB200_CUDA( cudaSetDevice( p->device ) );
     const long long stride = dim==0 ? g.sx : dim==1 ? g.sy : 1;
     k_slab_sum_self<<<nblocks( total ), 256, 0, p->stream>>>( s, p->f[field_id], total, ( long long )g.n[dim]*stride );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }
@@ -228,6 +231,7 @@ int sb200_halo_exchange_self( sb200_patch *p, int field_id, int dim )
     SB200_CUDA( cudaSetDevice( p->device ) );
     const long long stride = dim==0 ? g.sx : dim==1 ? g.sy : 1;
     k_slab_exch_self<<<nblocks( total ), 256, 0, p->stream>>>( s, p->f[field_id], total, ( long long )g.n[dim]*stride, ( long long )gsp*stride );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }
@@ -254,6 +258,7 @@ int sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wra
     if( ensure_perm( p, nb + 1 > s.cap ? nb + 1 : s.cap ) ) return 1;
     int *bc = p->perm;             // perm is free between sorts
     k_leave_count<<<( unsigned )nb, CP_T, 0, p->stream>>>( s.key, s.n, tag, bc );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     SB200_CUDA( cudaMemsetAsync( bc+nb, 0, sizeof( int ), p->stream ) );
     if( exclusive_scan_int( p, bc, nb+1 ) ) return 1;
@@ -269,6 +274,7 @@ int sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wra
         const GridDev &g = p->gd;
         const double hi = g.cell[dim]*( double )( g.n[dim]*g.npatch[dim] );   // Patch.cpp:626: cell_length*global_size
         k_leave_write<<<( unsigned )nb, CP_T, 0, p->stream>>>( in, s.key, s.n, tag, dim, wrap, 0., hi, bc, dev_buf, max_records );
+        sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
     }
     *n_packed = ( size_t )total;
@@ -288,6 +294,7 @@ int sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, siz
     out.q = s.q; out.key = s.key;
     const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*8 ? ( n + 255 )/256 : 148*8 );
     k_arrive<<<blocks, 256, 0, p->stream>>>( p->gd, out, s.n, dev_buf, n, p->leave_counts + 8*ispec );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     s.n += n;
     return 0;

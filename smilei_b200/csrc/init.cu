@@ -88,6 +88,7 @@ extern "C" int sb200_species_init_thermal( sb200_patch *p, int ispec, const int 
     const unsigned long long patch_lin = ( ( unsigned long long )g.pcoord[0]*g.npatch[1] + g.pcoord[1] )*g.npatch[2] + g.pcoord[2];
     k_init_thermal<<<148*16, 256, 0, p->stream>>>( g, out, ppc[0], ppc[1], ppc[2], weight, ( short )charge, sigma,
             splitmix64_host_seed( seed, ispec ), patch_lin*n, n );
+            sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     s.n = n;
     s.sorted = false;

@@ -191,9 +191,11 @@ int launch_maxwell( sb200_patch *p )
     const int blocks = 148*8;
     k_ampere<<<blocks, 256, 0, p->stream>>>( p->gd, p->f[SB200_EX], p->f[SB200_EY], p->f[SB200_EZ],
             p->f[SB200_BX], p->f[SB200_BY], p->f[SB200_BZ], p->f[SB200_JX], p->f[SB200_JY], p->f[SB200_JZ] );
+            sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     k_faraday_center<<<blocks, 256, 0, p->stream>>>( p->gd, p->f[SB200_EX], p->f[SB200_EY], p->f[SB200_EZ],
             p->f[SB200_BX], p->f[SB200_BY], p->f[SB200_BZ], p->f[SB200_BXM], p->f[SB200_BYM], p->f[SB200_BZM] );
+            sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }
@@ -202,6 +204,7 @@ int launch_center_shell( sb200_patch *p )
 {
     k_center_shell<<<148*8, 256, 0, p->stream>>>( p->gd, p->f[SB200_BX], p->f[SB200_BY], p->f[SB200_BZ],
             p->f[SB200_BXM], p->f[SB200_BYM], p->f[SB200_BZM] );
+            sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }

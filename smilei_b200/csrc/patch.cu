@@ -9,6 +9,7 @@
 namespace sb200 {
 
 static thread_local std::string g_err;
+unsigned long long g_launches = 0;
 void set_error( const std::string &s ) { g_err = s; }
 
 static void fill_grid( const sb200_grid &g, GridDev &d )
@@ -314,6 +315,7 @@ int sb200_field_set( sb200_patch *p, int field_id, const double *host, size_t n 
     SB200_CUDA( cudaMemcpyAsync( p->stage, host, total*sizeof( double ), cudaMemcpyHostToDevice, p->stream ) );
     SB200_CUDA( cudaMemsetAsync( p->f[field_id], 0, p->falloc*sizeof( double ), p->stream ) );
     k_field_pad<<<1184, 256, 0, p->stream>>>( p->stage, p->f[field_id], d[0], d[1], d[2], p->gd.sx, p->gd.sy, 1 );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     SB200_CUDA( cudaStreamSynchronize( p->stream ) );
     return 0;
@@ -329,6 +331,7 @@ int sb200_field_get( sb200_patch *p, int field_id, double *host, size_t n )
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( ensure_stage( p, total ) ) return 1;
     k_field_pad<<<1184, 256, 0, p->stream>>>( p->stage, p->f[field_id], d[0], d[1], d[2], p->gd.sx, p->gd.sy, 0 );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     SB200_CUDA( cudaMemcpyAsync( host, p->stage, total*sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
     SB200_CUDA( cudaStreamSynchronize( p->stream ) );
@@ -340,6 +343,13 @@ int sb200_field_device_ptr( sb200_patch *p, int field_id, void **dev_ptr, int al
     SB200_CHECK( p && dev_ptr && field_id >= 0 && field_id < SB200_NFIELDS, "sb200_field_device_ptr: bad arguments" );
     *dev_ptr = p->f[field_id];
     if( alloc ) { alloc[0] = p->gd.ax; alloc[1] = p->gd.ay; alloc[2] = p->gd.az; }
+    return 0;
+}
+
+int sb200_launch_count( unsigned long long *n )
+{
+    SB200_CHECK( n, "sb200_launch_count: null pointer" );
+    *n = g_launches;
     return 0;
 }
 

@@ -85,13 +85,16 @@ static int scan_rec( sb200_patch *p, int *data, size_t n, int *ws )
     const size_t nb = ( n + SCAN_B - 1 )/SCAN_B;
     if( nb == 1 ) {
         k_scan_block<<<1, SCAN_T, 0, p->stream>>>( data, nullptr, n );
+        sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
         return 0;
     }
     k_scan_block<<<( unsigned )nb, SCAN_T, 0, p->stream>>>( data, ws, n );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     if( scan_rec( p, ws, nb, ws+nb ) ) return 1;
     k_scan_add<<<( unsigned )nb, SCAN_T, 0, p->stream>>>( data, ws, n );
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }
@@ -170,6 +173,7 @@ int launch_sort( sb200_patch *p, int ispec )
         // freshly imported species (keys all 0, unsorted) gets them computed here
         const int recompute = s.sorted ? 0 : 1;
         k_keys_hist<<<blocks, 256, 0, p->stream>>>( p->gd, s.col[0], s.col[1], s.col[2], s.key, p->count, n, recompute, ncells, p->iflags );
+        sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
     }
     // first = exclusive scan(count) over ncells+1 entries (last = total kept)
@@ -181,8 +185,10 @@ int launch_sort( sb200_patch *p, int ispec )
     if( n > 0 ) {
         const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*16 ? ( n + 255 )/256 : 148*16 );
         k_scatter_idx<<<blocks, 256, 0, p->stream>>>( s.key, s.first, p->cursor, p->perm, n );
+        sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
         k_cell_sort<<<148*16, 128, 0, p->stream>>>( s.first, p->perm, ncells );
+        sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
     }
     SB200_CUDA( cudaStreamSynchronize( p->stream ) );
@@ -193,6 +199,7 @@ int launch_sort( sb200_patch *p, int ispec )
         in.q = s.q; in.key = s.key; out.q = p->spare.q; out.key = p->spare.key;
         const unsigned blocks = ( unsigned )( ( ( size_t )kept + 255 )/256 < 148*16 ? ( ( size_t )kept + 255 )/256 : 148*16 );
         k_gather<<<blocks, 256, 0, p->stream>>>( in, out, p->perm, ( size_t )kept );
+        sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
         // swap the species storage with the spare set
         for( int c=0; c<7; c++ ) { double *t = s.col[c]; s.col[c] = p->spare.col[c]; p->spare.col[c] = t; }
