@@ -17,6 +17,7 @@
 // algorithmic 110 B: read 7 doubles + 1 short, write 6 doubles + 1 int; Epart/Bpart/iold/
 // deltaold/invgf never exist in HBM unless SB200_DYN_KEEP_SCRATCH asks for them.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace sb200 {
 
@@ -175,6 +176,83 @@ __device__ __forceinline__ void place_S1( const double *w, int shift, double *S1
     }
 }
 
+// General Esirkepov deposit of one particle into the tile's J box (any cell crossing):
+// Projector3D2Order::currents (Projector3D2Order.cpp:160-340) / Projector3D4Order::currents
+// (Projector3D4Order.cpp:191-230) in outer-product form: J[i][j][k] += C[i]*W[j][k] with
+// C[i] = -cr * sum_{i'<i} DS[i'] (the reference's running sum over the flux direction).
+template<int ORDER>
+__device__ __forceinline__ void esirkepov_general( double *jb, const double ( &S0 )[3][ORDER+3], const double ( &DS )[3][ORDER+3], const double *cr )
+{
+    using T = Tile<ORDER>;
+    const double third = 1./3.;
+    // Jx: flux along x, weights over (y,z)
+    {
+        double C[T::WD];
+        double run = 0.;
+        C[0] = 0.;
+#pragma unroll
+        for( int i=1; i<T::WD; i++ ) { run -= cr[0]*DS[0][i-1]; C[i] = run; }
+#pragma unroll
+        for( int j=0; j<T::WD; j++ ) {
+#pragma unroll
+            for( int k=0; k<T::WD; k++ ) {
+                const double W = S0[1][j]*S0[2][k] + 0.5*DS[1][j]*S0[2][k] + 0.5*DS[2][k]*S0[1][j] + third*DS[1][j]*DS[2][k];
+                if( W != 0. ) {
+#pragma unroll
+                    for( int i=1; i<T::WD; i++ ) {
+                        const double v = C[i]*W;
+                        if( v != 0. ) atomicAdd( jb + 0*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
+                    }
+                }
+            }
+        }
+    }
+    // Jy: flux along y, weights over (z,x)
+    {
+        double C[T::WD];
+        double run = 0.;
+        C[0] = 0.;
+#pragma unroll
+        for( int j=1; j<T::WD; j++ ) { run -= cr[1]*DS[1][j-1]; C[j] = run; }
+#pragma unroll
+        for( int i=0; i<T::WD; i++ ) {
+#pragma unroll
+            for( int k=0; k<T::WD; k++ ) {
+                const double W = S0[2][k]*S0[0][i] + 0.5*DS[2][k]*S0[0][i] + 0.5*DS[0][i]*S0[2][k] + third*DS[2][k]*DS[0][i];
+                if( W != 0. ) {
+#pragma unroll
+                    for( int j=1; j<T::WD; j++ ) {
+                        const double v = C[j]*W;
+                        if( v != 0. ) atomicAdd( jb + 1*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
+                    }
+                }
+            }
+        }
+    }
+    // Jz: flux along z, weights over (x,y)
+    {
+        double C[T::WD];
+        double run = 0.;
+        C[0] = 0.;
+#pragma unroll
+        for( int k=1; k<T::WD; k++ ) { run -= cr[2]*DS[2][k-1]; C[k] = run; }
+#pragma unroll
+        for( int i=0; i<T::WD; i++ ) {
+#pragma unroll
+            for( int j=0; j<T::WD; j++ ) {
+                const double W = S0[0][i]*S0[1][j] + 0.5*DS[0][i]*S0[1][j] + 0.5*DS[1][j]*S0[0][i] + third*DS[0][i]*DS[1][j];
+                if( W != 0. ) {
+#pragma unroll
+                    for( int k=1; k<T::WD; k++ ) {
+                        const double v = C[k]*W;
+                        if( v != 0. ) atomicAdd( jb + 2*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
+                    }
+                }
+            }
+        }
+    }
+}
+
 template<int ORDER, int PUSHER, bool SCRATCH>
 __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, const DynArgs a )
 {
@@ -231,7 +309,6 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
     for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0.;
     __syncthreads();
 
-    const double third = 1./3.;
     for( int wi = tid; wi < total; wi += DYN_THREADS ) {
         // row of this work item (binary search in row_off)
         int lo = 0, hi = TX*TY;
@@ -327,72 +404,7 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
         const double charge_weight = g.inv_cell_volume*( double )charge*weight;
         const double cr[3] = { charge_weight*g.d_ov_dt[0], charge_weight*g.d_ov_dt[1], charge_weight*g.d_ov_dt[2] };
         double *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
-        // Jx: flux along x, weights over (y,z)
-        {
-            double C[T::WD];
-            double run = 0.;
-            C[0] = 0.;
-#pragma unroll
-            for( int i=1; i<T::WD; i++ ) { run -= cr[0]*DS[0][i-1]; C[i] = run; }
-#pragma unroll
-            for( int j=0; j<T::WD; j++ ) {
-#pragma unroll
-                for( int k=0; k<T::WD; k++ ) {
-                    const double W = S0[1][j]*S0[2][k] + 0.5*DS[1][j]*S0[2][k] + 0.5*DS[2][k]*S0[1][j] + third*DS[1][j]*DS[2][k];
-                    if( W != 0. ) {
-#pragma unroll
-                        for( int i=1; i<T::WD; i++ ) {
-                            const double v = C[i]*W;
-                            if( v != 0. ) atomicAdd( jb + 0*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
-                        }
-                    }
-                }
-            }
-        }
-        // Jy: flux along y, weights over (z,x)
-        {
-            double C[T::WD];
-            double run = 0.;
-            C[0] = 0.;
-#pragma unroll
-            for( int j=1; j<T::WD; j++ ) { run -= cr[1]*DS[1][j-1]; C[j] = run; }
-#pragma unroll
-            for( int i=0; i<T::WD; i++ ) {
-#pragma unroll
-                for( int k=0; k<T::WD; k++ ) {
-                    const double W = S0[2][k]*S0[0][i] + 0.5*DS[2][k]*S0[0][i] + 0.5*DS[0][i]*S0[2][k] + third*DS[2][k]*DS[0][i];
-                    if( W != 0. ) {
-#pragma unroll
-                        for( int j=1; j<T::WD; j++ ) {
-                            const double v = C[j]*W;
-                            if( v != 0. ) atomicAdd( jb + 1*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
-                        }
-                    }
-                }
-            }
-        }
-        // Jz: flux along z, weights over (x,y)
-        {
-            double C[T::WD];
-            double run = 0.;
-            C[0] = 0.;
-#pragma unroll
-            for( int k=1; k<T::WD; k++ ) { run -= cr[2]*DS[2][k-1]; C[k] = run; }
-#pragma unroll
-            for( int i=0; i<T::WD; i++ ) {
-#pragma unroll
-                for( int j=0; j<T::WD; j++ ) {
-                    const double W = S0[0][i]*S0[1][j] + 0.5*DS[0][i]*S0[1][j] + 0.5*DS[1][j]*S0[0][i] + third*DS[0][i]*DS[1][j];
-                    if( W != 0. ) {
-#pragma unroll
-                        for( int k=1; k<T::WD; k++ ) {
-                            const double v = C[k]*W;
-                            if( v != 0. ) atomicAdd( jb + 2*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
-                        }
-                    }
-                }
-            }
-        }
+        esirkepov_general<ORDER>( jb, S0, DS, cr );
     }
     __syncthreads();
 
@@ -440,6 +452,370 @@ static int launch_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int push
     }
 }
 
+// =================================================================================================
+// Order-2 fast kernel.
+//
+// What binds the straightforward kernel above is not HBM: every particle issues ~100 non-zero
+// double atomics on shared memory (compare-and-swap loops on sm_100), all lanes of a warp on the
+// same few addresses because sorted neighbours sit in the same cell.  This kernel removes them
+// from the common case:
+//   * work item = (cell, round): G = 8 consecutive lanes take up to 8 particles OF THE SAME CELL;
+//   * a particle whose primal node does not change during the step (the large majority in a
+//     thermal plasma: |dx| << 1 cell) deposits only on the 3x3x3 nodes around its cell:
+//     2x3x3 values per current component.  They are computed in registers, summed over the
+//     8 lanes with a shuffle transpose-reduction (18 -> 9 -> 5 -> 3 values per lane), and only
+//     the per-cell sums (3 per lane per component) reach the tile's J box in shared memory;
+//   * particles that do change cell are appended to a per-tile list and deposited afterwards by
+//     the general 5-point-window routine, one lane per particle, densely packed.
+// Gather, push, boundary tagging and next-key computation are as in the general kernel.
+// =================================================================================================
+constexpr int GRP = 8;                       // lanes per cell group
+constexpr int NCELL_TILE = TX*TY*TZ;         // 128
+constexpr int XCAP = 640;                    // cell-crossers kept per tile before falling back inline
+
+struct O2Smem {
+    static constexpr int FVOL = Tile<2>::FVOL, JVOL = Tile<2>::JVOL;
+    static constexpr size_t BYTES = ( size_t )( 6*FVOL + 3*JVOL + 3*XCAP )*sizeof( double ) + ( size_t )( 2*XCAP )*sizeof( int );
+};
+
+// one step of the transpose-reduction: N values -> (N+1)/2 values; lanes with `upper` keep the second half
+template<int N>
+__device__ __forceinline__ void xr_step( double *v, int lane_mask, bool upper )
+{
+    constexpr int H = ( N+1 )/2;
+#pragma unroll
+    for( int i=0; i<H; i++ ) {
+        const double a = v[i];
+        const double b = ( i+H < N ) ? v[i+H] : 0.;
+        const double send = upper ? a : b;
+        const double keep = upper ? b : a;
+        v[i] = keep + __shfl_xor_sync( 0xffffffffu, send, lane_mask );
+    }
+}
+
+// 2x3x3 contributions of a non-crossing particle for one current component:
+// flux dimension f, transverse dimensions a (slow) and b (fast).  S0/DS hold the 3 non-zero
+// window entries (window indices 1..3).  C[i] = -cr*sum_{i'<i} DS[i'] is non-zero for i = 2,3 only.
+__device__ __forceinline__ void o2_contrib( double *v, double cr, const double *DSf, const double *S0a, const double *DSa,
+                                            const double *S0b, const double *DSb )
+{
+    const double third = 1./3.;
+    const double C2 = -cr*DSf[0];
+    const double C3 = C2 - cr*DSf[1];
+    double A[3], B[3];
+#pragma unroll
+    for( int k=0; k<3; k++ ) { A[k] = S0b[k] + 0.5*DSb[k]; B[k] = 0.5*S0b[k] + third*DSb[k]; }
+#pragma unroll
+    for( int j=0; j<3; j++ ) {
+#pragma unroll
+        for( int k=0; k<3; k++ ) {
+            const double W = S0a[j]*A[k] + DSa[j]*B[k];
+            v[j*3+k] = C2*W;
+            v[9+j*3+k] = C3*W;
+        }
+    }
+}
+
+template<int PUSHER, bool SCRATCH>
+__global__ void __launch_bounds__( DYN_THREADS ) k_dynamics_o2( const GridDev g, const DynArgs a )
+{
+    using T = Tile<2>;
+    extern __shared__ double smem[];
+    double *sF = smem;
+    double *sJ = smem + 6*T::FVOL;
+    double *xs_d = sJ + 3*T::JVOL;                                   // deltaold of the listed crossers, 3*XCAP
+    int    *xs_ip = reinterpret_cast<int *>( xs_d + 3*XCAP );         // particle index
+    int    *xs_cl = xs_ip + XCAP;                                     // packed cell offset in the tile
+    __shared__ int cell_first[NCELL_TILE];
+    __shared__ int round_off[NCELL_TILE+1];
+    __shared__ int warp_tot[4];
+    __shared__ int xcount;
+
+    const int tid = threadIdx.x;
+    int b = blockIdx.x;
+    const int tz = b % a.tiles[2]; b /= a.tiles[2];
+    const int ty = b % a.tiles[1];
+    const int tx = b / a.tiles[1];
+    const int c0[3] = { tx*TX, ty*TY, tz*TZ };
+
+    // ---- per-cell particle runs and the prefix sum of their rounds
+    if( tid < NCELL_TILE ) {
+        const int lz = tid % TZ, ly = ( tid / TZ ) % TY, lx = tid / ( TZ*TY );
+        const int ix = c0[0]+lx, iy = c0[1]+ly, iz = c0[2]+lz;
+        int beg = 0, cnt = 0;
+        if( ix < g.ncell[0] && iy < g.ncell[1] && iz < g.ncell[2] ) {
+            const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + iz;
+            beg = a.first[cell];
+            cnt = a.first[cell+1] - beg;
+        }
+        cell_first[tid] = beg;
+        const int rounds = ( cnt + GRP - 1 )/GRP;
+        // pack count in the low bits of the round prefix later; first an inclusive warp scan of `rounds`
+        int inc = rounds;
+        const int lane = tid & 31;
+#pragma unroll
+        for( int d=1; d<32; d<<=1 ) { const int u = __shfl_up_sync( 0xffffffffu, inc, d ); if( lane >= d ) inc += u; }
+        if( lane == 31 ) warp_tot[tid >> 5] = inc;
+        round_off[tid+1] = inc;          // warp-local inclusive prefix, fixed up below
+    }
+    if( tid == 0 ) xcount = 0;
+    __syncthreads();
+    if( tid < NCELL_TILE ) {
+        int off = 0;
+        for( int w=0; w<( tid >> 5 ); w++ ) off += warp_tot[w];
+        round_off[tid+1] += off;
+    }
+    if( tid == 0 ) round_off[0] = 0;
+    __syncthreads();
+    const int nrounds = round_off[NCELL_TILE];
+    if( nrounds == 0 ) return;
+
+    // ---- stage the field boxes, clear the J box
+    const int gs[3] = { c0[0] + g.o[0] - T::H, c0[1] + g.o[1] - T::H, c0[2] + g.o[2] - T::H };
+    for( int t = tid; t < 6*T::FVOL; t += DYN_THREADS ) {
+        const int c = t / T::FVOL;
+        int r = t - c*T::FVOL;
+        const int k = r % T::FZ; r /= T::FZ;
+        const int j = r % T::FY;
+        const int i = r / T::FY;
+        const int gi = gs[0]+i, gj = gs[1]+j, gk = gs[2]+k;
+        double v = 0.;
+        if( gi < g.ax && gj < g.ay && gk < g.az ) v = a.F[c][gi*g.sx + gj*g.sy + gk];
+        sF[t] = v;
+    }
+    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0.;
+    __syncthreads();
+
+    // ---- lane geometry of the transpose-reduction: which of the 18 values of a component each of
+    //      this lane's 3 final slots holds, as an offset in the J box relative to the cell base
+    const int gl = tid & ( GRP-1 );
+    const int gid = tid / GRP;
+    const bool up4 = gl & 4, up2 = gl & 2, up1 = gl & 1;
+    int joff[3][3];
+#pragma unroll
+    for( int r=0; r<3; r++ ) {
+        int idx = r;
+        bool ok = true;
+        idx += up1 ? 3 : 0; ok = ok && idx < 5;
+        idx += up2 ? 5 : 0; ok = ok && idx < 9;
+        idx += up4 ? 9 : 0; ok = ok && idx < 18;
+        const int f = idx / 9, aa = ( idx / 3 ) % 3, bb = idx % 3;
+        // Jx: flux i = 2+f, (j,k) = (1+aa, 1+bb);  Jy: flux j = 2+f, (i,k) = (1+aa, 1+bb);  Jz: flux k = 2+f, (i,j) = (1+aa, 1+bb)
+        joff[0][r] = ok ? 0*T::JVOL + ( ( 2+f )*T::JY + ( 1+aa ) )*T::JZ + ( 1+bb ) : -1;
+        joff[1][r] = ok ? 1*T::JVOL + ( ( 1+aa )*T::JY + ( 2+f ) )*T::JZ + ( 1+bb ) : -1;
+        joff[2][r] = ok ? 2*T::JVOL + ( ( 1+aa )*T::JY + ( 1+bb ) )*T::JZ + ( 2+f ) : -1;
+    }
+
+    const int ngroups = DYN_THREADS/GRP;
+    const int niter = ( nrounds + ngroups - 1 )/ngroups;
+    for( int it = 0; it < niter; it++ ) {
+        const int wi = it*ngroups + gid;
+        const bool have = wi < nrounds;
+        // cell of this round: last c with round_off[c] <= wi
+        int lo = 0, hi = NCELL_TILE;
+        while( hi - lo > 1 ) { const int mid = ( lo+hi ) >> 1; if( round_off[mid] <= ( have ? wi : 0 ) ) lo = mid; else hi = mid; }
+        const int cellt = lo;
+        const int cl[3] = { cellt / ( TZ*TY ), ( cellt / TZ ) % TY, cellt % TZ };
+        const int rnd = ( have ? wi : 0 ) - round_off[cellt];
+        int cnt_cell;
+        {
+            const int ix = c0[0]+cl[0], iy = c0[1]+cl[1], iz = c0[2]+cl[2];
+            const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + iz;
+            cnt_cell = have ? a.first[cell+1] - cell_first[cellt] : 0;
+        }
+        const int slot = rnd*GRP + gl;
+        const bool active = have && slot < cnt_cell;
+        const size_t ip = ( size_t )cell_first[cellt] + ( size_t )( active ? slot : 0 );
+
+        double vx[18], vy[18], vz[18];
+        bool fast = false;
+        if( active ) {
+            double pos[3] = { a.col[0][ip], a.col[1][ip], a.col[2][ip] };
+            double px = a.col[3][ip], py = a.col[4][ip], pz = a.col[5][ip];
+            const double weight = a.col[6][ip];
+            const short charge = a.q[ip];
+
+            double cp[3][3], cd[3][3], delta_p[3];
+            int sp[3], sd[3];
+#pragma unroll
+            for( int d=0; d<3; d++ ) {
+                const double pn = pos[d]*g.dxi[d];
+                const int ipn = ( int )round( pn );
+                delta_p[d] = pn - ( double )ipn;
+                Shape<2>::w( delta_p[d], cp[d] );
+                const int idn = ( int )round( pn + 0.5 );
+                const double dd = pn - ( double )idn + 0.5;
+                Shape<2>::w( dd, cd[d] );
+                if( ipn - g.begin[d] - g.o[d] - c0[d] != cl[d] ) atomicAdd( &a.iflags[1], 1 );
+                sp[d] = cl[d] + T::H;
+                sd[d] = sp[d] + ( idn - ipn );
+            }
+            const double Ex = gather<2>( sF+0*T::FVOL, cd[0], cp[1], cp[2], sd[0], sp[1], sp[2] );
+            const double Ey = gather<2>( sF+1*T::FVOL, cp[0], cd[1], cp[2], sp[0], sd[1], sp[2] );
+            const double Ez = gather<2>( sF+2*T::FVOL, cp[0], cp[1], cd[2], sp[0], sp[1], sd[2] );
+            const double Bx = gather<2>( sF+3*T::FVOL, cp[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+            const double By = gather<2>( sF+4*T::FVOL, cd[0], cp[1], cd[2], sd[0], sp[1], sd[2] );
+            const double Bz = gather<2>( sF+5*T::FVOL, cd[0], cd[1], cp[2], sd[0], sd[1], sp[2] );
+
+            const double cmd = ( double )charge*a.one_over_mass*g.dts2;
+            double dxp, dyp, dzp, invgf;
+            push<PUSHER>( cmd, g.dt, px, py, pz, Ex, Ey, Ez, Bx, By, Bz, dxp, dyp, dzp, invgf );
+            const double npos[3] = { pos[0] + dxp, pos[1] + dyp, pos[2] + dzp };
+            a.col[0][ip] = npos[0]; a.col[1][ip] = npos[1]; a.col[2][ip] = npos[2];
+            a.col[3][ip] = px; a.col[4][ip] = py; a.col[5][ip] = pz;
+            if( SCRATCH ) {
+                a.sc_E[0*a.n+ip] = Ex; a.sc_E[1*a.n+ip] = Ey; a.sc_E[2*a.n+ip] = Ez;
+                a.sc_B[0*a.n+ip] = Bx; a.sc_B[1*a.n+ip] = By; a.sc_B[2*a.n+ip] = Bz;
+                a.sc_invgf[ip] = invgf;
+#pragma unroll
+                for( int d=0; d<3; d++ ) {
+                    a.sc_iold[d*a.n+ip] = cl[d] + c0[d] + g.o[d];
+                    a.sc_delta[d*a.n+ip] = delta_p[d];
+                }
+            }
+
+            // new shape factors, tag / next key
+            double w1[3][3];
+            int shift[3], nkey[3], tag = 0;
+#pragma unroll
+            for( int d=0; d<3; d++ ) {
+                const double pn = npos[d]*g.dxi[d];
+                const int ipn = ( int )round( pn );
+                Shape<2>::w( pn - ( double )ipn, w1[d] );
+                shift[d] = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );
+                nkey[d] = ( int )( ( double )ipn - g.min_loc_round[d] );
+                if( tag == 0 ) {
+                    if( npos[d] < g.xmin[d] ) tag = -2 - 2*d;
+                    else if( npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
+                }
+            }
+            int key = tag;
+            if( tag == 0 ) key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2];
+            else atomicAdd( &a.leave_counts[-tag-2], 1 );
+            a.key[ip] = key;
+
+            const double charge_weight = g.inv_cell_volume*( double )charge*weight;
+            const double cr[3] = { charge_weight*g.d_ov_dt[0], charge_weight*g.d_ov_dt[1], charge_weight*g.d_ov_dt[2] };
+            fast = ( shift[0] | shift[1] | shift[2] ) == 0;
+            if( fast ) {
+                double DS[3][3];
+#pragma unroll
+                for( int d=0; d<3; d++ )
+#pragma unroll
+                    for( int s=0; s<3; s++ ) DS[d][s] = w1[d][s] - cp[d][s];
+                o2_contrib( vx, cr[0], DS[0], cp[1], DS[1], cp[2], DS[2] );     // Jx: flux x, (j,k)
+                o2_contrib( vy, cr[1], DS[1], cp[0], DS[0], cp[2], DS[2] );     // Jy: flux y, (i,k)
+                o2_contrib( vz, cr[2], DS[2], cp[0], DS[0], cp[1], DS[1] );     // Jz: flux z, (i,j)
+            } else {
+                const int at = atomicAdd( &xcount, 1 );
+                if( at < XCAP ) {
+                    xs_ip[at] = ( int )ip;
+                    xs_cl[at] = cellt;
+                    xs_d[0*XCAP+at] = delta_p[0]; xs_d[1*XCAP+at] = delta_p[1]; xs_d[2*XCAP+at] = delta_p[2];
+                } else {
+                    // list full (very hot plasma): deposit this one right away with the general routine
+                    double S0[3][5], DS[3][5];
+#pragma unroll
+                    for( int d=0; d<3; d++ ) {
+                        double S1[5];
+                        place_S1<2>( w1[d], shift[d], S1 );
+                        S0[d][0] = 0.; S0[d][4] = 0.;
+#pragma unroll
+                        for( int s=0; s<3; s++ ) S0[d][s+1] = cp[d][s];
+#pragma unroll
+                        for( int s=0; s<5; s++ ) DS[d][s] = S1[s] - S0[d][s];
+                    }
+                    esirkepov_general<2>( sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2], S0, DS, cr );
+                }
+            }
+        }
+        if( !fast ) {
+#pragma unroll
+            for( int i=0; i<18; i++ ) { vx[i] = 0.; vy[i] = 0.; vz[i] = 0.; }
+        }
+        // ---- sum over the 8 lanes of the cell group (all 32 lanes take part in the shuffles)
+        xr_step<18>( vx, 4, up4 ); xr_step<9>( vx, 2, up2 ); xr_step<5>( vx, 1, up1 );
+        xr_step<18>( vy, 4, up4 ); xr_step<9>( vy, 2, up2 ); xr_step<5>( vy, 1, up1 );
+        xr_step<18>( vz, 4, up4 ); xr_step<9>( vz, 2, up2 ); xr_step<5>( vz, 1, up1 );
+        if( have ) {
+            double *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
+#pragma unroll
+            for( int r=0; r<3; r++ ) {
+                if( joff[0][r] >= 0 && vx[r] != 0. ) atomicAdd( jb + joff[0][r], vx[r] );
+                if( joff[1][r] >= 0 && vy[r] != 0. ) atomicAdd( jb + joff[1][r], vy[r] );
+                if( joff[2][r] >= 0 && vz[r] != 0. ) atomicAdd( jb + joff[2][r], vz[r] );
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- cell-crossers: general Esirkepov window, one lane per listed particle
+    const int nx = min( xcount, XCAP );
+    for( int t = tid; t < nx; t += DYN_THREADS ) {
+        const size_t ip = ( size_t )xs_ip[t];
+        const int cellt = xs_cl[t];
+        const int cl[3] = { cellt / ( TZ*TY ), ( cellt / TZ ) % TY, cellt % TZ };
+        const double npos[3] = { a.col[0][ip], a.col[1][ip], a.col[2][ip] };
+        const double weight = a.col[6][ip];
+        const short charge = a.q[ip];
+        double S0[3][5], DS[3][5];
+#pragma unroll
+        for( int d=0; d<3; d++ ) {
+            double w0[3], w1[3], S1[5];
+            Shape<2>::w( xs_d[d*XCAP+t], w0 );
+            const double pn = npos[d]*g.dxi[d];
+            const int ipn = ( int )round( pn );
+            Shape<2>::w( pn - ( double )ipn, w1 );
+            const int shift = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );
+            place_S1<2>( w1, shift, S1 );
+            S0[d][0] = 0.; S0[d][4] = 0.;
+#pragma unroll
+            for( int s=0; s<3; s++ ) S0[d][s+1] = w0[s];
+#pragma unroll
+            for( int s=0; s<5; s++ ) DS[d][s] = S1[s] - S0[d][s];
+        }
+        const double charge_weight = g.inv_cell_volume*( double )charge*weight;
+        const double cr[3] = { charge_weight*g.d_ov_dt[0], charge_weight*g.d_ov_dt[1], charge_weight*g.d_ov_dt[2] };
+        esirkepov_general<2>( sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2], S0, DS, cr );
+    }
+    __syncthreads();
+
+    // ---- flush the J box
+    const int js[3] = { c0[0] + g.o[0] - T::H - 1, c0[1] + g.o[1] - T::H - 1, c0[2] + g.o[2] - T::H - 1 };
+    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) {
+        const double v = sJ[t];
+        if( v == 0. ) continue;
+        const int c = t / T::JVOL;
+        int r = t - c*T::JVOL;
+        const int k = r % T::JZ; r /= T::JZ;
+        const int j = r % T::JY;
+        const int i = r / T::JY;
+        const int gi = js[0]+i, gj = js[1]+j, gk = js[2]+k;
+        if( gi >= 0 && gj >= 0 && gk >= 0 && gi < g.ax && gj < g.ay && gk < g.az )
+            atomicAdd( a.J[c] + gi*g.sx + gj*g.sy + gk, v );
+    }
+}
+
+template<int PUSHER, bool SCRATCH>
+static int launch_o2( sb200_patch *p, const DynArgs &a, int ntiles )
+{
+    auto kern = k_dynamics_o2<PUSHER, SCRATCH>;
+    SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )O2Smem::BYTES ) );
+    kern<<<ntiles, DYN_THREADS, O2Smem::BYTES, p->stream>>>( p->gd, a );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    return 0;
+}
+
+static int launch_o2_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int pusher, bool scratch )
+{
+    switch( pusher ) {
+        case SB200_PUSHER_BORIS: return scratch ? launch_o2<SB200_PUSHER_BORIS, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_BORIS, false>( p, a, ntiles );
+        case SB200_PUSHER_VAY: return scratch ? launch_o2<SB200_PUSHER_VAY, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_VAY, false>( p, a, ntiles );
+        default: return scratch ? launch_o2<SB200_PUSHER_HIGUERACARY, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_HIGUERACARY, false>( p, a, ntiles );
+    }
+}
+
 int launch_dynamics( sb200_patch *p, int ispec, int flags )
 {
     SpeciesDev &s = p->sp[ispec];
@@ -474,7 +850,12 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     a.tiles[1] = ( g.ncell[1] + TY - 1 )/TY;
     a.tiles[2] = ( g.ncell[2] + TZ - 1 )/TZ;
     const int ntiles = a.tiles[0]*a.tiles[1]*a.tiles[2];
-    if( g.order == 2 ) return launch_pusher<2>( p, a, ntiles, s.pusher, scratch );
+    if( g.order == 2 ) {
+        // SB200_DYN_GENERAL=1 selects the general (any-order) kernel for order 2 too: A/B checks only
+        static const bool general = getenv( "SB200_DYN_GENERAL" ) != nullptr;
+        if( !general ) return launch_o2_pusher( p, a, ntiles, s.pusher, scratch );
+        return launch_pusher<2>( p, a, ntiles, s.pusher, scratch );
+    }
     return launch_pusher<4>( p, a, ntiles, s.pusher, scratch );
 }
 
