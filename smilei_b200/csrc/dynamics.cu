@@ -471,11 +471,11 @@ static int launch_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int push
 // =================================================================================================
 constexpr int GRP = 8;                       // lanes per cell group
 constexpr int NCELL_TILE = TX*TY*TZ;         // 128
-constexpr int XCAP = 640;                    // cell-crossers kept per tile before falling back inline
+constexpr int XSCR = 32;                     // doubles of per-warp scratch for the cooperative crosser deposit
 
 struct O2Smem {
     static constexpr int FVOL = Tile<2>::FVOL, JVOL = Tile<2>::JVOL;
-    static constexpr size_t BYTES = ( size_t )( 6*FVOL + 3*JVOL + 3*XCAP )*sizeof( double ) + ( size_t )( 2*XCAP )*sizeof( int );
+    static constexpr size_t BYTES = ( size_t )( 6*FVOL + 3*JVOL + XSCR*( DYN_THREADS/32 ) )*sizeof( double );
 };
 
 // one step of the transpose-reduction: N values -> (N+1)/2 values; lanes with `upper` keep the second half
@@ -517,19 +517,16 @@ __device__ __forceinline__ void o2_contrib( double *v, double cr, const double *
 }
 
 template<int PUSHER, bool SCRATCH>
-__global__ void __launch_bounds__( DYN_THREADS ) k_dynamics_o2( const GridDev g, const DynArgs a )
+__global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev g, const DynArgs a )
 {
     using T = Tile<2>;
     extern __shared__ double smem[];
     double *sF = smem;
     double *sJ = smem + 6*T::FVOL;
-    double *xs_d = sJ + 3*T::JVOL;                                   // deltaold of the listed crossers, 3*XCAP
-    int    *xs_ip = reinterpret_cast<int *>( xs_d + 3*XCAP );         // particle index
-    int    *xs_cl = xs_ip + XCAP;                                     // packed cell offset in the tile
+    double *xscr = sJ + 3*T::JVOL + XSCR*( threadIdx.x >> 5 );       // this warp's S0/DS scratch: [d][0..4] S0, [15+d*5+..] DS
     __shared__ int cell_first[NCELL_TILE];
     __shared__ int round_off[NCELL_TILE+1];
     __shared__ int warp_tot[4];
-    __shared__ int xcount;
 
     const int tid = threadIdx.x;
     int b = blockIdx.x;
@@ -558,7 +555,6 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics_o2( const GridDev g,
         if( lane == 31 ) warp_tot[tid >> 5] = inc;
         round_off[tid+1] = inc;          // warp-local inclusive prefix, fixed up below
     }
-    if( tid == 0 ) xcount = 0;
     __syncthreads();
     if( tid < NCELL_TILE ) {
         int off = 0;
@@ -627,7 +623,7 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics_o2( const GridDev g,
         const bool active = have && slot < cnt_cell;
         const size_t ip = ( size_t )cell_first[cellt] + ( size_t )( active ? slot : 0 );
 
-        double vx[18], vy[18], vz[18];
+        double S0[3][3], DS[3][3], cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
         bool fast = false;
         if( active ) {
             double pos[3] = { a.col[0][ip], a.col[1][ip], a.col[2][ip] };
@@ -695,88 +691,111 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics_o2( const GridDev g,
             a.key[ip] = key;
 
             const double charge_weight = g.inv_cell_volume*( double )charge*weight;
-            const double cr[3] = { charge_weight*g.d_ov_dt[0], charge_weight*g.d_ov_dt[1], charge_weight*g.d_ov_dt[2] };
+            cr[0] = charge_weight*g.d_ov_dt[0]; cr[1] = charge_weight*g.d_ov_dt[1]; cr[2] = charge_weight*g.d_ov_dt[2];
             fast = ( shift[0] | shift[1] | shift[2] ) == 0;
+#pragma unroll
+            for( int d=0; d<3; d++ ) {
+                xdelta[d] = delta_p[d]; xnpos[d] = npos[d]*g.dxi[d];
+#pragma unroll
+                for( int s=0; s<3; s++ ) { S0[d][s] = cp[d][s]; DS[d][s] = w1[d][s] - cp[d][s]; }
+            }
+        }
+        double *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
+        // ---- non-crossing particles: 2x3x3 values per component, summed over the 8 lanes of the cell
+        //      group in registers (all 32 lanes take part in the shuffles), 3 sums per lane reach the J box
+#pragma unroll
+        for( int c=0; c<3; c++ ) {
+            double v[18];
             if( fast ) {
-                double DS[3][3];
-#pragma unroll
-                for( int d=0; d<3; d++ )
-#pragma unroll
-                    for( int s=0; s<3; s++ ) DS[d][s] = w1[d][s] - cp[d][s];
-                o2_contrib( vx, cr[0], DS[0], cp[1], DS[1], cp[2], DS[2] );     // Jx: flux x, (j,k)
-                o2_contrib( vy, cr[1], DS[1], cp[0], DS[0], cp[2], DS[2] );     // Jy: flux y, (i,k)
-                o2_contrib( vz, cr[2], DS[2], cp[0], DS[0], cp[1], DS[1] );     // Jz: flux z, (i,j)
+                if( c == 0 ) o2_contrib( v, cr[0], DS[0], S0[1], DS[1], S0[2], DS[2] );          // Jx: flux x, (j,k)
+                else if( c == 1 ) o2_contrib( v, cr[1], DS[1], S0[0], DS[0], S0[2], DS[2] );     // Jy: flux y, (i,k)
+                else o2_contrib( v, cr[2], DS[2], S0[0], DS[0], S0[1], DS[1] );                  // Jz: flux z, (i,j)
             } else {
-                const int at = atomicAdd( &xcount, 1 );
-                if( at < XCAP ) {
-                    xs_ip[at] = ( int )ip;
-                    xs_cl[at] = cellt;
-                    xs_d[0*XCAP+at] = delta_p[0]; xs_d[1*XCAP+at] = delta_p[1]; xs_d[2*XCAP+at] = delta_p[2];
-                } else {
-                    // list full (very hot plasma): deposit this one right away with the general routine
-                    double S0[3][5], DS[3][5];
 #pragma unroll
-                    for( int d=0; d<3; d++ ) {
-                        double S1[5];
-                        place_S1<2>( w1[d], shift[d], S1 );
-                        S0[d][0] = 0.; S0[d][4] = 0.;
+                for( int i=0; i<18; i++ ) v[i] = 0.;
+            }
+            xr_step<18>( v, 4, up4 ); xr_step<9>( v, 2, up2 ); xr_step<5>( v, 1, up1 );
+            if( have ) {
 #pragma unroll
-                        for( int s=0; s<3; s++ ) S0[d][s+1] = cp[d][s];
+                for( int r=0; r<3; r++ )
+                    if( joff[c][r] >= 0 && v[r] != 0. ) atomicAdd( jb + joff[c][r], v[r] );
+            }
+        }
+        // ---- particles that changed cell: the whole warp deposits them one at a time, lane (a,b) of a
+        //      5x5 face taking the 4 flux points of each component (general window, Projector3D2Order.cpp:160-340)
+        unsigned xmask = __ballot_sync( 0xffffffffu, active && !fast );
+        const int lane = tid & 31;
+        while( xmask ) {
+            const int src = __ffs( xmask ) - 1;
+            xmask &= xmask - 1;
+            double bd[3], bn[3], bc[3];
 #pragma unroll
-                        for( int s=0; s<5; s++ ) DS[d][s] = S1[s] - S0[d][s];
+            for( int d=0; d<3; d++ ) {
+                bd[d] = __shfl_sync( 0xffffffffu, xdelta[d], src );
+                bn[d] = __shfl_sync( 0xffffffffu, xnpos[d], src );
+                bc[d] = __shfl_sync( 0xffffffffu, cr[d], src );
+            }
+            const int bcell = __shfl_sync( 0xffffffffu, cellt, src );
+            const int bcl[3] = { bcell / ( TZ*TY ), ( bcell / TZ ) % TY, bcell % TZ };
+            __syncwarp();
+            if( lane < 15 ) {
+                // lane -> (dimension d, window index s): S0[d][s] and DS[d][s]
+                const int d = lane / 5, sidx = lane % 5;
+                const double dl0 = d == 0 ? bd[0] : d == 1 ? bd[1] : bd[2];
+                const double pn  = d == 0 ? bn[0] : d == 1 ? bn[1] : bn[2];
+                const int    cld = d == 0 ? bcl[0] : d == 1 ? bcl[1] : bcl[2];
+                const int    c0d = d == 0 ? c0[0] : d == 1 ? c0[1] : c0[2];
+                const int    bgd = d == 0 ? g.begin[0] : d == 1 ? g.begin[1] : g.begin[2];
+                const int    od  = d == 0 ? g.o[0] : d == 1 ? g.o[1] : g.o[2];
+                double w0[3], w1[3];
+                Shape<2>::w( dl0, w0 );
+                const int ipn = ( int )round( pn );
+                Shape<2>::w( pn - ( double )ipn, w1 );
+                const int shift = ipn - bgd - ( cld + c0d + od );
+                const int t0 = sidx - 1, t1 = sidx - 1 - shift;
+                const double s0 = t0 == 0 ? w0[0] : t0 == 1 ? w0[1] : t0 == 2 ? w0[2] : 0.;
+                const double s1 = t1 == 0 ? w1[0] : t1 == 1 ? w1[1] : t1 == 2 ? w1[2] : 0.;
+                xscr[lane] = s0;
+                xscr[15+lane] = s1 - s0;
+            }
+            __syncwarp();
+            if( lane < 25 ) {
+                const int aa = lane / 5, bb = lane % 5;
+                const double third = 1./3.;
+                const double *S0x = xscr, *S0y = xscr+5, *S0z = xscr+10, *DSx = xscr+15, *DSy = xscr+20, *DSz = xscr+25;
+                double *xb = sJ + ( bcl[0]*T::JY + bcl[1] )*T::JZ + bcl[2];
+                {   // Jx: W(j=aa,k=bb), flux over i
+                    const double W = S0y[aa]*( S0z[bb] + 0.5*DSz[bb] ) + DSy[aa]*( 0.5*S0z[bb] + third*DSz[bb] );
+                    double run = 0.;
+#pragma unroll
+                    for( int i=1; i<5; i++ ) {
+                        run -= bc[0]*DSx[i-1];
+                        const double v = run*W;
+                        if( v != 0. ) atomicAdd( xb + 0*T::JVOL + ( i*T::JY + aa )*T::JZ + bb, v );
                     }
-                    esirkepov_general<2>( sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2], S0, DS, cr );
+                }
+                {   // Jy: W(i=aa,k=bb), flux over j
+                    const double W = S0x[aa]*( S0z[bb] + 0.5*DSz[bb] ) + DSx[aa]*( 0.5*S0z[bb] + third*DSz[bb] );
+                    double run = 0.;
+#pragma unroll
+                    for( int j=1; j<5; j++ ) {
+                        run -= bc[1]*DSy[j-1];
+                        const double v = run*W;
+                        if( v != 0. ) atomicAdd( xb + 1*T::JVOL + ( aa*T::JY + j )*T::JZ + bb, v );
+                    }
+                }
+                {   // Jz: W(i=aa,j=bb), flux over k
+                    const double W = S0x[aa]*( S0y[bb] + 0.5*DSy[bb] ) + DSx[aa]*( 0.5*S0y[bb] + third*DSy[bb] );
+                    double run = 0.;
+#pragma unroll
+                    for( int k=1; k<5; k++ ) {
+                        run -= bc[2]*DSz[k-1];
+                        const double v = run*W;
+                        if( v != 0. ) atomicAdd( xb + 2*T::JVOL + ( aa*T::JY + bb )*T::JZ + k, v );
+                    }
                 }
             }
         }
-        if( !fast ) {
-#pragma unroll
-            for( int i=0; i<18; i++ ) { vx[i] = 0.; vy[i] = 0.; vz[i] = 0.; }
-        }
-        // ---- sum over the 8 lanes of the cell group (all 32 lanes take part in the shuffles)
-        xr_step<18>( vx, 4, up4 ); xr_step<9>( vx, 2, up2 ); xr_step<5>( vx, 1, up1 );
-        xr_step<18>( vy, 4, up4 ); xr_step<9>( vy, 2, up2 ); xr_step<5>( vy, 1, up1 );
-        xr_step<18>( vz, 4, up4 ); xr_step<9>( vz, 2, up2 ); xr_step<5>( vz, 1, up1 );
-        if( have ) {
-            double *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
-#pragma unroll
-            for( int r=0; r<3; r++ ) {
-                if( joff[0][r] >= 0 && vx[r] != 0. ) atomicAdd( jb + joff[0][r], vx[r] );
-                if( joff[1][r] >= 0 && vy[r] != 0. ) atomicAdd( jb + joff[1][r], vy[r] );
-                if( joff[2][r] >= 0 && vz[r] != 0. ) atomicAdd( jb + joff[2][r], vz[r] );
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- cell-crossers: general Esirkepov window, one lane per listed particle
-    const int nx = min( xcount, XCAP );
-    for( int t = tid; t < nx; t += DYN_THREADS ) {
-        const size_t ip = ( size_t )xs_ip[t];
-        const int cellt = xs_cl[t];
-        const int cl[3] = { cellt / ( TZ*TY ), ( cellt / TZ ) % TY, cellt % TZ };
-        const double npos[3] = { a.col[0][ip], a.col[1][ip], a.col[2][ip] };
-        const double weight = a.col[6][ip];
-        const short charge = a.q[ip];
-        double S0[3][5], DS[3][5];
-#pragma unroll
-        for( int d=0; d<3; d++ ) {
-            double w0[3], w1[3], S1[5];
-            Shape<2>::w( xs_d[d*XCAP+t], w0 );
-            const double pn = npos[d]*g.dxi[d];
-            const int ipn = ( int )round( pn );
-            Shape<2>::w( pn - ( double )ipn, w1 );
-            const int shift = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );
-            place_S1<2>( w1, shift, S1 );
-            S0[d][0] = 0.; S0[d][4] = 0.;
-#pragma unroll
-            for( int s=0; s<3; s++ ) S0[d][s+1] = w0[s];
-#pragma unroll
-            for( int s=0; s<5; s++ ) DS[d][s] = S1[s] - S0[d][s];
-        }
-        const double charge_weight = g.inv_cell_volume*( double )charge*weight;
-        const double cr[3] = { charge_weight*g.d_ov_dt[0], charge_weight*g.d_ov_dt[1], charge_weight*g.d_ov_dt[2] };
-        esirkepov_general<2>( sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2], S0, DS, cr );
     }
     __syncthreads();
 
@@ -801,6 +820,7 @@ static int launch_o2( sb200_patch *p, const DynArgs &a, int ntiles )
 {
     auto kern = k_dynamics_o2<PUSHER, SCRATCH>;
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )O2Smem::BYTES ) );
+    SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
     kern<<<ntiles, DYN_THREADS, O2Smem::BYTES, p->stream>>>( p->gd, a );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
