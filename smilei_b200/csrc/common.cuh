@@ -62,6 +62,9 @@ struct SpeciesDev {
     int    *key = nullptr;
     int    *first = nullptr;       // ncells+1, valid after sort
     bool   sorted = false;
+    int    maxcount = 0;       // most particles in one cell (after the last sort)
+    double qwmax = 0.;         // max |charge*weight| seen in this species
+    unsigned long long *d_qwmax = nullptr;   // device copy kept up to date by imports / arrivals (bits of a positive double)
 };
 
 struct ParticleBuf {               // spare SoA set the sort scatters into, then swaps with the species
@@ -103,6 +106,7 @@ struct sb200_patch {
     double           *red = nullptr;         // device partial sums
     int              *leave_counts = nullptr;// device int[8]
     int              *iflags = nullptr;      // device int[8] : error / overflow flags
+    int              *d_maxcount = nullptr;  // device int: max particles per cell of the species being sorted
     // optional scratch (SB200_DYN_KEEP_SCRATCH)
     double           *sc_E = nullptr, *sc_B = nullptr, *sc_invgf = nullptr, *sc_delta = nullptr;
     int              *sc_iold = nullptr;     size_t sc_cap = 0;
@@ -119,4 +123,5 @@ int ensure_spare( sb200_patch *p, size_t cap );
 int ensure_perm( sb200_patch *p, size_t cap );
 int ensure_stage( sb200_patch *p, size_t elems );
 int exclusive_scan_int( sb200_patch *p, int *data, size_t n );   // in place, device
+int update_qwmax( sb200_patch *p, int ispec, size_t first, size_t n );   // fold |q*w| of particles [first, first+n) into d_qwmax
 }

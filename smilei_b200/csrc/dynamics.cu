@@ -18,10 +18,10 @@
 // deltaold/invgf never exist in HBM unless SB200_DYN_KEEP_SCRATCH asks for them.
 #include "common.cuh"
 #include <cstdlib>
+#include <cmath>
 
 namespace sb200 {
 
-constexpr int TX = 4, TY = 4, TZ = 8;
 constexpr int DYN_THREADS = 256;
 
 template<int ORDER> struct Shape;
@@ -48,7 +48,9 @@ template<> struct Shape<4> {
     }
 };
 
-template<int ORDER> struct Tile {
+template<int ORDER, int TX_ = 4, int TY_ = 4, int TZ_ = 8> struct Tile {
+    static constexpr int O  = ORDER;
+    static constexpr int TX = TX_, TY = TY_, TZ = TZ_;
     static constexpr int H  = ORDER/2;
     static constexpr int NW = ORDER+1;            // gather points per dim
     static constexpr int WD = ORDER+3;            // Esirkepov window per dim (5 or 7)
@@ -57,6 +59,27 @@ template<int ORDER> struct Tile {
     static constexpr int FVOL = FX*FY*FZ, JVOL = JX*JY*JZ;
     static constexpr size_t SMEM = ( size_t )( 6*FVOL + 3*JVOL )*sizeof( double );
 };
+
+// The tile's J box accumulates in 64-bit FIXED POINT: value*jscale rounded to an integer and added with the
+// native 64-bit integer shared-memory atomic (sm_100 has no native double atomic on shared memory: a
+// double atomicAdd there is a compare-and-swap loop).  jscale is a power of two chosen per launch from a
+// rigorous bound of |J| in the box (see launch_dynamics), so nothing can overflow and the rounding error
+// of one contribution is <= 2^-62 of that bound, i.e. far below 1 ulp of typical J values.  Integer
+// addition is associative, so the box sums are also bitwise reproducible.
+typedef unsigned long long jbox_t;
+// 64-bit add as two NATIVE 32-bit shared-memory atomics (ATOMS.ADD) with carry: sm_100 implements a 64-bit
+// atomicAdd on shared memory as a compare-and-swap loop (ATOMS.CAST.SPIN), measured 1.5-2.5x slower than this
+// pair and much worse under address conflicts (tools/smem_atomic_bench.cu).  Every wrap of the low word is
+// seen by exactly one adder, so the sum of carries is exact whatever the interleaving.
+__device__ __forceinline__ void jadd_scaled( jbox_t *p, double vs )
+{
+    const long long iv = __double2ll_rn( vs );
+    unsigned *w = reinterpret_cast<unsigned *>( p );
+    const unsigned lo = ( unsigned )iv, hi = ( unsigned )( iv >> 32 );
+    const unsigned old = atomicAdd( w, lo );
+    atomicAdd( w+1, hi + ( ( old + lo ) < old ? 1u : 0u ) );
+}
+__device__ __forceinline__ void jadd( jbox_t *p, double v, double jscale ) { jadd_scaled( p, v*jscale ); }
 
 struct DynArgs {
     double *col[7];
@@ -71,15 +94,15 @@ struct DynArgs {
     int    *sc_iold;
     size_t  n;
     double  one_over_mass;
+    double  jscale, jinv;     // fixed-point scale of the J box and its inverse
     int     tiles[3];
 };
 
 // separable gather of one component from its staged box: sum_i cx[i] sum_j cy[j] sum_k cz[k] F
-template<int ORDER>
+template<class T>
 __device__ __forceinline__ double gather( const double *__restrict__ sF, const double *cx, const double *cy, const double *cz,
                                           int sx, int sy, int sz )
 {
-    using T = Tile<ORDER>;
     double acc = 0.;
 #pragma unroll
     for( int i=0; i<T::NW; i++ ) {
@@ -163,10 +186,9 @@ __device__ __forceinline__ void push( double cmd, double dt, double &px, double 
 
 // S1 on the WD-point window from the NW weights `w` at shift s = ip - ipo in {-1,0,1}
 // (Projector3D2Order.cpp:124-152: Sx1[ip_m_ipo+1 .. +3] = weights)
-template<int ORDER>
+template<class T>
 __device__ __forceinline__ void place_S1( const double *w, int shift, double *S1 )
 {
-    using T = Tile<ORDER>;
 #pragma unroll
     for( int s=0; s<T::WD; s++ ) {
         const double a = ( s-1 >= 0 && s-1 < T::NW ) ? w[( s-1 >= 0 && s-1 < T::NW ) ? s-1 : 0] : 0.;   // shift  0
@@ -180,10 +202,9 @@ __device__ __forceinline__ void place_S1( const double *w, int shift, double *S1
 // Projector3D2Order::currents (Projector3D2Order.cpp:160-340) / Projector3D4Order::currents
 // (Projector3D4Order.cpp:191-230) in outer-product form: J[i][j][k] += C[i]*W[j][k] with
 // C[i] = -cr * sum_{i'<i} DS[i'] (the reference's running sum over the flux direction).
-template<int ORDER>
-__device__ __forceinline__ void esirkepov_general( double *jb, const double ( &S0 )[3][ORDER+3], const double ( &DS )[3][ORDER+3], const double *cr )
+template<class T>
+__device__ __forceinline__ void esirkepov_general( jbox_t *jb, const double ( &S0 )[3][T::WD], const double ( &DS )[3][T::WD], const double *cr, double jscale )
 {
-    using T = Tile<ORDER>;
     const double third = 1./3.;
     // Jx: flux along x, weights over (y,z)
     {
@@ -201,7 +222,7 @@ __device__ __forceinline__ void esirkepov_general( double *jb, const double ( &S
 #pragma unroll
                     for( int i=1; i<T::WD; i++ ) {
                         const double v = C[i]*W;
-                        if( v != 0. ) atomicAdd( jb + 0*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
+                        if( v != 0. ) jadd( jb + 0*T::JVOL + ( i*T::JY + j )*T::JZ + k, v, jscale );
                     }
                 }
             }
@@ -223,7 +244,7 @@ __device__ __forceinline__ void esirkepov_general( double *jb, const double ( &S
 #pragma unroll
                     for( int j=1; j<T::WD; j++ ) {
                         const double v = C[j]*W;
-                        if( v != 0. ) atomicAdd( jb + 1*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
+                        if( v != 0. ) jadd( jb + 1*T::JVOL + ( i*T::JY + j )*T::JZ + k, v, jscale );
                     }
                 }
             }
@@ -245,7 +266,7 @@ __device__ __forceinline__ void esirkepov_general( double *jb, const double ( &S
 #pragma unroll
                     for( int k=1; k<T::WD; k++ ) {
                         const double v = C[k]*W;
-                        if( v != 0. ) atomicAdd( jb + 2*T::JVOL + ( i*T::JY + j )*T::JZ + k, v );
+                        if( v != 0. ) jadd( jb + 2*T::JVOL + ( i*T::JY + j )*T::JZ + k, v, jscale );
                     }
                 }
             }
@@ -259,23 +280,23 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
     using T = Tile<ORDER>;
     extern __shared__ double smem[];
     double *sF = smem;                    // 6 boxes of FVOL
-    double *sJ = smem + 6*T::FVOL;        // 3 boxes of JVOL
-    __shared__ int row_off[TX*TY+1];
-    __shared__ int row_base[TX*TY];
+    jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FVOL );        // 3 boxes of JVOL (fixed point)
+    __shared__ int row_off[T::TX*T::TY+1];
+    __shared__ int row_base[T::TX*T::TY];
 
     const int tid = threadIdx.x;
     int b = blockIdx.x;
     const int tz = b % a.tiles[2]; b /= a.tiles[2];
     const int ty = b % a.tiles[1];
     const int tx = b / a.tiles[1];
-    const int c0[3] = { tx*TX, ty*TY, tz*TZ };
+    const int c0[3] = { tx*T::TX, ty*T::TY, tz*T::TZ };
 
     // particle runs of the tile
-    if( tid < TX*TY ) {
-        const int ix = c0[0] + tid/TY, iy = c0[1] + tid%TY;
+    if( tid < T::TX*T::TY ) {
+        const int ix = c0[0] + tid/T::TY, iy = c0[1] + tid%T::TY;
         int beg = 0, end = 0;
         if( ix < g.ncell[0] && iy < g.ncell[1] ) {
-            const int kz1 = min( c0[2]+TZ, g.ncell[2] );
+            const int kz1 = min( c0[2]+T::TZ, g.ncell[2] );
             const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + c0[2];
             beg = a.first[cell];
             end = a.first[cell + ( kz1 - c0[2] )];
@@ -287,10 +308,10 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
     if( tid == 0 ) {
         int s = 0;
         row_off[0] = 0;
-        for( int r=0; r<TX*TY; r++ ) { s += row_off[r+1]; row_off[r+1] = s; }
+        for( int r=0; r<T::TX*T::TY; r++ ) { s += row_off[r+1]; row_off[r+1] = s; }
     }
     __syncthreads();
-    const int total = row_off[TX*TY];
+    const int total = row_off[T::TX*T::TY];
     if( total == 0 ) return;
 
     // stage the field boxes: box index s <-> array index gs + s, gs = c0 + o - H
@@ -306,12 +327,12 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
         if( gi < g.ax && gj < g.ay && gk < g.az ) v = a.F[c][gi*g.sx + gj*g.sy + gk];
         sF[t] = v;
     }
-    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0.;
+    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0ull;
     __syncthreads();
 
     for( int wi = tid; wi < total; wi += DYN_THREADS ) {
         // row of this work item (binary search in row_off)
-        int lo = 0, hi = TX*TY;
+        int lo = 0, hi = T::TX*T::TY;
         while( hi - lo > 1 ) { const int mid = ( lo+hi ) >> 1; if( row_off[mid] <= wi ) lo = mid; else hi = mid; }
         const size_t ip = ( size_t )row_base[lo] + ( size_t )( wi - row_off[lo] );
 
@@ -334,7 +355,7 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
             const double dd = pn - ( double )idn + 0.5;
             Shape<ORDER>::w( dd, cd[d] );
             int c = ipn - g.begin[d] - g.o[d] - c0[d];       // cell offset inside the tile
-            const int tdim = d==0 ? TX : d==1 ? TY : TZ;
+            const int tdim = d==0 ? T::TX : d==1 ? T::TY : T::TZ;
             if( c < 0 || c >= tdim ) { bad = true; c = c < 0 ? 0 : tdim-1; }
             cl[d] = c;
             sp[d] = c + T::H;
@@ -343,12 +364,12 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
         if( bad ) atomicAdd( &a.iflags[1], 1 );   // particle not in the cell its sort key says
 
         // ---- gather (fieldsWrapper): Ex(d,p,p) Ey(p,d,p) Ez(p,p,d) Bx(p,d,d) By(d,p,d) Bz(d,d,p)
-        const double Ex = gather<ORDER>( sF+0*T::FVOL, cd[0], cp[1], cp[2], sd[0], sp[1], sp[2] );
-        const double Ey = gather<ORDER>( sF+1*T::FVOL, cp[0], cd[1], cp[2], sp[0], sd[1], sp[2] );
-        const double Ez = gather<ORDER>( sF+2*T::FVOL, cp[0], cp[1], cd[2], sp[0], sp[1], sd[2] );
-        const double Bx = gather<ORDER>( sF+3*T::FVOL, cp[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
-        const double By = gather<ORDER>( sF+4*T::FVOL, cd[0], cp[1], cd[2], sd[0], sp[1], sd[2] );
-        const double Bz = gather<ORDER>( sF+5*T::FVOL, cd[0], cd[1], cp[2], sd[0], sd[1], sp[2] );
+        const double Ex = gather<T>( sF+0*T::FVOL, cd[0], cp[1], cp[2], sd[0], sp[1], sp[2] );
+        const double Ey = gather<T>( sF+1*T::FVOL, cp[0], cd[1], cp[2], sp[0], sd[1], sp[2] );
+        const double Ez = gather<T>( sF+2*T::FVOL, cp[0], cp[1], cd[2], sp[0], sp[1], sd[2] );
+        const double Bx = gather<T>( sF+3*T::FVOL, cp[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+        const double By = gather<T>( sF+4*T::FVOL, cd[0], cp[1], cd[2], sd[0], sp[1], sd[2] );
+        const double Bz = gather<T>( sF+5*T::FVOL, cd[0], cd[1], cp[2], sd[0], sd[1], sp[2] );
 
         // ---- push
         const double cmd = ( double )charge*a.one_over_mass*g.dts2;
@@ -382,7 +403,7 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
             double w1[T::NW], S1[T::WD];
             Shape<ORDER>::w( dl, w1 );
             const int shift = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );    // ip - ipo - i_domain_begin
-            place_S1<ORDER>( w1, shift, S1 );
+            place_S1<T>( w1, shift, S1 );
             S0[d][0] = 0.; S0[d][T::WD-1] = 0.;
 #pragma unroll
             for( int s=0; s<T::NW; s++ ) S0[d][s+1] = cp[d][s];
@@ -403,16 +424,17 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
         // ---- currents (Esirkepov), accumulated in the tile's J box
         const double charge_weight = g.inv_cell_volume*( double )charge*weight;
         const double cr[3] = { charge_weight*g.d_ov_dt[0], charge_weight*g.d_ov_dt[1], charge_weight*g.d_ov_dt[2] };
-        double *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
-        esirkepov_general<ORDER>( jb, S0, DS, cr );
+        jbox_t *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
+        esirkepov_general<T>( jb, S0, DS, cr, a.jscale );
     }
     __syncthreads();
 
     // flush the J box: box index s <-> array index c0 + o - H - 1 + s
     const int js[3] = { c0[0] + g.o[0] - T::H - 1, c0[1] + g.o[1] - T::H - 1, c0[2] + g.o[2] - T::H - 1 };
     for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) {
-        const double v = sJ[t];
-        if( v == 0. ) continue;
+        const long long iv = ( long long )sJ[t];
+        if( iv == 0 ) continue;
+        const double v = ( double )iv*a.jinv;
         const int c = t / T::JVOL;
         int r = t - c*T::JVOL;
         const int k = r % T::JZ; r /= T::JZ;
@@ -455,27 +477,32 @@ static int launch_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int push
 // =================================================================================================
 // Order-2 fast kernel.
 //
-// What binds the straightforward kernel above is not HBM: every particle issues ~100 non-zero
-// double atomics on shared memory (compare-and-swap loops on sm_100), all lanes of a warp on the
-// same few addresses because sorted neighbours sit in the same cell.  This kernel removes them
-// from the common case:
+// What binds the general kernel above is not HBM: every particle issues ~100 non-zero double
+// atomics on shared memory (compare-and-swap loops on sm_100), all lanes of a warp on the same few
+// addresses because sorted neighbours sit in the same cell.  This kernel removes them from the
+// common case:
+//   * tile of 8x8x8 cells per CTA (staging and flush amortised over ~8k particles);
 //   * work item = (cell, round): G = 8 consecutive lanes take up to 8 particles OF THE SAME CELL;
 //   * a particle whose primal node does not change during the step (the large majority in a
-//     thermal plasma: |dx| << 1 cell) deposits only on the 3x3x3 nodes around its cell:
-//     2x3x3 values per current component.  They are computed in registers, summed over the
-//     8 lanes with a shuffle transpose-reduction (18 -> 9 -> 5 -> 3 values per lane), and only
-//     the per-cell sums (3 per lane per component) reach the tile's J box in shared memory;
-//   * particles that do change cell are appended to a per-tile list and deposited afterwards by
-//     the general 5-point-window routine, one lane per particle, densely packed.
+//     thermal plasma: |dx| << 1 cell) deposits only on the 3x3x3 nodes around its cell: 2x3x3 values
+//     per current component.  They are computed in registers, summed over the 8 lanes with a shuffle
+//     transpose-reduction (18 -> 9 -> 5 -> 3 values per lane), and only the per-cell sums reach the
+//     tile's J box in shared memory (3 atomics per lane per component per round);
+//   * particles that do change cell are deposited by their own 8-lane group, one at a time and up to
+//     four groups of the warp concurrently: their Esirkepov window is exactly 4 points wide per
+//     dimension (S0 on 1..3, S1 shifted by -1/0/+1), so each lane takes 2 of the 4x4 transverse
+//     positions and the 3 non-zero flux points of each component.
 // Gather, push, boundary tagging and next-key computation are as in the general kernel.
 // =================================================================================================
-constexpr int GRP = 8;                       // lanes per cell group
-constexpr int NCELL_TILE = TX*TY*TZ;         // 128
-constexpr int XSCR = 32;                     // doubles of per-warp scratch for the cooperative crosser deposit
+using TileO2 = Tile<2, 4, 8, 8>;
+constexpr int GRP = 8;                                   // lanes per cell group
+constexpr int NCELL_O2 = TileO2::TX*TileO2::TY*TileO2::TZ;   // 256
+constexpr int XSCR = 24;                                 // doubles of crosser scratch per lane group: S0[3][4], DS[3][4]
+constexpr int XQ = 16;                                   // cell-crossers a warp can keep pending
+constexpr int XQD = 9*XQ + XQ/2;                         // doubles per warp queue: deltaold[3], new pos[3], cr[3] (SoA) + XQ ints
 
 struct O2Smem {
-    static constexpr int FVOL = Tile<2>::FVOL, JVOL = Tile<2>::JVOL;
-    static constexpr size_t BYTES = ( size_t )( 6*FVOL + 3*JVOL + XSCR*( DYN_THREADS/32 ) )*sizeof( double );
+    static constexpr size_t BYTES = ( size_t )( 6*TileO2::FVOL + 3*TileO2::JVOL + XSCR*( DYN_THREADS/GRP ) + XQD*( DYN_THREADS/32 ) )*sizeof( double );
 };
 
 // one step of the transpose-reduction: N values -> (N+1)/2 values; lanes with `upper` keep the second half
@@ -516,54 +543,123 @@ __device__ __forceinline__ void o2_contrib( double *v, double cr, const double *
     }
 }
 
+// One pass over the warp's crosser queue: lane group `grp` (0..3) deposits entry head+grp if it exists.
+// The Esirkepov window of a particle that changed cell is exactly 4 points wide per dimension, starting at
+// lo = (shift<0 ? 0 : 1): S0 on window points 1..3, S1 on 1+shift..3+shift.  Lanes 0..2 of the group
+// evaluate S0/DS of one dimension each into the group's scratch; then every lane takes 2 of the 4x4
+// transverse positions and the 3 non-zero flux points (lo+1..lo+3) of each current component.
+__device__ __forceinline__ void o2_cross_pass( jbox_t *sJ, const double *xq, const int *xqm, double *xscr, int qh, int qn,
+                                               int gl, int grp, const int *c0, const GridDev &g, double jscale )
+{
+    using T = TileO2;
+    const bool work = grp < qn;
+    const int e = ( qh + ( work ? grp : 0 ) ) % XQ;
+    const int meta = xqm[e];
+    const int cellt = meta & 0xffff, bsh = meta >> 16;
+    if( work && gl < 3 ) {
+        const int d = gl;
+        const double dl0 = xq[( 0+d )*XQ+e];
+        const double pn  = xq[( 3+d )*XQ+e];
+        const int shift = ( ( bsh >> ( 2*d ) ) & 3 ) - 1;
+        double w0[3], w1[3];
+        Shape<2>::w( dl0, w0 );
+        Shape<2>::w( pn - round( pn ), w1 );
+        const int lo_ = shift < 0 ? 0 : 1;
+#pragma unroll
+        for( int s=0; s<4; s++ ) {
+            const int t0 = lo_ + s - 1, t1 = lo_ + s - 1 - shift;
+            const double s0 = t0 == 0 ? w0[0] : t0 == 1 ? w0[1] : t0 == 2 ? w0[2] : 0.;
+            const double s1 = t1 == 0 ? w1[0] : t1 == 1 ? w1[1] : t1 == 2 ? w1[2] : 0.;
+            xscr[d*4+s] = s0;
+            xscr[12+d*4+s] = s1 - s0;
+        }
+    }
+    __syncwarp();
+    if( work ) {
+        const double third = 1./3.;
+        const int cl[3] = { cellt / ( T::TZ*T::TY ), ( cellt / T::TZ ) % T::TY, cellt % T::TZ };
+        const int lo0 = ( ( bsh      ) & 3 ) == 0 ? 0 : 1;
+        const int lo1 = ( ( bsh >> 2 ) & 3 ) == 0 ? 0 : 1;
+        const int lo2 = ( ( bsh >> 4 ) & 3 ) == 0 ? 0 : 1;
+        const double *S0x = xscr, *S0y = xscr+4, *S0z = xscr+8, *DSx = xscr+12, *DSy = xscr+16, *DSz = xscr+20;
+        jbox_t *xb = sJ + ( ( cl[0]+lo0 )*T::JY + ( cl[1]+lo1 ) )*T::JZ + ( cl[2]+lo2 );
+        const double c0x = xq[6*XQ+e]*jscale, c1y = xq[7*XQ+e]*jscale, c2z = xq[8*XQ+e]*jscale;   // fixed-point scale folded in
+        const double Cx1 = -c0x*DSx[0], Cx2 = Cx1 - c0x*DSx[1], Cx3 = Cx2 - c0x*DSx[2];
+        const double Cy1 = -c1y*DSy[0], Cy2 = Cy1 - c1y*DSy[1], Cy3 = Cy2 - c1y*DSy[2];
+        const double Cz1 = -c2z*DSz[0], Cz2 = Cz1 - c2z*DSz[1], Cz3 = Cz2 - c2z*DSz[2];
+#pragma unroll
+        for( int h=0; h<2; h++ ) {
+            const int pp = gl + 8*h, aa = pp >> 2, bb = pp & 3;
+            const double Az = S0z[bb] + 0.5*DSz[bb], Bz = 0.5*S0z[bb] + third*DSz[bb];
+            const double Wx = S0y[aa]*Az + DSy[aa]*Bz;                                                       // Jx: W(j=aa,k=bb)
+            const double Wy = S0x[aa]*Az + DSx[aa]*Bz;                                                       // Jy: W(i=aa,k=bb)
+            const double Wz = S0x[aa]*( S0y[bb] + 0.5*DSy[bb] ) + DSx[aa]*( 0.5*S0y[bb] + third*DSy[bb] );   // Jz: W(i=aa,j=bb)
+            jbox_t *qx = xb + 0*T::JVOL + ( 1*T::JY + aa )*T::JZ + bb;      // flux points lo0+1..lo0+3
+            jbox_t *qy = xb + 1*T::JVOL + ( aa*T::JY + 1 )*T::JZ + bb;      // flux points lo1+1..lo1+3
+            jbox_t *qz = xb + 2*T::JVOL + ( aa*T::JY + bb )*T::JZ + 1;      // flux points lo2+1..lo2+3
+            jadd_scaled( qx, Cx1*Wx ); jadd_scaled( qx + T::JY*T::JZ, Cx2*Wx ); jadd_scaled( qx + 2*T::JY*T::JZ, Cx3*Wx );
+            jadd_scaled( qy, Cy1*Wy ); jadd_scaled( qy + T::JZ, Cy2*Wy ); jadd_scaled( qy + 2*T::JZ, Cy3*Wy );
+            jadd_scaled( qz, Cz1*Wz ); jadd_scaled( qz + 1, Cz2*Wz ); jadd_scaled( qz + 2, Cz3*Wz );
+        }
+    }
+    __syncwarp();
+}
+
 template<int PUSHER, bool SCRATCH>
 __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev g, const DynArgs a )
 {
-    using T = Tile<2>;
+    using T = TileO2;
     extern __shared__ double smem[];
     double *sF = smem;
-    double *sJ = smem + 6*T::FVOL;
-    double *xscr = sJ + 3*T::JVOL + XSCR*( threadIdx.x >> 5 );       // this warp's S0/DS scratch: [d][0..4] S0, [15+d*5+..] DS
-    __shared__ int cell_first[NCELL_TILE];
-    __shared__ int round_off[NCELL_TILE+1];
-    __shared__ int warp_tot[4];
+    jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FVOL );
+    double *xscr = smem + 6*T::FVOL + 3*T::JVOL + XSCR*( threadIdx.x/GRP );      // this lane group's crosser scratch
+    __shared__ int cell_first[NCELL_O2];
+    __shared__ int round_off[NCELL_O2+1];
+    __shared__ int warp_tot[DYN_THREADS/32];
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     int b = blockIdx.x;
     const int tz = b % a.tiles[2]; b /= a.tiles[2];
     const int ty = b % a.tiles[1];
     const int tx = b / a.tiles[1];
-    const int c0[3] = { tx*TX, ty*TY, tz*TZ };
+    const int c0[3] = { tx*T::TX, ty*T::TY, tz*T::TZ };
 
-    // ---- per-cell particle runs and the prefix sum of their rounds
-    if( tid < NCELL_TILE ) {
-        const int lz = tid % TZ, ly = ( tid / TZ ) % TY, lx = tid / ( TZ*TY );
-        const int ix = c0[0]+lx, iy = c0[1]+ly, iz = c0[2]+lz;
-        int beg = 0, cnt = 0;
-        if( ix < g.ncell[0] && iy < g.ncell[1] && iz < g.ncell[2] ) {
-            const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + iz;
-            beg = a.first[cell];
-            cnt = a.first[cell+1] - beg;
+    // ---- per-cell particle runs and the prefix sum of their rounds (2 cells per thread)
+    {
+        int run = 0;
+        int rounds[NCELL_O2/DYN_THREADS];
+#pragma unroll
+        for( int e=0; e<NCELL_O2/DYN_THREADS; e++ ) {
+            const int ct = tid*( NCELL_O2/DYN_THREADS ) + e;
+            const int lz = ct % T::TZ, ly = ( ct / T::TZ ) % T::TY, lx = ct / ( T::TZ*T::TY );
+            const int ix = c0[0]+lx, iy = c0[1]+ly, iz = c0[2]+lz;
+            int beg = 0, cnt = 0;
+            if( ix < g.ncell[0] && iy < g.ncell[1] && iz < g.ncell[2] ) {
+                const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + iz;
+                beg = a.first[cell];
+                cnt = a.first[cell+1] - beg;
+            }
+            cell_first[ct] = beg | ( cnt > 0 ? 0 : 0 );
+            rounds[e] = ( cnt + GRP - 1 )/GRP;
+            run += rounds[e];
         }
-        cell_first[tid] = beg;
-        const int rounds = ( cnt + GRP - 1 )/GRP;
-        // pack count in the low bits of the round prefix later; first an inclusive warp scan of `rounds`
-        int inc = rounds;
-        const int lane = tid & 31;
+        int inc = run;
 #pragma unroll
         for( int d=1; d<32; d<<=1 ) { const int u = __shfl_up_sync( 0xffffffffu, inc, d ); if( lane >= d ) inc += u; }
         if( lane == 31 ) warp_tot[tid >> 5] = inc;
-        round_off[tid+1] = inc;          // warp-local inclusive prefix, fixed up below
-    }
-    __syncthreads();
-    if( tid < NCELL_TILE ) {
-        int off = 0;
+        __syncthreads();
+        int off = inc - run;
         for( int w=0; w<( tid >> 5 ); w++ ) off += warp_tot[w];
-        round_off[tid+1] += off;
+#pragma unroll
+        for( int e=0; e<NCELL_O2/DYN_THREADS; e++ ) {
+            off += rounds[e];
+            round_off[tid*( NCELL_O2/DYN_THREADS ) + e + 1] = off;
+        }
+        if( tid == 0 ) round_off[0] = 0;
     }
-    if( tid == 0 ) round_off[0] = 0;
     __syncthreads();
-    const int nrounds = round_off[NCELL_TILE];
+    const int nrounds = round_off[NCELL_O2];
     if( nrounds == 0 ) return;
 
     // ---- stage the field boxes, clear the J box
@@ -579,7 +675,7 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
         if( gi < g.ax && gj < g.ay && gk < g.az ) v = a.F[c][gi*g.sx + gj*g.sy + gk];
         sF[t] = v;
     }
-    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0.;
+    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0ull;
     __syncthreads();
 
     // ---- lane geometry of the transpose-reduction: which of the 18 values of a component each of
@@ -602,28 +698,34 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
         joff[2][r] = ok ? 2*T::JVOL + ( ( 1+aa )*T::JY + ( 1+bb ) )*T::JZ + ( 2+f ) : -1;
     }
 
-    const int ngroups = DYN_THREADS/GRP;
-    const int niter = ( nrounds + ngroups - 1 )/ngroups;
+    double *xq = smem + 6*T::FVOL + 3*T::JVOL + XSCR*( DYN_THREADS/GRP ) + XQD*( tid >> 5 );   // this warp's queue
+    int *xqm = reinterpret_cast<int *>( xq + 9*XQ );
+    int qh = 0, qn = 0;                                       // queue head / pending entries (warp-uniform)
+
+    constexpr int NGROUPS = DYN_THREADS/GRP;
+    const int niter = ( nrounds + NGROUPS - 1 )/NGROUPS;
     for( int it = 0; it < niter; it++ ) {
-        const int wi = it*ngroups + gid;
+        const int wi = it*NGROUPS + gid;
         const bool have = wi < nrounds;
         // cell of this round: last c with round_off[c] <= wi
-        int lo = 0, hi = NCELL_TILE;
-        while( hi - lo > 1 ) { const int mid = ( lo+hi ) >> 1; if( round_off[mid] <= ( have ? wi : 0 ) ) lo = mid; else hi = mid; }
+        int lo = 0, hi = NCELL_O2;
+        const int wq = have ? wi : 0;
+#pragma unroll
+        for( int st=0; st<8; st++ ) { const int mid = ( lo+hi ) >> 1; if( round_off[mid] <= wq ) lo = mid; else hi = mid; }
         const int cellt = lo;
-        const int cl[3] = { cellt / ( TZ*TY ), ( cellt / TZ ) % TY, cellt % TZ };
-        const int rnd = ( have ? wi : 0 ) - round_off[cellt];
-        int cnt_cell;
-        {
-            const int ix = c0[0]+cl[0], iy = c0[1]+cl[1], iz = c0[2]+cl[2];
-            const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + iz;
-            cnt_cell = have ? a.first[cell+1] - cell_first[cellt] : 0;
+        const int cl[3] = { cellt / ( T::TZ*T::TY ), ( cellt / T::TZ ) % T::TY, cellt % T::TZ };
+        const int rnd = wq - round_off[cellt];
+        int cnt_cell = 0;
+        if( have ) {
+            const int cell = ( ( c0[0]+cl[0] )*g.ncell[1] + ( c0[1]+cl[1] ) )*g.ncell[2] + ( c0[2]+cl[2] );
+            cnt_cell = a.first[cell+1] - cell_first[cellt];
         }
         const int slot = rnd*GRP + gl;
         const bool active = have && slot < cnt_cell;
         const size_t ip = ( size_t )cell_first[cellt] + ( size_t )( active ? slot : 0 );
 
         double S0[3][3], DS[3][3], cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
+        int shifts = 0;                       // (shift+1) per dimension, 2 bits each
         bool fast = false;
         if( active ) {
             double pos[3] = { a.col[0][ip], a.col[1][ip], a.col[2][ip] };
@@ -646,12 +748,12 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
                 sp[d] = cl[d] + T::H;
                 sd[d] = sp[d] + ( idn - ipn );
             }
-            const double Ex = gather<2>( sF+0*T::FVOL, cd[0], cp[1], cp[2], sd[0], sp[1], sp[2] );
-            const double Ey = gather<2>( sF+1*T::FVOL, cp[0], cd[1], cp[2], sp[0], sd[1], sp[2] );
-            const double Ez = gather<2>( sF+2*T::FVOL, cp[0], cp[1], cd[2], sp[0], sp[1], sd[2] );
-            const double Bx = gather<2>( sF+3*T::FVOL, cp[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
-            const double By = gather<2>( sF+4*T::FVOL, cd[0], cp[1], cd[2], sd[0], sp[1], sd[2] );
-            const double Bz = gather<2>( sF+5*T::FVOL, cd[0], cd[1], cp[2], sd[0], sd[1], sp[2] );
+            const double Ex = gather<T>( sF+0*T::FVOL, cd[0], cp[1], cp[2], sd[0], sp[1], sp[2] );
+            const double Ey = gather<T>( sF+1*T::FVOL, cp[0], cd[1], cp[2], sp[0], sd[1], sp[2] );
+            const double Ez = gather<T>( sF+2*T::FVOL, cp[0], cp[1], cd[2], sp[0], sp[1], sd[2] );
+            const double Bx = gather<T>( sF+3*T::FVOL, cp[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+            const double By = gather<T>( sF+4*T::FVOL, cd[0], cp[1], cd[2], sd[0], sp[1], sd[2] );
+            const double Bz = gather<T>( sF+5*T::FVOL, cd[0], cd[1], cp[2], sd[0], sd[1], sp[2] );
 
             const double cmd = ( double )charge*a.one_over_mass*g.dts2;
             double dxp, dyp, dzp, invgf;
@@ -671,19 +773,25 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
             }
 
             // new shape factors, tag / next key
-            double w1[3][3];
-            int shift[3], nkey[3], tag = 0;
+            int nkey[3], tag = 0;
+            bool same = true;
 #pragma unroll
             for( int d=0; d<3; d++ ) {
                 const double pn = npos[d]*g.dxi[d];
                 const int ipn = ( int )round( pn );
-                Shape<2>::w( pn - ( double )ipn, w1[d] );
-                shift[d] = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );
+                double w1[3];
+                Shape<2>::w( pn - ( double )ipn, w1 );
+                const int shift = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );
+                shifts |= ( shift+1 ) << ( 2*d );
+                same = same && shift == 0;
                 nkey[d] = ( int )( ( double )ipn - g.min_loc_round[d] );
                 if( tag == 0 ) {
                     if( npos[d] < g.xmin[d] ) tag = -2 - 2*d;
                     else if( npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
                 }
+                xdelta[d] = delta_p[d]; xnpos[d] = pn;
+#pragma unroll
+                for( int s=0; s<3; s++ ) { S0[d][s] = cp[d][s]; DS[d][s] = w1[s] - cp[d][s]; }
             }
             int key = tag;
             if( tag == 0 ) key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2];
@@ -692,17 +800,12 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
 
             const double charge_weight = g.inv_cell_volume*( double )charge*weight;
             cr[0] = charge_weight*g.d_ov_dt[0]; cr[1] = charge_weight*g.d_ov_dt[1]; cr[2] = charge_weight*g.d_ov_dt[2];
-            fast = ( shift[0] | shift[1] | shift[2] ) == 0;
-#pragma unroll
-            for( int d=0; d<3; d++ ) {
-                xdelta[d] = delta_p[d]; xnpos[d] = npos[d]*g.dxi[d];
-#pragma unroll
-                for( int s=0; s<3; s++ ) { S0[d][s] = cp[d][s]; DS[d][s] = w1[d][s] - cp[d][s]; }
-            }
+            fast = same;
         }
-        double *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
+        jbox_t *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
         // ---- non-crossing particles: 2x3x3 values per component, summed over the 8 lanes of the cell
-        //      group in registers (all 32 lanes take part in the shuffles), 3 sums per lane reach the J box
+        //      group in registers (all 32 lanes take part in the shuffles); 3 sums per lane and component
+        double fsum[9];
 #pragma unroll
         for( int c=0; c<3; c++ ) {
             double v[18];
@@ -715,95 +818,87 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
                 for( int i=0; i<18; i++ ) v[i] = 0.;
             }
             xr_step<18>( v, 4, up4 ); xr_step<9>( v, 2, up2 ); xr_step<5>( v, 1, up1 );
-            if( have ) {
 #pragma unroll
-                for( int r=0; r<3; r++ )
-                    if( joff[c][r] >= 0 && v[r] != 0. ) atomicAdd( jb + joff[c][r], v[r] );
-            }
+            for( int r=0; r<3; r++ ) fsum[c*3+r] = v[r];
         }
-        // ---- particles that changed cell: the whole warp deposits them one at a time, lane (a,b) of a
-        //      5x5 face taking the 4 flux points of each component (general window, Projector3D2Order.cpp:160-340)
+        // two rounds of the same cell often sit in neighbouring groups of the warp: add them up here
+        // instead of letting their atomics collide on identical addresses
+        bool owner = have;
+        {
+            const int mycell = have ? cellt : -1 - gid;
+            const int c8 = __shfl_xor_sync( 0xffffffffu, mycell, 8 );
+            const bool same8 = c8 == mycell;
+#pragma unroll
+            for( int i=0; i<9; i++ ) { const double o = __shfl_xor_sync( 0xffffffffu, fsum[i], 8 ); if( same8 ) fsum[i] += o; }
+            if( same8 && ( lane & 8 ) ) owner = false;
+            const int c16 = __shfl_xor_sync( 0xffffffffu, mycell, 16 );
+            const bool own16 = __shfl_xor_sync( 0xffffffffu, ( int )owner, 16 ) != 0;
+            const bool same16 = c16 == mycell && owner && own16;
+#pragma unroll
+            for( int i=0; i<9; i++ ) { const double o = __shfl_xor_sync( 0xffffffffu, fsum[i], 16 ); if( same16 ) fsum[i] += o; }
+            if( same16 && ( lane & 16 ) ) owner = false;
+        }
+        {
+            jbox_t *ad[9];
+            bool doit[9];
+#pragma unroll
+            for( int c=0; c<3; c++ )
+#pragma unroll
+                for( int r=0; r<3; r++ ) {
+                    ad[c*3+r] = jb + ( joff[c][r] >= 0 ? joff[c][r] : 0 );
+                    doit[c*3+r] = owner && joff[c][r] >= 0 && fsum[c*3+r] != 0.;
+                }
+#pragma unroll
+            for( int i=0; i<9; i++ ) if( doit[i] ) jadd( ad[i], fsum[i], a.jscale );
+        }
+        // ---- particles that changed cell (Projector3D2Order.cpp:124-340 with ip_m_ipo != 0) go to the warp's
+        //      queue; whenever 4 are pending the warp deposits them, one per lane group (o2_cross_pass)
         unsigned xmask = __ballot_sync( 0xffffffffu, active && !fast );
-        const int lane = tid & 31;
-        while( xmask ) {
-            const int src = __ffs( xmask ) - 1;
-            xmask &= xmask - 1;
-            double bd[3], bn[3], bc[3];
+        while( xmask ) {                                                  // warp-uniform
+            const int room = XQ - qn;
+            const int rank = __popc( xmask & ( ( 1u << lane ) - 1u ) );
+            const bool mineq = ( ( xmask >> lane ) & 1u ) && rank < room;
+            if( mineq ) {
+                const int e = ( qh + qn + rank ) % XQ;
 #pragma unroll
-            for( int d=0; d<3; d++ ) {
-                bd[d] = __shfl_sync( 0xffffffffu, xdelta[d], src );
-                bn[d] = __shfl_sync( 0xffffffffu, xnpos[d], src );
-                bc[d] = __shfl_sync( 0xffffffffu, cr[d], src );
+                for( int d=0; d<3; d++ ) { xq[( 0+d )*XQ+e] = xdelta[d]; xq[( 3+d )*XQ+e] = xnpos[d]; xq[( 6+d )*XQ+e] = cr[d]; }
+                xqm[e] = cellt | ( shifts << 16 );
             }
-            const int bcell = __shfl_sync( 0xffffffffu, cellt, src );
-            const int bcl[3] = { bcell / ( TZ*TY ), ( bcell / TZ ) % TY, bcell % TZ };
+            const unsigned done = __ballot_sync( 0xffffffffu, mineq );
+            xmask &= ~done;
+            qn += __popc( done );
             __syncwarp();
-            if( lane < 15 ) {
-                // lane -> (dimension d, window index s): S0[d][s] and DS[d][s]
-                const int d = lane / 5, sidx = lane % 5;
-                const double dl0 = d == 0 ? bd[0] : d == 1 ? bd[1] : bd[2];
-                const double pn  = d == 0 ? bn[0] : d == 1 ? bn[1] : bn[2];
-                const int    cld = d == 0 ? bcl[0] : d == 1 ? bcl[1] : bcl[2];
-                const int    c0d = d == 0 ? c0[0] : d == 1 ? c0[1] : c0[2];
-                const int    bgd = d == 0 ? g.begin[0] : d == 1 ? g.begin[1] : g.begin[2];
-                const int    od  = d == 0 ? g.o[0] : d == 1 ? g.o[1] : g.o[2];
-                double w0[3], w1[3];
-                Shape<2>::w( dl0, w0 );
-                const int ipn = ( int )round( pn );
-                Shape<2>::w( pn - ( double )ipn, w1 );
-                const int shift = ipn - bgd - ( cld + c0d + od );
-                const int t0 = sidx - 1, t1 = sidx - 1 - shift;
-                const double s0 = t0 == 0 ? w0[0] : t0 == 1 ? w0[1] : t0 == 2 ? w0[2] : 0.;
-                const double s1 = t1 == 0 ? w1[0] : t1 == 1 ? w1[1] : t1 == 2 ? w1[2] : 0.;
-                xscr[lane] = s0;
-                xscr[15+lane] = s1 - s0;
-            }
-            __syncwarp();
-            if( lane < 25 ) {
-                const int aa = lane / 5, bb = lane % 5;
-                const double third = 1./3.;
-                const double *S0x = xscr, *S0y = xscr+5, *S0z = xscr+10, *DSx = xscr+15, *DSy = xscr+20, *DSz = xscr+25;
-                double *xb = sJ + ( bcl[0]*T::JY + bcl[1] )*T::JZ + bcl[2];
-                {   // Jx: W(j=aa,k=bb), flux over i
-                    const double W = S0y[aa]*( S0z[bb] + 0.5*DSz[bb] ) + DSy[aa]*( 0.5*S0z[bb] + third*DSz[bb] );
-                    double run = 0.;
-#pragma unroll
-                    for( int i=1; i<5; i++ ) {
-                        run -= bc[0]*DSx[i-1];
-                        const double v = run*W;
-                        if( v != 0. ) atomicAdd( xb + 0*T::JVOL + ( i*T::JY + aa )*T::JZ + bb, v );
-                    }
-                }
-                {   // Jy: W(i=aa,k=bb), flux over j
-                    const double W = S0x[aa]*( S0z[bb] + 0.5*DSz[bb] ) + DSx[aa]*( 0.5*S0z[bb] + third*DSz[bb] );
-                    double run = 0.;
-#pragma unroll
-                    for( int j=1; j<5; j++ ) {
-                        run -= bc[1]*DSy[j-1];
-                        const double v = run*W;
-                        if( v != 0. ) atomicAdd( xb + 1*T::JVOL + ( aa*T::JY + j )*T::JZ + bb, v );
-                    }
-                }
-                {   // Jz: W(i=aa,j=bb), flux over k
-                    const double W = S0x[aa]*( S0y[bb] + 0.5*DSy[bb] ) + DSx[aa]*( 0.5*S0y[bb] + third*DSy[bb] );
-                    double run = 0.;
-#pragma unroll
-                    for( int k=1; k<5; k++ ) {
-                        run -= bc[2]*DSz[k-1];
-                        const double v = run*W;
-                        if( v != 0. ) atomicAdd( xb + 2*T::JVOL + ( aa*T::JY + bb )*T::JZ + k, v );
-                    }
-                }
+#ifdef SB200_COUNT_CROSSERS
+            if( lane == 0 ) atomicAdd( &a.iflags[2], __popc( done ) );
+#endif
+            while( qn >= 4 || ( xmask && qn > 0 ) ) {
+#ifdef SB200_COUNT_CROSSERS
+                if( lane == 0 ) atomicAdd( &a.iflags[3], 1 );
+#endif
+                o2_cross_pass( sJ, xq, xqm, xscr, qh, qn, gl, lane >> 3, c0, g, a.jscale );
+                const int took = qn < 4 ? qn : 4;
+                qh = ( qh + took ) % XQ;
+                qn -= took;
             }
         }
+    }
+    while( qn > 0 ) {                                                     // drain what is left in the queue
+#ifdef SB200_COUNT_CROSSERS
+        if( lane == 0 ) atomicAdd( &a.iflags[4], 1 );
+#endif
+        o2_cross_pass( sJ, xq, xqm, xscr, qh, qn, gl, lane >> 3, c0, g, a.jscale );
+        const int took = qn < 4 ? qn : 4;
+        qh = ( qh + took ) % XQ;
+        qn -= took;
     }
     __syncthreads();
 
     // ---- flush the J box
     const int js[3] = { c0[0] + g.o[0] - T::H - 1, c0[1] + g.o[1] - T::H - 1, c0[2] + g.o[2] - T::H - 1 };
     for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) {
-        const double v = sJ[t];
-        if( v == 0. ) continue;
+        const long long iv = ( long long )sJ[t];
+        if( iv == 0 ) continue;
+        const double v = ( double )iv*a.jinv;
         const int c = t / T::JVOL;
         int r = t - c*T::JVOL;
         const int k = r % T::JZ; r /= T::JZ;
@@ -866,16 +961,32 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     a.sc_E = p->sc_E; a.sc_B = p->sc_B; a.sc_invgf = p->sc_invgf; a.sc_delta = p->sc_delta; a.sc_iold = p->sc_iold;
     a.n = s.n;
     a.one_over_mass = 1.0/s.mass;                      // Pusher.cpp:20
-    a.tiles[0] = ( g.ncell[0] + TX - 1 )/TX;
-    a.tiles[1] = ( g.ncell[1] + TY - 1 )/TY;
-    a.tiles[2] = ( g.ncell[2] + TZ - 1 )/TZ;
-    const int ntiles = a.tiles[0]*a.tiles[1]*a.tiles[2];
-    if( g.order == 2 ) {
-        // SB200_DYN_GENERAL=1 selects the general (any-order) kernel for order 2 too: A/B checks only
-        static const bool general = getenv( "SB200_DYN_GENERAL" ) != nullptr;
-        if( !general ) return launch_o2_pusher( p, a, ntiles, s.pusher, scratch );
-        return launch_pusher<2>( p, a, ntiles, s.pusher, scratch );
+    {
+        // |J box entry| <= (particles whose window can reach a node) * max|q w|/V * max(d/dt): a node is reached
+        // from (2H+3)^3 cells, each holding at most s.maxcount particles; |C| <= cr and |W| <= 1.
+        const int reach = g.order + 3;
+        const double dmax = fmax( g.d_ov_dt[0], fmax( g.d_ov_dt[1], g.d_ov_dt[2] ) );
+        const double bound = ( double )reach*reach*reach*( double )( s.maxcount > 0 ? s.maxcount : 1 )*s.qwmax*g.inv_cell_volume*dmax;
+        int e = 0;
+        frexp( bound > 0. ? bound : 1., &e );          // bound < 2^e
+        a.jscale = ldexp( 1.0, 61 - e );                // bound*jscale < 2^61
+        a.jinv = ldexp( 1.0, e - 61 );
     }
+    // SB200_DYN_GENERAL=1 selects the general (any-order) kernel for order 2 too: A/B checks only
+    static const bool general = getenv( "SB200_DYN_GENERAL" ) != nullptr;
+    if( g.order == 2 && !general ) {
+        using T = TileO2;
+        a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
+        a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
+        a.tiles[2] = ( g.ncell[2] + T::TZ - 1 )/T::TZ;
+        return launch_o2_pusher( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
+    }
+    using T = Tile<2>;                        // same tile footprint for both orders of the general kernel
+    a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
+    a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
+    a.tiles[2] = ( g.ncell[2] + T::TZ - 1 )/T::TZ;
+    const int ntiles = a.tiles[0]*a.tiles[1]*a.tiles[2];
+    if( g.order == 2 ) return launch_pusher<2>( p, a, ntiles, s.pusher, scratch );
     return launch_pusher<4>( p, a, ntiles, s.pusher, scratch );
 }
 

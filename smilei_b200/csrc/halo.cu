@@ -296,8 +296,9 @@ int sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, siz
     k_arrive<<<blocks, 256, 0, p->stream>>>( p->gd, out, s.n, dev_buf, n, p->leave_counts + 8*ispec );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
+    const size_t n0 = s.n;
     s.n += n;
-    return 0;
+    return update_qwmax( p, ispec, n0, n );
 }
 
 } // extern "C"

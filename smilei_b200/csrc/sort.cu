@@ -14,6 +14,7 @@
 //   k_cell_sort   ascending insertion sort of each cell's run of perm        (restores stability)
 //   k_gather      out[c][j] = in[c][perm[j]] for the 9 columns               124 B/particle
 #include "common.cuh"
+#include <cstring>
 
 namespace sb200 {
 
@@ -144,6 +145,39 @@ __global__ void __launch_bounds__( 128 ) k_cell_sort( const int *__restrict__ fi
     }
 }
 
+__global__ void __launch_bounds__( 256 ) k_max_count( const int *__restrict__ first, int ncells, int *__restrict__ out )
+{
+    int m = 0;
+    for( int c = blockIdx.x*blockDim.x + threadIdx.x; c < ncells; c += gridDim.x*blockDim.x ) m = max( m, first[c+1] - first[c] );
+#pragma unroll
+    for( int d=16; d>0; d>>=1 ) m = max( m, __shfl_xor_sync( 0xffffffffu, m, d ) );
+    if( ( threadIdx.x & 31 ) == 0 && m > 0 ) atomicMax( out, m );
+}
+
+// max |q*w| over a range of particles, folded into a device scalar holding the bits of a positive double
+// (positive doubles order like their bit patterns)
+__global__ void __launch_bounds__( 256 ) k_qwmax( const double *__restrict__ w, const short *__restrict__ q, size_t first, size_t n,
+        unsigned long long *__restrict__ out )
+{
+    double m = 0.;
+    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < n; i += ( size_t )gridDim.x*blockDim.x )
+        m = fmax( m, fabs( ( double )q[first+i]*w[first+i] ) );
+#pragma unroll
+    for( int d=16; d>0; d>>=1 ) m = fmax( m, __shfl_xor_sync( 0xffffffffu, m, d ) );
+    if( ( threadIdx.x & 31 ) == 0 && m > 0. ) atomicMax( out, ( unsigned long long )__double_as_longlong( m ) );
+}
+
+int update_qwmax( sb200_patch *p, int ispec, size_t first, size_t n )
+{
+    SpeciesDev &s = p->sp[ispec];
+    if( n == 0 ) return 0;
+    const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*8 ? ( n + 255 )/256 : 148*8 );
+    k_qwmax<<<blocks, 256, 0, p->stream>>>( s.col[6], s.q, first, n, s.d_qwmax );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    return 0;
+}
+
 struct Cols { double *c[7]; short *q; int *key; };
 
 __global__ void __launch_bounds__( 256 ) k_gather( Cols in, Cols out, const int *__restrict__ perm, size_t n )
@@ -179,7 +213,14 @@ int launch_sort( sb200_patch *p, int ispec )
     // first = exclusive scan(count) over ncells+1 entries (last = total kept)
     if( exclusive_scan_int( p, p->count, p->ncells+1 ) ) return 1;
     SB200_CUDA( cudaMemcpyAsync( s.first, p->count, ( p->ncells+1 )*sizeof( int ), cudaMemcpyDeviceToDevice, p->stream ) );
-    int kept = 0, flags[8];
+    int kept = 0, flags[8], maxcount = 0;
+    unsigned long long qwbits = 0;
+    SB200_CUDA( cudaMemsetAsync( p->d_maxcount, 0, sizeof( int ), p->stream ) );
+    k_max_count<<<148*8, 256, 0, p->stream>>>( s.first, ncells, p->d_maxcount );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    SB200_CUDA( cudaMemcpyAsync( &maxcount, p->d_maxcount, sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+    SB200_CUDA( cudaMemcpyAsync( &qwbits, s.d_qwmax, sizeof( qwbits ), cudaMemcpyDeviceToHost, p->stream ) );
     SB200_CUDA( cudaMemcpyAsync( &kept, s.first + p->ncells, sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
     SB200_CUDA( cudaMemcpyAsync( flags, p->iflags, 8*sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
     if( n > 0 ) {
@@ -209,6 +250,8 @@ int launch_sort( sb200_patch *p, int ispec )
     }
     s.n = ( size_t )kept;
     s.sorted = true;
+    s.maxcount = maxcount;
+    { double v; memcpy( &v, &qwbits, sizeof( v ) ); s.qwmax = v; }
     return 0;
 }
 

@@ -33,6 +33,7 @@ for it in range(steps):
     p.restart_rhoJ(); e.append(ev())
     p.dynamics(0); e.append(ev())
     p.dynamics(1); e.append(ev())
+    if it == steps - 1: print('flags after dynamics', p.debug_flags(), flush=True)
     for s in range(2):
         for dim in range(3):
             for side in (0, 1):
