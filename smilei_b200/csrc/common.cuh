@@ -64,6 +64,8 @@ struct SpeciesDev {
     bool   sorted = false;
     int    maxcount = 0;       // most particles in one cell (after the last sort)
     double qwmax = 0.;         // max |charge*weight| seen in this species
+    int    *leave_idx = nullptr;   // [6][leave_cap] indices of the particles tagged -2..-7, in the order the atomics served them
+    size_t leave_cap = 0;
     unsigned long long *d_qwmax = nullptr;   // device copy kept up to date by imports / arrivals (bits of a positive double)
 };
 

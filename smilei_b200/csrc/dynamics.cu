@@ -89,6 +89,8 @@ struct DynArgs {
     const double *F[6];       // Ex Ey Ez Bxm Bym Bzm
     double *J[3];
     int    *leave_counts;
+    int    *leave_idx;        // [6][leave_cap]
+    int     leave_cap;
     int    *iflags;
     double *sc_E, *sc_B, *sc_invgf, *sc_delta;
     int    *sc_iold;
@@ -97,6 +99,14 @@ struct DynArgs {
     double  jscale, jinv;     // fixed-point scale of the J box and its inverse
     int     tiles[3];
 };
+
+// a particle tagged for exchange: count it and remember its index (sb200_leaving_pack orders the list)
+__device__ __forceinline__ void note_leaver( const DynArgs &a, int tag, size_t ip )
+{
+    const int t = -tag-2;
+    const int c = atomicAdd( &a.leave_counts[t], 1 );
+    if( c < a.leave_cap ) a.leave_idx[( size_t )t*a.leave_cap + c] = ( int )ip;
+}
 
 // separable gather of one component from its staged box: sum_i cx[i] sum_j cy[j] sum_k cz[k] F
 template<class T>
@@ -418,7 +428,7 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
         }
         int key = tag;
         if( tag == 0 ) key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2];
-        else atomicAdd( &a.leave_counts[-tag-2], 1 );
+        else note_leaver( a, tag, ip );
         a.key[ip] = key;
 
         // ---- currents (Esirkepov), accumulated in the tile's J box
@@ -795,7 +805,7 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
             }
             int key = tag;
             if( tag == 0 ) key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2];
-            else atomicAdd( &a.leave_counts[-tag-2], 1 );
+            else note_leaver( a, tag, ip );
             a.key[ip] = key;
 
             const double charge_weight = g.inv_cell_volume*( double )charge*weight;
@@ -957,6 +967,8 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     for( int c=0; c<6; c++ ) a.F[c] = p->f[fid[c]];
     a.J[0] = p->f[SB200_JX]; a.J[1] = p->f[SB200_JY]; a.J[2] = p->f[SB200_JZ];
     a.leave_counts = p->leave_counts + 8*ispec;
+    a.leave_idx = s.leave_idx;
+    a.leave_cap = ( int )s.leave_cap;
     a.iflags = p->iflags;
     a.sc_E = p->sc_E; a.sc_B = p->sc_B; a.sc_invgf = p->sc_invgf; a.sc_delta = p->sc_delta; a.sc_iold = p->sc_iold;
     a.n = s.n;

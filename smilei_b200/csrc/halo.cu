@@ -148,7 +148,7 @@ __global__ void __launch_bounds__( CP_T ) k_leave_write( ConstCols in, const int
 struct MutCols { double *c[7]; short *q; int *key; };
 
 __global__ void __launch_bounds__( 256 ) k_arrive( GridDev g, MutCols out, size_t n0, const double *__restrict__ buf, size_t n,
-        int *__restrict__ leave_counts )
+        int *__restrict__ leave_counts, int *__restrict__ leave_idx, int leave_cap )
 {
     for( size_t t = blockIdx.x*( size_t )blockDim.x + threadIdx.x; t < n; t += ( size_t )gridDim.x*blockDim.x ) {
         const double *r = buf + t*SB200_PARTICLE_RECORD_DOUBLES;
@@ -158,8 +158,38 @@ __global__ void __launch_bounds__( 256 ) k_arrive( GridDev g, MutCols out, size_
         out.q[i] = ( short )r[7];
         const int k = tag_or_key( g, r[0], r[1], r[2] );
         out.key[i] = k;
-        if( k < 0 ) atomicAdd( &leave_counts[-k-2], 1 );
+        if( k < 0 ) {
+            const int c = atomicAdd( &leave_counts[-k-2], 1 );
+            if( c < leave_cap ) leave_idx[( size_t )( -k-2 )*leave_cap + c] = ( int )i;
+        }
     }
+}
+
+// Leavers of one (dim, side) from the index list the dynamics kernel / arrivals filled in atomic order:
+// each entry finds its rank (number of listed indices below its own) by brute force - the list is a
+// boundary layer's worth of particles - and writes its record there, so the packed order is the index
+// order whatever order the atomics were served in.
+__global__ void __launch_bounds__( 256 ) k_rank_pack( ConstCols in, const int *__restrict__ list, int m, int dim, double wrap,
+        double lo, double hi, double *__restrict__ buf )
+{
+    __shared__ int tile[256];
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int mine = t < m ? list[t] : 0x7fffffff;
+    int rank = 0;
+    for( int base = 0; base < m; base += 256 ) {
+        __syncthreads();
+        tile[threadIdx.x] = base + threadIdx.x < m ? list[base + threadIdx.x] : 0x7fffffff;
+        __syncthreads();
+        const int lim = min( 256, m - base );
+        for( int j=0; j<lim; j++ ) rank += tile[j] < mine;
+    }
+    if( t >= m ) return;
+    double *r = buf + ( size_t )rank*SB200_PARTICLE_RECORD_DOUBLES;
+#pragma unroll
+    for( int cc=0; cc<7; cc++ ) r[cc] = in.c[cc][mine];
+    if( wrap > 0. ) { if( r[dim] < lo ) r[dim] += wrap; }
+    else if( wrap < 0. ) { if( r[dim] >= hi ) r[dim] += wrap; }
+    r[7] = ( double )in.q[mine];
 }
 
 } // namespace sb200
@@ -254,6 +284,29 @@ int sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wra
     *n_packed = 0;
     if( s.n == 0 ) return 0;
     const int tag = -2 - 2*dim - side;
+    const GridDev &g = p->gd;
+    const double hi = g.cell[dim]*( double )( g.n[dim]*g.npatch[dim] );   // Patch.cpp:626: cell_length*global_size
+    ConstCols in;
+    for( int c=0; c<7; c++ ) in.c[c] = s.col[c];
+    in.q = s.q;
+    {
+        // fast path: the tagged particles were listed when they were tagged
+        int cnt = 0;
+        SB200_CUDA( cudaMemcpyAsync( &cnt, p->leave_counts + 8*ispec + ( -tag-2 ), sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+        SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+        if( ( size_t )cnt <= s.leave_cap && cnt <= 200000 ) {
+            SB200_CHECK( ( size_t )cnt <= max_records, "sb200_leaving_pack: buffer too small for the leaving particles" );
+            if( cnt > 0 ) {
+                SB200_CHECK( dev_buf, "sb200_leaving_pack: null buffer" );
+                k_rank_pack<<<( cnt + 255 )/256, 256, 0, p->stream>>>( in, s.leave_idx + ( size_t )( -tag-2 )*s.leave_cap, cnt, dim, wrap, 0., hi, dev_buf );
+                sb200::g_launches++;
+                SB200_CUDA( cudaGetLastError() );
+            }
+            *n_packed = ( size_t )cnt;
+            return 0;
+        }
+    }
+    // general path (list overflow or very many leavers): stable compaction over all keys
     const size_t nb = ( s.n + CP_B - 1 )/CP_B;
     if( ensure_perm( p, nb + 1 > s.cap ? nb + 1 : s.cap ) ) return 1;
     int *bc = p->perm;             // perm is free between sorts
@@ -268,11 +321,6 @@ int sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wra
     SB200_CHECK( ( size_t )total <= max_records, "sb200_leaving_pack: buffer too small for the leaving particles" );
     if( total > 0 ) {
         SB200_CHECK( dev_buf, "sb200_leaving_pack: null buffer" );
-        ConstCols in;
-        for( int c=0; c<7; c++ ) in.c[c] = s.col[c];
-        in.q = s.q;
-        const GridDev &g = p->gd;
-        const double hi = g.cell[dim]*( double )( g.n[dim]*g.npatch[dim] );   // Patch.cpp:626: cell_length*global_size
         k_leave_write<<<( unsigned )nb, CP_T, 0, p->stream>>>( in, s.key, s.n, tag, dim, wrap, 0., hi, bc, dev_buf, max_records );
         sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
@@ -293,7 +341,7 @@ int sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, siz
     for( int c=0; c<7; c++ ) out.c[c] = s.col[c];
     out.q = s.q; out.key = s.key;
     const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*8 ? ( n + 255 )/256 : 148*8 );
-    k_arrive<<<blocks, 256, 0, p->stream>>>( p->gd, out, s.n, dev_buf, n, p->leave_counts + 8*ispec );
+    k_arrive<<<blocks, 256, 0, p->stream>>>( p->gd, out, s.n, dev_buf, n, p->leave_counts + 8*ispec, s.leave_idx, ( int )s.leave_cap );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     const size_t n0 = s.n;

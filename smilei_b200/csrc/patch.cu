@@ -182,6 +182,7 @@ int sb200_patch_destroy( sb200_patch *p )
         free_particle_cols( p->sp[s].col, &p->sp[s].q, &p->sp[s].key );
         if( p->sp[s].first ) cudaFree( p->sp[s].first );
         if( p->sp[s].d_qwmax ) cudaFree( p->sp[s].d_qwmax );
+        if( p->sp[s].leave_idx ) cudaFree( p->sp[s].leave_idx );
     }
     free_particle_cols( p->spare.col, &p->spare.q, &p->spare.key );
     void *misc[] = { p->count, p->cursor, p->perm, p->blocksums, p->stage, p->red, p->leave_counts, p->iflags, p->d_maxcount,
@@ -222,6 +223,15 @@ int sb200_species_config( sb200_patch *p, int ispec, double mass, int pusher, si
         free_particle_cols( s.col, &s.q, &s.key );
         if( alloc_particle_cols( s.col, &s.q, &s.key, capacity ) ) return 1;
         s.cap = capacity;
+    }
+    {
+        const size_t want = capacity/64 > ( size_t )65536 ? capacity/64 : ( size_t )65536;
+        if( want > s.leave_cap ) {
+            if( s.leave_idx ) cudaFree( s.leave_idx );
+            s.leave_idx = nullptr; s.leave_cap = 0;
+            SB200_CUDA( cudaMalloc( &s.leave_idx, 6*want*sizeof( int ) ) );
+            s.leave_cap = want;
+        }
     }
     if( !s.d_qwmax ) {
         SB200_CUDA( cudaMalloc( &s.d_qwmax, sizeof( unsigned long long ) ) );
