@@ -485,35 +485,54 @@ static int launch_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int push
 }
 
 // =================================================================================================
-// Order-2 fast kernel.
+// Cell-group kernel, orders 2 and 4.
 //
-// What binds the general kernel above is not HBM: every particle issues ~100 non-zero double
-// atomics on shared memory (compare-and-swap loops on sm_100), all lanes of a warp on the same few
-// addresses because sorted neighbours sit in the same cell.  This kernel removes them from the
-// common case:
-//   * tile of 8x8x8 cells per CTA (staging and flush amortised over ~8k particles);
+// What binds the general kernel above is not HBM: every particle issues (ORDER+2)*(ORDER+3)^2 accumulations
+// per current component on shared memory, all lanes of a warp on the same few addresses because sorted
+// neighbours sit in the same cell.  This kernel removes them from the common case:
 //   * work item = (cell, round): G = 8 consecutive lanes take up to 8 particles OF THE SAME CELL;
-//   * a particle whose primal node does not change during the step (the large majority in a
-//     thermal plasma: |dx| << 1 cell) deposits only on the 3x3x3 nodes around its cell: 2x3x3 values
-//     per current component.  They are computed in registers, summed over the 8 lanes with a shuffle
-//     transpose-reduction (18 -> 9 -> 5 -> 3 values per lane), and only the per-cell sums reach the
-//     tile's J box in shared memory (3 atomics per lane per component per round);
-//   * particles that do change cell are deposited by their own 8-lane group, one at a time and up to
-//     four groups of the warp concurrently: their Esirkepov window is exactly 4 points wide per
-//     dimension (S0 on 1..3, S1 shifted by -1/0/+1), so each lane takes 2 of the 4x4 transverse
-//     positions and the 3 non-zero flux points of each component.
+//   * a particle whose primal node does not change during the step (the large majority in a thermal
+//     plasma: |dx| << 1 cell) deposits only on the NW^3 nodes its shape covers (NW = ORDER+1): per current
+//     component NW-1 flux points x NW x NW values.  They are formed in registers, NV at a time, summed over
+//     the 8 lanes with a shuffle transpose-reduction (order 2: 18 -> 9 -> 5 -> 3 values per lane; order 4:
+//     25 -> 13 -> 7 -> 4, once per flux point), and only the per-cell sums reach the tile's J box;
+//   * particles that do change cell go to a per-warp queue; whenever four are pending the warp deposits them,
+//     one per 8-lane group: their Esirkepov window is exactly NW+1 points wide per dimension (S0 on 1..NW, S1
+//     shifted by -1/0/+1), each lane takes a share of the (NW+1)^2 transverse positions and the NW non-zero
+//     flux points of each component.
 // Gather, push, boundary tagging and next-key computation are as in the general kernel.
 // =================================================================================================
-using TileO2 = Tile<2, 4, 8, 8>;
 constexpr int GRP = 8;                                   // lanes per cell group
-constexpr int NCELL_O2 = TileO2::TX*TileO2::TY*TileO2::TZ;   // 256
-constexpr int XSCR = 24;                                 // doubles of crosser scratch per lane group: S0[3][4], DS[3][4]
 constexpr int XQ = 16;                                   // cell-crossers a warp can keep pending
 constexpr int XQD = 9*XQ + XQ/2;                         // doubles per warp queue: deltaold[3], new pos[3], cr[3] (SoA) + XQ ints
 
-struct O2Smem {
-    static constexpr size_t BYTES = ( size_t )( 6*TileO2::FVOL + 3*TileO2::JVOL + XSCR*( DYN_THREADS/GRP ) + XQD*( DYN_THREADS/32 ) )*sizeof( double );
+template<int ORDER> struct CG;
+template<> struct CG<2> {
+    using T = Tile<2, 4, 8, 8>;
+    static constexpr int NSL = 2;      // flux points reduced together
+    static constexpr int MINB = 2;     // CTAs per SM asked of the compiler
+    static constexpr int LOG2CELLS = 8;
 };
+template<> struct CG<4> {
+    using T = Tile<4, 4, 4, 8>;
+    static constexpr int NSL = 1;
+    static constexpr int MINB = 1;
+    static constexpr int LOG2CELLS = 7;
+};
+template<int ORDER> struct CGDim {
+    using T = typename CG<ORDER>::T;
+    static constexpr int NW = ORDER+1;                     // non-zero shape points
+    static constexpr int NSL = CG<ORDER>::NSL;
+    static constexpr int NPASS = ( NW-1 )/NSL;             // reductions per component
+    static constexpr int NV = NSL*NW*NW;                   // values reduced together (18 or 25)
+    static constexpr int N1 = ( NV+1 )/2, N2 = ( N1+1 )/2, NS = ( N2+1 )/2;   // after each of the 3 steps
+    static constexpr int WX = NW+1;                        // crosser window width
+    static constexpr int XSCR = 6*WX;                      // crosser scratch per lane group: S0[3][WX], DS[3][WX]
+    static constexpr int NCELL = T::TX*T::TY*T::TZ;
+    static constexpr int CPT = ( NCELL + DYN_THREADS - 1 )/DYN_THREADS;
+    static constexpr size_t BYTES = ( size_t )( 6*T::FVOL + 3*T::JVOL + XSCR*( DYN_THREADS/GRP ) + XQD*( DYN_THREADS/32 ) )*sizeof( double );
+};
+using TileO2 = CG<2>::T;
 
 // one step of the transpose-reduction: N values -> (N+1)/2 values; lanes with `upper` keep the second half
 template<int N>
@@ -530,38 +549,28 @@ __device__ __forceinline__ void xr_step( double *v, int lane_mask, bool upper )
     }
 }
 
-// 2x3x3 contributions of a non-crossing particle for one current component:
-// flux dimension f, transverse dimensions a (slow) and b (fast).  S0/DS hold the 3 non-zero
-// window entries (window indices 1..3).  C[i] = -cr*sum_{i'<i} DS[i'] is non-zero for i = 2,3 only.
-__device__ __forceinline__ void o2_contrib( double *v, double cr, const double *DSf, const double *S0a, const double *DSa,
-                                            const double *S0b, const double *DSb )
+// select w[t] for a run-time t (registers cannot be indexed dynamically), 0 outside [0,N)
+template<int N>
+__device__ __forceinline__ double pick( const double *w, int t )
 {
-    const double third = 1./3.;
-    const double C2 = -cr*DSf[0];
-    const double C3 = C2 - cr*DSf[1];
-    double A[3], B[3];
+    double r = 0.;
 #pragma unroll
-    for( int k=0; k<3; k++ ) { A[k] = S0b[k] + 0.5*DSb[k]; B[k] = 0.5*S0b[k] + third*DSb[k]; }
-#pragma unroll
-    for( int j=0; j<3; j++ ) {
-#pragma unroll
-        for( int k=0; k<3; k++ ) {
-            const double W = S0a[j]*A[k] + DSa[j]*B[k];
-            v[j*3+k] = C2*W;
-            v[9+j*3+k] = C3*W;
-        }
-    }
+    for( int i=0; i<N; i++ ) r = t == i ? w[i] : r;
+    return r;
 }
 
 // One pass over the warp's crosser queue: lane group `grp` (0..3) deposits entry head+grp if it exists.
-// The Esirkepov window of a particle that changed cell is exactly 4 points wide per dimension, starting at
-// lo = (shift<0 ? 0 : 1): S0 on window points 1..3, S1 on 1+shift..3+shift.  Lanes 0..2 of the group
-// evaluate S0/DS of one dimension each into the group's scratch; then every lane takes 2 of the 4x4
-// transverse positions and the 3 non-zero flux points (lo+1..lo+3) of each current component.
-__device__ __forceinline__ void o2_cross_pass( jbox_t *sJ, const double *xq, const int *xqm, double *xscr, int qh, int qn,
-                                               int gl, int grp, const int *c0, const GridDev &g, double jscale )
+// The Esirkepov window of a particle that changed cell is exactly WX = NW+1 points wide per dimension,
+// starting at lo = (shift<0 ? 0 : 1): S0 on window points 1..NW, S1 on 1+shift..NW+shift.  Lanes 0..2 of
+// the group evaluate S0/DS of one dimension each into the group's scratch; then every lane takes its share
+// of the WX x WX transverse positions and the NW non-zero flux points (lo+1..lo+NW) of each component.
+template<int ORDER>
+__device__ __forceinline__ void cross_pass( jbox_t *sJ, const double *xq, const int *xqm, double *xscr, int qh, int qn,
+                                            int gl, int grp, double jscale )
 {
-    using T = TileO2;
+    using D = CGDim<ORDER>;
+    using T = typename D::T;
+    constexpr int NW = D::NW, WX = D::WX;
     const bool work = grp < qn;
     const int e = ( qh + ( work ? grp : 0 ) ) % XQ;
     const int meta = xqm[e];
@@ -571,17 +580,16 @@ __device__ __forceinline__ void o2_cross_pass( jbox_t *sJ, const double *xq, con
         const double dl0 = xq[( 0+d )*XQ+e];
         const double pn  = xq[( 3+d )*XQ+e];
         const int shift = ( ( bsh >> ( 2*d ) ) & 3 ) - 1;
-        double w0[3], w1[3];
-        Shape<2>::w( dl0, w0 );
-        Shape<2>::w( pn - round( pn ), w1 );
+        double w0[NW], w1[NW];
+        Shape<ORDER>::w( dl0, w0 );
+        Shape<ORDER>::w( pn - round( pn ), w1 );
         const int lo_ = shift < 0 ? 0 : 1;
 #pragma unroll
-        for( int s=0; s<4; s++ ) {
-            const int t0 = lo_ + s - 1, t1 = lo_ + s - 1 - shift;
-            const double s0 = t0 == 0 ? w0[0] : t0 == 1 ? w0[1] : t0 == 2 ? w0[2] : 0.;
-            const double s1 = t1 == 0 ? w1[0] : t1 == 1 ? w1[1] : t1 == 2 ? w1[2] : 0.;
-            xscr[d*4+s] = s0;
-            xscr[12+d*4+s] = s1 - s0;
+        for( int s=0; s<WX; s++ ) {
+            const double s0 = pick<NW>( w0, lo_ + s - 1 );
+            const double s1 = pick<NW>( w1, lo_ + s - 1 - shift );
+            xscr[d*WX+s] = s0;
+            xscr[3*WX+d*WX+s] = s1 - s0;
         }
     }
     __syncwarp();
@@ -591,40 +599,55 @@ __device__ __forceinline__ void o2_cross_pass( jbox_t *sJ, const double *xq, con
         const int lo0 = ( ( bsh      ) & 3 ) == 0 ? 0 : 1;
         const int lo1 = ( ( bsh >> 2 ) & 3 ) == 0 ? 0 : 1;
         const int lo2 = ( ( bsh >> 4 ) & 3 ) == 0 ? 0 : 1;
-        const double *S0x = xscr, *S0y = xscr+4, *S0z = xscr+8, *DSx = xscr+12, *DSy = xscr+16, *DSz = xscr+20;
+        const double *S0x = xscr, *S0y = xscr+WX, *S0z = xscr+2*WX, *DSx = xscr+3*WX, *DSy = xscr+4*WX, *DSz = xscr+5*WX;
         jbox_t *xb = sJ + ( ( cl[0]+lo0 )*T::JY + ( cl[1]+lo1 ) )*T::JZ + ( cl[2]+lo2 );
         const double c0x = xq[6*XQ+e]*jscale, c1y = xq[7*XQ+e]*jscale, c2z = xq[8*XQ+e]*jscale;   // fixed-point scale folded in
-        const double Cx1 = -c0x*DSx[0], Cx2 = Cx1 - c0x*DSx[1], Cx3 = Cx2 - c0x*DSx[2];
-        const double Cy1 = -c1y*DSy[0], Cy2 = Cy1 - c1y*DSy[1], Cy3 = Cy2 - c1y*DSy[2];
-        const double Cz1 = -c2z*DSz[0], Cz2 = Cz1 - c2z*DSz[1], Cz3 = Cz2 - c2z*DSz[2];
+        double Cx[NW], Cy[NW], Cz[NW];     // flux coefficients at window points lo+1 .. lo+NW
+        {
+            double rx = 0., ry = 0., rz = 0.;
 #pragma unroll
-        for( int h=0; h<2; h++ ) {
-            const int pp = gl + 8*h, aa = pp >> 2, bb = pp & 3;
-            const double Az = S0z[bb] + 0.5*DSz[bb], Bz = 0.5*S0z[bb] + third*DSz[bb];
-            const double Wx = S0y[aa]*Az + DSy[aa]*Bz;                                                       // Jx: W(j=aa,k=bb)
-            const double Wy = S0x[aa]*Az + DSx[aa]*Bz;                                                       // Jy: W(i=aa,k=bb)
-            const double Wz = S0x[aa]*( S0y[bb] + 0.5*DSy[bb] ) + DSx[aa]*( 0.5*S0y[bb] + third*DSy[bb] );   // Jz: W(i=aa,j=bb)
-            jbox_t *qx = xb + 0*T::JVOL + ( 1*T::JY + aa )*T::JZ + bb;      // flux points lo0+1..lo0+3
-            jbox_t *qy = xb + 1*T::JVOL + ( aa*T::JY + 1 )*T::JZ + bb;      // flux points lo1+1..lo1+3
-            jbox_t *qz = xb + 2*T::JVOL + ( aa*T::JY + bb )*T::JZ + 1;      // flux points lo2+1..lo2+3
-            jadd_scaled( qx, Cx1*Wx ); jadd_scaled( qx + T::JY*T::JZ, Cx2*Wx ); jadd_scaled( qx + 2*T::JY*T::JZ, Cx3*Wx );
-            jadd_scaled( qy, Cy1*Wy ); jadd_scaled( qy + T::JZ, Cy2*Wy ); jadd_scaled( qy + 2*T::JZ, Cy3*Wy );
-            jadd_scaled( qz, Cz1*Wz ); jadd_scaled( qz + 1, Cz2*Wz ); jadd_scaled( qz + 2, Cz3*Wz );
+            for( int f=0; f<NW; f++ ) {
+                rx -= c0x*DSx[f]; ry -= c1y*DSy[f]; rz -= c2z*DSz[f];
+                Cx[f] = rx; Cy[f] = ry; Cz[f] = rz;
+            }
+        }
+#pragma unroll
+        for( int h=0; h<( WX*WX + GRP - 1 )/GRP; h++ ) {
+            const int pp = gl + GRP*h;
+            if( pp < WX*WX ) {
+                const int aa = pp / WX, bb = pp % WX;
+                const double Az = S0z[bb] + 0.5*DSz[bb], Bz = 0.5*S0z[bb] + third*DSz[bb];
+                const double Wx = S0y[aa]*Az + DSy[aa]*Bz;                                                       // Jx: W(j=aa,k=bb)
+                const double Wy = S0x[aa]*Az + DSx[aa]*Bz;                                                       // Jy: W(i=aa,k=bb)
+                const double Wz = S0x[aa]*( S0y[bb] + 0.5*DSy[bb] ) + DSx[aa]*( 0.5*S0y[bb] + third*DSy[bb] );   // Jz: W(i=aa,j=bb)
+                jbox_t *qx = xb + 0*T::JVOL + ( 1*T::JY + aa )*T::JZ + bb;      // flux points lo0+1..
+                jbox_t *qy = xb + 1*T::JVOL + ( aa*T::JY + 1 )*T::JZ + bb;      // flux points lo1+1..
+                jbox_t *qz = xb + 2*T::JVOL + ( aa*T::JY + bb )*T::JZ + 1;      // flux points lo2+1..
+#pragma unroll
+                for( int f=0; f<NW; f++ ) {
+                    jadd_scaled( qx + f*T::JY*T::JZ, Cx[f]*Wx );
+                    jadd_scaled( qy + f*T::JZ, Cy[f]*Wy );
+                    jadd_scaled( qz + f, Cz[f]*Wz );
+                }
+            }
         }
     }
     __syncwarp();
 }
 
-template<int PUSHER, bool SCRATCH>
-__global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev g, const DynArgs a )
+template<int ORDER, int PUSHER, bool SCRATCH>
+__global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg( const GridDev g, const DynArgs a )
 {
-    using T = TileO2;
+    using D = CGDim<ORDER>;
+    using T = typename D::T;
+    constexpr int NW = D::NW, NCELL = D::NCELL, CPT = D::CPT, NV = D::NV, NS = D::NS, NSL = D::NSL, NPASS = D::NPASS;
     extern __shared__ double smem[];
     double *sF = smem;
     jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FVOL );
-    double *xscr = smem + 6*T::FVOL + 3*T::JVOL + XSCR*( threadIdx.x/GRP );      // this lane group's crosser scratch
-    __shared__ int cell_first[NCELL_O2];
-    __shared__ int round_off[NCELL_O2+1];
+    double *xscr = smem + 6*T::FVOL + 3*T::JVOL + D::XSCR*( threadIdx.x/GRP );      // this lane group's crosser scratch
+    __shared__ int cell_first[NCELL];
+    __shared__ int cell_cnt[NCELL];
+    __shared__ int round_off[NCELL+1];
     __shared__ int warp_tot[DYN_THREADS/32];
 
     const int tid = threadIdx.x;
@@ -635,22 +658,25 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
     const int tx = b / a.tiles[1];
     const int c0[3] = { tx*T::TX, ty*T::TY, tz*T::TZ };
 
-    // ---- per-cell particle runs and the prefix sum of their rounds (2 cells per thread)
+    // ---- per-cell particle runs and the prefix sum of their rounds
     {
         int run = 0;
-        int rounds[NCELL_O2/DYN_THREADS];
+        int rounds[CPT];
 #pragma unroll
-        for( int e=0; e<NCELL_O2/DYN_THREADS; e++ ) {
-            const int ct = tid*( NCELL_O2/DYN_THREADS ) + e;
-            const int lz = ct % T::TZ, ly = ( ct / T::TZ ) % T::TY, lx = ct / ( T::TZ*T::TY );
-            const int ix = c0[0]+lx, iy = c0[1]+ly, iz = c0[2]+lz;
+        for( int e=0; e<CPT; e++ ) {
+            const int ct = tid*CPT + e;
             int beg = 0, cnt = 0;
-            if( ix < g.ncell[0] && iy < g.ncell[1] && iz < g.ncell[2] ) {
-                const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + iz;
-                beg = a.first[cell];
-                cnt = a.first[cell+1] - beg;
+            if( ct < NCELL ) {
+                const int lz = ct % T::TZ, ly = ( ct / T::TZ ) % T::TY, lx = ct / ( T::TZ*T::TY );
+                const int ix = c0[0]+lx, iy = c0[1]+ly, iz = c0[2]+lz;
+                if( ix < g.ncell[0] && iy < g.ncell[1] && iz < g.ncell[2] ) {
+                    const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + iz;
+                    beg = a.first[cell];
+                    cnt = a.first[cell+1] - beg;
+                }
+                cell_first[ct] = beg;
+                cell_cnt[ct] = cnt;
             }
-            cell_first[ct] = beg | ( cnt > 0 ? 0 : 0 );
             rounds[e] = ( cnt + GRP - 1 )/GRP;
             run += rounds[e];
         }
@@ -662,14 +688,14 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
         int off = inc - run;
         for( int w=0; w<( tid >> 5 ); w++ ) off += warp_tot[w];
 #pragma unroll
-        for( int e=0; e<NCELL_O2/DYN_THREADS; e++ ) {
+        for( int e=0; e<CPT; e++ ) {
             off += rounds[e];
-            round_off[tid*( NCELL_O2/DYN_THREADS ) + e + 1] = off;
+            if( tid*CPT + e < NCELL ) round_off[tid*CPT + e + 1] = off;
         }
         if( tid == 0 ) round_off[0] = 0;
     }
     __syncthreads();
-    const int nrounds = round_off[NCELL_O2];
+    const int nrounds = round_off[NCELL];
     if( nrounds == 0 ) return;
 
     // ---- stage the field boxes, clear the J box
@@ -688,27 +714,28 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
     for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0ull;
     __syncthreads();
 
-    // ---- lane geometry of the transpose-reduction: which of the 18 values of a component each of
-    //      this lane's 3 final slots holds, as an offset in the J box relative to the cell base
+    // ---- lane geometry of the transpose-reduction: which of the NV values each of this lane's NS final
+    //      slots holds, as an offset in the J box relative to the cell base (for the first flux pass)
     const int gl = tid & ( GRP-1 );
     const int gid = tid / GRP;
     const bool up4 = gl & 4, up2 = gl & 2, up1 = gl & 1;
-    int joff[3][3];
+    int joff[3][NS];
 #pragma unroll
-    for( int r=0; r<3; r++ ) {
+    for( int r=0; r<NS; r++ ) {
         int idx = r;
         bool ok = true;
-        idx += up1 ? 3 : 0; ok = ok && idx < 5;
-        idx += up2 ? 5 : 0; ok = ok && idx < 9;
-        idx += up4 ? 9 : 0; ok = ok && idx < 18;
-        const int f = idx / 9, aa = ( idx / 3 ) % 3, bb = idx % 3;
+        idx += up1 ? NS : 0;     ok = ok && idx < D::N2;
+        idx += up2 ? D::N2 : 0;  ok = ok && idx < D::N1;
+        idx += up4 ? D::N1 : 0;  ok = ok && idx < NV;
+        const int f = idx / ( NW*NW ), aa = ( idx / NW ) % NW, bb = idx % NW;
         // Jx: flux i = 2+f, (j,k) = (1+aa, 1+bb);  Jy: flux j = 2+f, (i,k) = (1+aa, 1+bb);  Jz: flux k = 2+f, (i,j) = (1+aa, 1+bb)
         joff[0][r] = ok ? 0*T::JVOL + ( ( 2+f )*T::JY + ( 1+aa ) )*T::JZ + ( 1+bb ) : -1;
         joff[1][r] = ok ? 1*T::JVOL + ( ( 1+aa )*T::JY + ( 2+f ) )*T::JZ + ( 1+bb ) : -1;
         joff[2][r] = ok ? 2*T::JVOL + ( ( 1+aa )*T::JY + ( 1+bb ) )*T::JZ + ( 2+f ) : -1;
     }
+    const int fstride[3] = { NSL*T::JY*T::JZ, NSL*T::JZ, NSL };      // J-box stride of one flux pass per component
 
-    double *xq = smem + 6*T::FVOL + 3*T::JVOL + XSCR*( DYN_THREADS/GRP ) + XQD*( tid >> 5 );   // this warp's queue
+    double *xq = smem + 6*T::FVOL + 3*T::JVOL + D::XSCR*( DYN_THREADS/GRP ) + XQD*( tid >> 5 );   // this warp's queue
     int *xqm = reinterpret_cast<int *>( xq + 9*XQ );
     int qh = 0, qn = 0;                                       // queue head / pending entries (warp-uniform)
 
@@ -718,23 +745,17 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
         const int wi = it*NGROUPS + gid;
         const bool have = wi < nrounds;
         // cell of this round: last c with round_off[c] <= wi
-        int lo = 0, hi = NCELL_O2;
+        int lo = 0, hi = NCELL;
         const int wq = have ? wi : 0;
 #pragma unroll
-        for( int st=0; st<8; st++ ) { const int mid = ( lo+hi ) >> 1; if( round_off[mid] <= wq ) lo = mid; else hi = mid; }
+        for( int st=0; st<CG<ORDER>::LOG2CELLS; st++ ) { const int mid = ( lo+hi ) >> 1; if( round_off[mid] <= wq ) lo = mid; else hi = mid; }
         const int cellt = lo;
         const int cl[3] = { cellt / ( T::TZ*T::TY ), ( cellt / T::TZ ) % T::TY, cellt % T::TZ };
-        const int rnd = wq - round_off[cellt];
-        int cnt_cell = 0;
-        if( have ) {
-            const int cell = ( ( c0[0]+cl[0] )*g.ncell[1] + ( c0[1]+cl[1] ) )*g.ncell[2] + ( c0[2]+cl[2] );
-            cnt_cell = a.first[cell+1] - cell_first[cellt];
-        }
-        const int slot = rnd*GRP + gl;
-        const bool active = have && slot < cnt_cell;
+        const int slot = ( wq - round_off[cellt] )*GRP + gl;
+        const bool active = have && slot < cell_cnt[cellt];
         const size_t ip = ( size_t )cell_first[cellt] + ( size_t )( active ? slot : 0 );
 
-        double S0[3][3], DS[3][3], cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
+        double S0[3][NW], DS[3][NW], cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
         int shifts = 0;                       // (shift+1) per dimension, 2 bits each
         bool fast = false;
         if( active ) {
@@ -743,27 +764,27 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
             const double weight = a.col[6][ip];
             const short charge = a.q[ip];
 
-            double cp[3][3], cd[3][3], delta_p[3];
+            double cd[3][NW];
             int sp[3], sd[3];
 #pragma unroll
             for( int d=0; d<3; d++ ) {
                 const double pn = pos[d]*g.dxi[d];
                 const int ipn = ( int )round( pn );
-                delta_p[d] = pn - ( double )ipn;
-                Shape<2>::w( delta_p[d], cp[d] );
+                xdelta[d] = pn - ( double )ipn;
+                Shape<ORDER>::w( xdelta[d], S0[d] );          // primal coefficients = S0 of the deposit
                 const int idn = ( int )round( pn + 0.5 );
                 const double dd = pn - ( double )idn + 0.5;
-                Shape<2>::w( dd, cd[d] );
+                Shape<ORDER>::w( dd, cd[d] );
                 if( ipn - g.begin[d] - g.o[d] - c0[d] != cl[d] ) atomicAdd( &a.iflags[1], 1 );
                 sp[d] = cl[d] + T::H;
                 sd[d] = sp[d] + ( idn - ipn );
             }
-            const double Ex = gather<T>( sF+0*T::FVOL, cd[0], cp[1], cp[2], sd[0], sp[1], sp[2] );
-            const double Ey = gather<T>( sF+1*T::FVOL, cp[0], cd[1], cp[2], sp[0], sd[1], sp[2] );
-            const double Ez = gather<T>( sF+2*T::FVOL, cp[0], cp[1], cd[2], sp[0], sp[1], sd[2] );
-            const double Bx = gather<T>( sF+3*T::FVOL, cp[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
-            const double By = gather<T>( sF+4*T::FVOL, cd[0], cp[1], cd[2], sd[0], sp[1], sd[2] );
-            const double Bz = gather<T>( sF+5*T::FVOL, cd[0], cd[1], cp[2], sd[0], sd[1], sp[2] );
+            const double Ex = gather<T>( sF+0*T::FVOL, cd[0], S0[1], S0[2], sd[0], sp[1], sp[2] );
+            const double Ey = gather<T>( sF+1*T::FVOL, S0[0], cd[1], S0[2], sp[0], sd[1], sp[2] );
+            const double Ez = gather<T>( sF+2*T::FVOL, S0[0], S0[1], cd[2], sp[0], sp[1], sd[2] );
+            const double Bx = gather<T>( sF+3*T::FVOL, S0[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+            const double By = gather<T>( sF+4*T::FVOL, cd[0], S0[1], cd[2], sd[0], sp[1], sd[2] );
+            const double Bz = gather<T>( sF+5*T::FVOL, cd[0], cd[1], S0[2], sd[0], sd[1], sp[2] );
 
             const double cmd = ( double )charge*a.one_over_mass*g.dts2;
             double dxp, dyp, dzp, invgf;
@@ -778,7 +799,7 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
 #pragma unroll
                 for( int d=0; d<3; d++ ) {
                     a.sc_iold[d*a.n+ip] = cl[d] + c0[d] + g.o[d];
-                    a.sc_delta[d*a.n+ip] = delta_p[d];
+                    a.sc_delta[d*a.n+ip] = xdelta[d];
                 }
             }
 
@@ -789,8 +810,8 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
             for( int d=0; d<3; d++ ) {
                 const double pn = npos[d]*g.dxi[d];
                 const int ipn = ( int )round( pn );
-                double w1[3];
-                Shape<2>::w( pn - ( double )ipn, w1 );
+                double w1[NW];
+                Shape<ORDER>::w( pn - ( double )ipn, w1 );
                 const int shift = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );
                 shifts |= ( shift+1 ) << ( 2*d );
                 same = same && shift == 0;
@@ -799,9 +820,9 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
                     if( npos[d] < g.xmin[d] ) tag = -2 - 2*d;
                     else if( npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
                 }
-                xdelta[d] = delta_p[d]; xnpos[d] = pn;
+                xnpos[d] = pn;
 #pragma unroll
-                for( int s=0; s<3; s++ ) { S0[d][s] = cp[d][s]; DS[d][s] = w1[s] - cp[d][s]; }
+                for( int s=0; s<NW; s++ ) DS[d][s] = w1[s] - S0[d][s];
             }
             int key = tag;
             if( tag == 0 ) key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2];
@@ -813,56 +834,58 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
             fast = same;
         }
         jbox_t *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
-        // ---- non-crossing particles: 2x3x3 values per component, summed over the 8 lanes of the cell
-        //      group in registers (all 32 lanes take part in the shuffles); 3 sums per lane and component
-        double fsum[9];
+        // two rounds of the same cell often sit in neighbouring groups of the warp: their sums are added up
+        // below instead of letting their adds collide on identical addresses
+        const int mycell = have ? cellt : -1 - gid;
+        const bool same8 = __shfl_xor_sync( 0xffffffffu, mycell, 8 ) == mycell;
+        const bool own8 = have && !( same8 && ( lane & 8 ) );
+        // every lane must execute both shuffles: no short-circuit evaluation around them
+        const int c16 = __shfl_xor_sync( 0xffffffffu, mycell, 16 );
+        const int o16own = __shfl_xor_sync( 0xffffffffu, ( int )own8, 16 );
+        const bool same16 = c16 == mycell && own8 && o16own != 0;
+        const bool owner = own8 && !( same16 && ( lane & 16 ) );
+        // ---- non-crossing particles: (NW-1) x NW x NW values per component, NV at a time, summed over the 8
+        //      lanes of the cell group in registers (all 32 lanes take part in the shuffles)
 #pragma unroll
         for( int c=0; c<3; c++ ) {
-            double v[18];
+            const int da = c == 0 ? 1 : 0, db = c == 2 ? 1 : 2;      // transverse dimensions (slow, fast)
+            const double third = 1./3.;
+            double A[NW], B[NW], Cf[NW-1];
             if( fast ) {
-                if( c == 0 ) o2_contrib( v, cr[0], DS[0], S0[1], DS[1], S0[2], DS[2] );          // Jx: flux x, (j,k)
-                else if( c == 1 ) o2_contrib( v, cr[1], DS[1], S0[0], DS[0], S0[2], DS[2] );     // Jy: flux y, (i,k)
-                else o2_contrib( v, cr[2], DS[2], S0[0], DS[0], S0[1], DS[1] );                  // Jz: flux z, (i,j)
-            } else {
 #pragma unroll
-                for( int i=0; i<18; i++ ) v[i] = 0.;
+                for( int k=0; k<NW; k++ ) { A[k] = S0[db][k] + 0.5*DS[db][k]; B[k] = 0.5*S0[db][k] + third*DS[db][k]; }
+                double run = 0.;
+#pragma unroll
+                for( int f=0; f<NW-1; f++ ) { run -= cr[c]*DS[c][f]; Cf[f] = run; }
             }
-            xr_step<18>( v, 4, up4 ); xr_step<9>( v, 2, up2 ); xr_step<5>( v, 1, up1 );
 #pragma unroll
-            for( int r=0; r<3; r++ ) fsum[c*3+r] = v[r];
-        }
-        // two rounds of the same cell often sit in neighbouring groups of the warp: add them up here
-        // instead of letting their atomics collide on identical addresses
-        bool owner = have;
-        {
-            const int mycell = have ? cellt : -1 - gid;
-            const int c8 = __shfl_xor_sync( 0xffffffffu, mycell, 8 );
-            const bool same8 = c8 == mycell;
+            for( int ps=0; ps<NPASS; ps++ ) {
+                double v[NV];
+                if( fast ) {
 #pragma unroll
-            for( int i=0; i<9; i++ ) { const double o = __shfl_xor_sync( 0xffffffffu, fsum[i], 8 ); if( same8 ) fsum[i] += o; }
-            if( same8 && ( lane & 8 ) ) owner = false;
-            const int c16 = __shfl_xor_sync( 0xffffffffu, mycell, 16 );
-            const bool own16 = __shfl_xor_sync( 0xffffffffu, ( int )owner, 16 ) != 0;
-            const bool same16 = c16 == mycell && owner && own16;
+                    for( int fl=0; fl<NSL; fl++ )
 #pragma unroll
-            for( int i=0; i<9; i++ ) { const double o = __shfl_xor_sync( 0xffffffffu, fsum[i], 16 ); if( same16 ) fsum[i] += o; }
-            if( same16 && ( lane & 16 ) ) owner = false;
-        }
-        {
-            jbox_t *ad[9];
-            bool doit[9];
+                        for( int j=0; j<NW; j++ )
 #pragma unroll
-            for( int c=0; c<3; c++ )
+                            for( int k=0; k<NW; k++ )
+                                v[( fl*NW + j )*NW + k] = Cf[ps*NSL+fl]*( S0[da][j]*A[k] + DS[da][j]*B[k] );
+                } else {
 #pragma unroll
-                for( int r=0; r<3; r++ ) {
-                    ad[c*3+r] = jb + ( joff[c][r] >= 0 ? joff[c][r] : 0 );
-                    doit[c*3+r] = owner && joff[c][r] >= 0 && fsum[c*3+r] != 0.;
+                    for( int i=0; i<NV; i++ ) v[i] = 0.;
                 }
+                xr_step<NV>( v, 4, up4 ); xr_step<D::N1>( v, 2, up2 ); xr_step<D::N2>( v, 1, up1 );
 #pragma unroll
-            for( int i=0; i<9; i++ ) if( doit[i] ) jadd( ad[i], fsum[i], a.jscale );
+                for( int r=0; r<NS; r++ ) {
+                    const double o8 = __shfl_xor_sync( 0xffffffffu, v[r], 8 );
+                    if( same8 ) v[r] += o8;
+                    const double o16 = __shfl_xor_sync( 0xffffffffu, v[r], 16 );
+                    if( same16 ) v[r] += o16;
+                    if( owner && joff[c][r] >= 0 && v[r] != 0. ) jadd( jb + joff[c][r] + ps*fstride[c], v[r], a.jscale );
+                }
+            }
         }
         // ---- particles that changed cell (Projector3D2Order.cpp:124-340 with ip_m_ipo != 0) go to the warp's
-        //      queue; whenever 4 are pending the warp deposits them, one per lane group (o2_cross_pass)
+        //      queue; whenever 4 are pending the warp deposits them, one per lane group (cross_pass)
         unsigned xmask = __ballot_sync( 0xffffffffu, active && !fast );
         while( xmask ) {                                                  // warp-uniform
             const int room = XQ - qn;
@@ -878,14 +901,8 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
             xmask &= ~done;
             qn += __popc( done );
             __syncwarp();
-#ifdef SB200_COUNT_CROSSERS
-            if( lane == 0 ) atomicAdd( &a.iflags[2], __popc( done ) );
-#endif
             while( qn >= 4 || ( xmask && qn > 0 ) ) {
-#ifdef SB200_COUNT_CROSSERS
-                if( lane == 0 ) atomicAdd( &a.iflags[3], 1 );
-#endif
-                o2_cross_pass( sJ, xq, xqm, xscr, qh, qn, gl, lane >> 3, c0, g, a.jscale );
+                cross_pass<ORDER>( sJ, xq, xqm, xscr, qh, qn, gl, lane >> 3, a.jscale );
                 const int took = qn < 4 ? qn : 4;
                 qh = ( qh + took ) % XQ;
                 qn -= took;
@@ -893,10 +910,7 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
         }
     }
     while( qn > 0 ) {                                                     // drain what is left in the queue
-#ifdef SB200_COUNT_CROSSERS
-        if( lane == 0 ) atomicAdd( &a.iflags[4], 1 );
-#endif
-        o2_cross_pass( sJ, xq, xqm, xscr, qh, qn, gl, lane >> 3, c0, g, a.jscale );
+        cross_pass<ORDER>( sJ, xq, xqm, xscr, qh, qn, gl, lane >> 3, a.jscale );
         const int took = qn < 4 ? qn : 4;
         qh = ( qh + took ) % XQ;
         qn -= took;
@@ -920,24 +934,25 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
     }
 }
 
-template<int PUSHER, bool SCRATCH>
-static int launch_o2( sb200_patch *p, const DynArgs &a, int ntiles )
+template<int ORDER, int PUSHER, bool SCRATCH>
+static int launch_cg( sb200_patch *p, const DynArgs &a, int ntiles )
 {
-    auto kern = k_dynamics_o2<PUSHER, SCRATCH>;
-    SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )O2Smem::BYTES ) );
+    auto kern = k_dynamics_cg<ORDER, PUSHER, SCRATCH>;
+    SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )CGDim<ORDER>::BYTES ) );
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
-    kern<<<ntiles, DYN_THREADS, O2Smem::BYTES, p->stream>>>( p->gd, a );
+    kern<<<ntiles, DYN_THREADS, CGDim<ORDER>::BYTES, p->stream>>>( p->gd, a );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }
 
-static int launch_o2_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int pusher, bool scratch )
+template<int ORDER>
+static int launch_cg_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int pusher, bool scratch )
 {
     switch( pusher ) {
-        case SB200_PUSHER_BORIS: return scratch ? launch_o2<SB200_PUSHER_BORIS, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_BORIS, false>( p, a, ntiles );
-        case SB200_PUSHER_VAY: return scratch ? launch_o2<SB200_PUSHER_VAY, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_VAY, false>( p, a, ntiles );
-        default: return scratch ? launch_o2<SB200_PUSHER_HIGUERACARY, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_HIGUERACARY, false>( p, a, ntiles );
+        case SB200_PUSHER_BORIS: return scratch ? launch_cg<ORDER, SB200_PUSHER_BORIS, true>( p, a, ntiles ) : launch_cg<ORDER, SB200_PUSHER_BORIS, false>( p, a, ntiles );
+        case SB200_PUSHER_VAY: return scratch ? launch_cg<ORDER, SB200_PUSHER_VAY, true>( p, a, ntiles ) : launch_cg<ORDER, SB200_PUSHER_VAY, false>( p, a, ntiles );
+        default: return scratch ? launch_cg<ORDER, SB200_PUSHER_HIGUERACARY, true>( p, a, ntiles ) : launch_cg<ORDER, SB200_PUSHER_HIGUERACARY, false>( p, a, ntiles );
     }
 }
 
@@ -984,14 +999,21 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
         a.jscale = ldexp( 1.0, 61 - e );                // bound*jscale < 2^61
         a.jinv = ldexp( 1.0, e - 61 );
     }
-    // SB200_DYN_GENERAL=1 selects the general (any-order) kernel for order 2 too: A/B checks only
+    // SB200_DYN_GENERAL=1 selects the general one-thread-per-particle kernel: A/B checks only
     static const bool general = getenv( "SB200_DYN_GENERAL" ) != nullptr;
-    if( g.order == 2 && !general ) {
-        using T = TileO2;
+    if( !general ) {
+        if( g.order == 2 ) {
+            using T = CG<2>::T;
+            a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
+            a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
+            a.tiles[2] = ( g.ncell[2] + T::TZ - 1 )/T::TZ;
+            return launch_cg_pusher<2>( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
+        }
+        using T = CG<4>::T;
         a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
         a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
         a.tiles[2] = ( g.ncell[2] + T::TZ - 1 )/T::TZ;
-        return launch_o2_pusher( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
+        return launch_cg_pusher<4>( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
     }
     using T = Tile<2>;                        // same tile footprint for both orders of the general kernel
     a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
