@@ -17,6 +17,7 @@
 // algorithmic 110 B: read 7 doubles + 1 short, write 6 doubles + 1 int; Epart/Bpart/iold/
 // deltaold/invgf never exist in HBM unless SB200_DYN_KEEP_SCRATCH asks for them.
 #include "common.cuh"
+#include <cuda.h>
 #include <cstdlib>
 #include <cmath>
 
@@ -54,10 +55,13 @@ template<int ORDER, int TX_ = 4, int TY_ = 4, int TZ_ = 8> struct Tile {
     static constexpr int H  = ORDER/2;
     static constexpr int NW = ORDER+1;            // gather points per dim
     static constexpr int WD = ORDER+3;            // Esirkepov window per dim (5 or 7)
-    static constexpr int FX = TX+2*H+1, FY = TY+2*H+1, FZ = TZ+2*H+1;   // staged field box
+    // staged field box; FZ has one spare point and is rounded up to even: a box row is a multiple of 16 B and
+    // the box may start one element early so that its first element is 16-B aligned in HBM (TMA requirements)
+    static constexpr int FX = TX+2*H+1, FY = TY+2*H+1, FZ = ( TZ+2*H+2 + 1 )/2*2;
     static constexpr int JX = TX+2*H+2, JY = TY+2*H+2, JZ = TZ+2*H+2;   // J accumulation box
     static constexpr int FVOL = FX*FY*FZ, JVOL = JX*JY*JZ;
-    static constexpr size_t SMEM = ( size_t )( 6*FVOL + 3*JVOL )*sizeof( double );
+    static constexpr int FBOX = ( FVOL + 15 )/16*16;          // box stride in shared memory: 128-B aligned (TMA destination)
+    static constexpr size_t SMEM = ( size_t )( 6*FBOX + 3*JVOL )*sizeof( double );
 };
 
 // The tile's J box accumulates in 64-bit FIXED POINT: value*jscale rounded to an integer and added with the
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
     using T = Tile<ORDER>;
     extern __shared__ double smem[];
     double *sF = smem;                    // 6 boxes of FVOL
-    jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FVOL );        // 3 boxes of JVOL (fixed point)
+    jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FBOX );        // 3 boxes of JVOL (fixed point)
     __shared__ int row_off[T::TX*T::TY+1];
     __shared__ int row_base[T::TX*T::TY];
 
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
         const int gi = gs[0]+i, gj = gs[1]+j, gk = gs[2]+k;
         double v = 0.;
         if( gi < g.ax && gj < g.ay && gk < g.az ) v = a.F[c][gi*g.sx + gj*g.sy + gk];
-        sF[t] = v;
+        sF[c*T::FBOX + ( t - c*T::FVOL )] = v;
     }
     for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0ull;
     __syncthreads();
@@ -374,12 +378,12 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
         if( bad ) atomicAdd( &a.iflags[1], 1 );   // particle not in the cell its sort key says
 
         // ---- gather (fieldsWrapper): Ex(d,p,p) Ey(p,d,p) Ez(p,p,d) Bx(p,d,d) By(d,p,d) Bz(d,d,p)
-        const double Ex = gather<T>( sF+0*T::FVOL, cd[0], cp[1], cp[2], sd[0], sp[1], sp[2] );
-        const double Ey = gather<T>( sF+1*T::FVOL, cp[0], cd[1], cp[2], sp[0], sd[1], sp[2] );
-        const double Ez = gather<T>( sF+2*T::FVOL, cp[0], cp[1], cd[2], sp[0], sp[1], sd[2] );
-        const double Bx = gather<T>( sF+3*T::FVOL, cp[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
-        const double By = gather<T>( sF+4*T::FVOL, cd[0], cp[1], cd[2], sd[0], sp[1], sd[2] );
-        const double Bz = gather<T>( sF+5*T::FVOL, cd[0], cd[1], cp[2], sd[0], sd[1], sp[2] );
+        const double Ex = gather<T>( sF+0*T::FBOX, cd[0], cp[1], cp[2], sd[0], sp[1], sp[2] );
+        const double Ey = gather<T>( sF+1*T::FBOX, cp[0], cd[1], cp[2], sp[0], sd[1], sp[2] );
+        const double Ez = gather<T>( sF+2*T::FBOX, cp[0], cp[1], cd[2], sp[0], sp[1], sd[2] );
+        const double Bx = gather<T>( sF+3*T::FBOX, cp[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+        const double By = gather<T>( sF+4*T::FBOX, cd[0], cp[1], cd[2], sd[0], sp[1], sd[2] );
+        const double Bz = gather<T>( sF+5*T::FBOX, cd[0], cd[1], cp[2], sd[0], sd[1], sp[2] );
 
         // ---- push
         const double cmd = ( double )charge*a.one_over_mass*g.dts2;
@@ -484,6 +488,30 @@ static int launch_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int push
     }
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: raw PTX for sm_100a -----------------------------------
+struct FieldMaps { CUtensorMap m[6]; };      // Ex Ey Ez Bxm Bym Bzm, box = (FZ, FY, FX) of the kernel's tile
+
+__device__ __forceinline__ unsigned smem_u32( const void *p ) { return ( unsigned )__cvta_generic_to_shared( p ); }
+__device__ __forceinline__ void tma_bar_init( unsigned long long *bar, unsigned count )
+{
+    asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"( smem_u32( bar ) ), "r"( count ) : "memory" );
+    asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+}
+__device__ __forceinline__ void tma_expect( unsigned long long *bar, unsigned bytes )
+{
+    asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"( smem_u32( bar ) ), "r"( bytes ) : "memory" );
+}
+__device__ __forceinline__ void tma_load_3d( void *dst, const CUtensorMap *map, unsigned long long *bar, int x0, int x1, int x2 )
+{
+    asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                  :: "r"( smem_u32( dst ) ), "l"( ( unsigned long long )map ), "r"( smem_u32( bar ) ), "r"( x0 ), "r"( x1 ), "r"( x2 ) : "memory" );
+}
+__device__ __forceinline__ void tma_wait( unsigned long long *bar, unsigned phase )
+{
+    asm volatile( "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                  :: "r"( smem_u32( bar ) ), "r"( phase ) : "memory" );
+}
+
 // =================================================================================================
 // Cell-group kernel, orders 2 and 4.
 //
@@ -530,7 +558,8 @@ template<int ORDER> struct CGDim {
     static constexpr int XSCR = 6*WX;                      // crosser scratch per lane group: S0[3][WX], DS[3][WX]
     static constexpr int NCELL = T::TX*T::TY*T::TZ;
     static constexpr int CPT = ( NCELL + DYN_THREADS - 1 )/DYN_THREADS;
-    static constexpr size_t BYTES = ( size_t )( 6*T::FVOL + 3*T::JVOL + XSCR*( DYN_THREADS/GRP ) + XQD*( DYN_THREADS/32 ) )*sizeof( double );
+    static constexpr size_t BYTES = ( size_t )( 6*T::FBOX + 3*T::JVOL + XSCR*( DYN_THREADS/GRP ) + XQD*( DYN_THREADS/32 ) )*sizeof( double );
+    static constexpr unsigned TMA_BYTES = 6u*T::FVOL*sizeof( double );   // bytes the six box loads deliver
 };
 using TileO2 = CG<2>::T;
 
@@ -636,15 +665,16 @@ __device__ __forceinline__ void cross_pass( jbox_t *sJ, const double *xq, const 
 }
 
 template<int ORDER, int PUSHER, bool SCRATCH>
-__global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg( const GridDev g, const DynArgs a )
+__global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg( const GridDev g, const DynArgs a, const __grid_constant__ FieldMaps tm )
 {
     using D = CGDim<ORDER>;
     using T = typename D::T;
     constexpr int NW = D::NW, NCELL = D::NCELL, CPT = D::CPT, NV = D::NV, NS = D::NS, NSL = D::NSL, NPASS = D::NPASS;
-    extern __shared__ double smem[];
+    extern __shared__ __align__( 128 ) double smem[];
     double *sF = smem;
-    jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FVOL );
-    double *xscr = smem + 6*T::FVOL + 3*T::JVOL + D::XSCR*( threadIdx.x/GRP );      // this lane group's crosser scratch
+    jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FBOX );
+    double *xscr = smem + 6*T::FBOX + 3*T::JVOL + D::XSCR*( threadIdx.x/GRP );      // this lane group's crosser scratch
+    __shared__ __align__( 8 ) unsigned long long tma_bar;
     __shared__ int cell_first[NCELL];
     __shared__ int cell_cnt[NCELL];
     __shared__ int round_off[NCELL+1];
@@ -657,6 +687,19 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
     const int ty = b % a.tiles[1];
     const int tx = b / a.tiles[1];
     const int c0[3] = { tx*T::TX, ty*T::TY, tz*T::TZ };
+
+    // the box starts at an even z index (16-B aligned rows): one element early when o - H is odd (order 2)
+    const int zs = ( c0[2] + g.o[2] - T::H ) & 1;
+    // ---- TMA: one elected thread asks for the six E/B_m stencil boxes of the tile (box index s <-> array
+    //      index c0 + o - H + s); they land while the CTA sets up its cell runs
+    if( tid == 0 ) tma_bar_init( &tma_bar, 1 );
+    __syncthreads();
+    if( tid == 0 ) {
+        tma_expect( &tma_bar, D::TMA_BYTES );
+#pragma unroll
+        for( int c=0; c<6; c++ )
+            tma_load_3d( sF + c*T::FBOX, &tm.m[c], &tma_bar, c0[2] + g.o[2] - T::H - zs, c0[1] + g.o[1] - T::H, c0[0] + g.o[0] - T::H );
+    }
 
     // ---- per-cell particle runs and the prefix sum of their rounds
     {
@@ -696,22 +739,15 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
     }
     __syncthreads();
     const int nrounds = round_off[NCELL];
-    if( nrounds == 0 ) return;
-
-    // ---- stage the field boxes, clear the J box
-    const int gs[3] = { c0[0] + g.o[0] - T::H, c0[1] + g.o[1] - T::H, c0[2] + g.o[2] - T::H };
-    for( int t = tid; t < 6*T::FVOL; t += DYN_THREADS ) {
-        const int c = t / T::FVOL;
-        int r = t - c*T::FVOL;
-        const int k = r % T::FZ; r /= T::FZ;
-        const int j = r % T::FY;
-        const int i = r / T::FY;
-        const int gi = gs[0]+i, gj = gs[1]+j, gk = gs[2]+k;
-        double v = 0.;
-        if( gi < g.ax && gj < g.ay && gk < g.az ) v = a.F[c][gi*g.sx + gj*g.sy + gk];
-        sF[t] = v;
+    if( nrounds == 0 ) {
+        tma_wait( &tma_bar, 0 );      // the boxes must have landed before this CTA's shared memory is released
+        return;
     }
+
+    // ---- the six field boxes arrive by TMA (issued before the per-cell set-up, see above); clear the J box
+    //      meanwhile and wait for the boxes.  Out-of-range box elements are zero-filled by the TMA unit.
     for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0ull;
+    tma_wait( &tma_bar, 0 );
     __syncthreads();
 
     // ---- lane geometry of the transpose-reduction: which of the NV values each of this lane's NS final
@@ -735,7 +771,7 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
     }
     const int fstride[3] = { NSL*T::JY*T::JZ, NSL*T::JZ, NSL };      // J-box stride of one flux pass per component
 
-    double *xq = smem + 6*T::FVOL + 3*T::JVOL + D::XSCR*( DYN_THREADS/GRP ) + XQD*( tid >> 5 );   // this warp's queue
+    double *xq = smem + 6*T::FBOX + 3*T::JVOL + D::XSCR*( DYN_THREADS/GRP ) + XQD*( tid >> 5 );   // this warp's queue
     int *xqm = reinterpret_cast<int *>( xq + 9*XQ );
     int qh = 0, qn = 0;                                       // queue head / pending entries (warp-uniform)
 
@@ -776,15 +812,15 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
                 const double dd = pn - ( double )idn + 0.5;
                 Shape<ORDER>::w( dd, cd[d] );
                 if( ipn - g.begin[d] - g.o[d] - c0[d] != cl[d] ) atomicAdd( &a.iflags[1], 1 );
-                sp[d] = cl[d] + T::H;
+                sp[d] = cl[d] + T::H + ( d == 2 ? zs : 0 );
                 sd[d] = sp[d] + ( idn - ipn );
             }
-            const double Ex = gather<T>( sF+0*T::FVOL, cd[0], S0[1], S0[2], sd[0], sp[1], sp[2] );
-            const double Ey = gather<T>( sF+1*T::FVOL, S0[0], cd[1], S0[2], sp[0], sd[1], sp[2] );
-            const double Ez = gather<T>( sF+2*T::FVOL, S0[0], S0[1], cd[2], sp[0], sp[1], sd[2] );
-            const double Bx = gather<T>( sF+3*T::FVOL, S0[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
-            const double By = gather<T>( sF+4*T::FVOL, cd[0], S0[1], cd[2], sd[0], sp[1], sd[2] );
-            const double Bz = gather<T>( sF+5*T::FVOL, cd[0], cd[1], S0[2], sd[0], sd[1], sp[2] );
+            const double Ex = gather<T>( sF+0*T::FBOX, cd[0], S0[1], S0[2], sd[0], sp[1], sp[2] );
+            const double Ey = gather<T>( sF+1*T::FBOX, S0[0], cd[1], S0[2], sp[0], sd[1], sp[2] );
+            const double Ez = gather<T>( sF+2*T::FBOX, S0[0], S0[1], cd[2], sp[0], sp[1], sd[2] );
+            const double Bx = gather<T>( sF+3*T::FBOX, S0[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+            const double By = gather<T>( sF+4*T::FBOX, cd[0], S0[1], cd[2], sd[0], sp[1], sd[2] );
+            const double Bz = gather<T>( sF+5*T::FBOX, cd[0], cd[1], S0[2], sd[0], sd[1], sp[2] );
 
             const double cmd = ( double )charge*a.one_over_mass*g.dts2;
             double dxp, dyp, dzp, invgf;
@@ -934,13 +970,46 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
     }
 }
 
+// Tensor maps of the six gathered fields for a given box: element (k,j,i) innermost first, row pitch AZ*8 B
+// (a multiple of 128 B by construction of the padded layout), out-of-bounds elements read as zero.
+static int field_maps( sb200_patch *p, int fx, int fy, int fz, FieldMaps &out )
+{
+    typedef CUresult ( *encode_t )( CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+    static encode_t encode = nullptr;
+    if( !encode ) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SB200_CUDA( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q ) );
+        SB200_CHECK( fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver" );
+        encode = ( encode_t )fn;
+    }
+    const GridDev &g = p->gd;
+    const int fid[6] = { SB200_EX, SB200_EY, SB200_EZ, SB200_BXM, SB200_BYM, SB200_BZM };
+    const cuuint64_t dims[3] = { ( cuuint64_t )g.az, ( cuuint64_t )g.ay, ( cuuint64_t )g.ax };
+    const cuuint64_t strides[2] = { ( cuuint64_t )g.az*sizeof( double ), ( cuuint64_t )g.ay*g.az*sizeof( double ) };
+    const cuuint32_t box[3] = { ( cuuint32_t )fz, ( cuuint32_t )fy, ( cuuint32_t )fx };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    for( int c=0; c<6; c++ ) {
+        const CUresult r = encode( &out.m[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p->f[fid[c]], dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+        SB200_CHECK( r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for a field box" );
+    }
+    return 0;
+}
+
 template<int ORDER, int PUSHER, bool SCRATCH>
 static int launch_cg( sb200_patch *p, const DynArgs &a, int ntiles )
 {
+    using T = typename CG<ORDER>::T;
+    FieldMaps tm;
+    if( field_maps( p, T::FX, T::FY, T::FZ, tm ) ) return 1;
     auto kern = k_dynamics_cg<ORDER, PUSHER, SCRATCH>;
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )CGDim<ORDER>::BYTES ) );
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
-    kern<<<ntiles, DYN_THREADS, CGDim<ORDER>::BYTES, p->stream>>>( p->gd, a );
+    kern<<<ntiles, DYN_THREADS, CGDim<ORDER>::BYTES, p->stream>>>( p->gd, a, tm );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
