@@ -58,10 +58,13 @@ template<int ORDER, int TX_ = 4, int TY_ = 4, int TZ_ = 8> struct Tile {
     // staged field box; FZ has one spare point and is rounded up to even: a box row is a multiple of 16 B and
     // the box may start one element early so that its first element is 16-B aligned in HBM (TMA requirements)
     static constexpr int FX = TX+2*H+1, FY = TY+2*H+1, FZ = ( TZ+2*H+2 + 1 )/2*2;
-    static constexpr int JX = TX+2*H+2, JY = TY+2*H+2, JZ = TZ+2*H+2;   // J accumulation box
+    // J accumulation box; along z it may start one element early so that the TMA reduction of the box into
+    // HBM begins on a 16-B boundary (needed when oversize-H-1 is odd), hence the spare and the even extent
+    static constexpr int JX = TX+2*H+2, JY = TY+2*H+2, JZ = ( TZ+2*H+2 + ( ( ORDER-H-1 ) & 1 ) + 1 )/2*2;
     static constexpr int FVOL = FX*FY*FZ, JVOL = JX*JY*JZ;
-    static constexpr int FBOX = ( FVOL + 15 )/16*16;          // box stride in shared memory: 128-B aligned (TMA destination)
-    static constexpr size_t SMEM = ( size_t )( 6*FBOX + 3*JVOL )*sizeof( double );
+    static constexpr int FBOX = ( FVOL + 15 )/16*16;          // box strides in shared memory: 128-B aligned (TMA source / destination)
+    static constexpr int JBOX = ( JVOL + 15 )/16*16;
+    static constexpr size_t SMEM = ( size_t )( 6*FBOX + 3*JBOX )*sizeof( double );
 };
 
 // The tile's J box accumulates in 64-bit FIXED POINT: value*jscale rounded to an integer and added with the
@@ -236,7 +239,7 @@ __device__ __forceinline__ void esirkepov_general( jbox_t *jb, const double ( &S
 #pragma unroll
                     for( int i=1; i<T::WD; i++ ) {
                         const double v = C[i]*W;
-                        if( v != 0. ) jadd( jb + 0*T::JVOL + ( i*T::JY + j )*T::JZ + k, v, jscale );
+                        if( v != 0. ) jadd( jb + 0*T::JBOX + ( i*T::JY + j )*T::JZ + k, v, jscale );
                     }
                 }
             }
@@ -258,7 +261,7 @@ __device__ __forceinline__ void esirkepov_general( jbox_t *jb, const double ( &S
 #pragma unroll
                     for( int j=1; j<T::WD; j++ ) {
                         const double v = C[j]*W;
-                        if( v != 0. ) jadd( jb + 1*T::JVOL + ( i*T::JY + j )*T::JZ + k, v, jscale );
+                        if( v != 0. ) jadd( jb + 1*T::JBOX + ( i*T::JY + j )*T::JZ + k, v, jscale );
                     }
                 }
             }
@@ -280,7 +283,7 @@ __device__ __forceinline__ void esirkepov_general( jbox_t *jb, const double ( &S
 #pragma unroll
                     for( int k=1; k<T::WD; k++ ) {
                         const double v = C[k]*W;
-                        if( v != 0. ) jadd( jb + 2*T::JVOL + ( i*T::JY + j )*T::JZ + k, v, jscale );
+                        if( v != 0. ) jadd( jb + 2*T::JBOX + ( i*T::JY + j )*T::JZ + k, v, jscale );
                     }
                 }
             }
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
         if( gi < g.ax && gj < g.ay && gk < g.az ) v = a.F[c][gi*g.sx + gj*g.sy + gk];
         sF[c*T::FBOX + ( t - c*T::FVOL )] = v;
     }
-    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0ull;
+    for( int t = tid; t < 3*T::JBOX; t += DYN_THREADS ) sJ[t] = 0ull;
     __syncthreads();
 
     for( int wi = tid; wi < total; wi += DYN_THREADS ) {
@@ -446,11 +449,11 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
     // flush the J box: box index s <-> array index c0 + o - H - 1 + s
     const int js[3] = { c0[0] + g.o[0] - T::H - 1, c0[1] + g.o[1] - T::H - 1, c0[2] + g.o[2] - T::H - 1 };
     for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) {
-        const long long iv = ( long long )sJ[t];
-        if( iv == 0 ) continue;
-        const double v = ( double )iv*a.jinv;
         const int c = t / T::JVOL;
         int r = t - c*T::JVOL;
+        const long long iv = ( long long )sJ[c*T::JBOX + r];
+        if( iv == 0 ) continue;
+        const double v = ( double )iv*a.jinv;
         const int k = r % T::JZ; r /= T::JZ;
         const int j = r % T::JY;
         const int i = r / T::JY;
@@ -489,7 +492,7 @@ static int launch_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int push
 }
 
 // ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: raw PTX for sm_100a -----------------------------------
-struct FieldMaps { CUtensorMap m[6]; };      // Ex Ey Ez Bxm Bym Bzm, box = (FZ, FY, FX) of the kernel's tile
+struct FieldMaps { CUtensorMap m[6]; CUtensorMap j[3]; };   // Ex Ey Ez Bxm Bym Bzm boxes (FZ,FY,FX); Jx Jy Jz boxes (JZ,JY,JX)
 
 __device__ __forceinline__ unsigned smem_u32( const void *p ) { return ( unsigned )__cvta_generic_to_shared( p ); }
 __device__ __forceinline__ void tma_bar_init( unsigned long long *bar, unsigned count )
@@ -505,6 +508,19 @@ __device__ __forceinline__ void tma_load_3d( void *dst, const CUtensorMap *map, 
 {
     asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                   :: "r"( smem_u32( dst ) ), "l"( ( unsigned long long )map ), "r"( smem_u32( bar ) ), "r"( x0 ), "r"( x1 ), "r"( x2 ) : "memory" );
+}
+// shared -> global element-wise ADD of a box (f64), performed by the TMA unit / L2 atomically per element;
+// elements of the box that fall outside the tensor are dropped
+__device__ __forceinline__ void tma_reduce_add_3d( const CUtensorMap *map, const void *src, int x0, int x1, int x2 )
+{
+    asm volatile( "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                  :: "l"( ( unsigned long long )map ), "r"( smem_u32( src ) ), "r"( x0 ), "r"( x1 ), "r"( x2 ) : "memory" );
+}
+__device__ __forceinline__ void tma_store_fence() { asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ); }
+__device__ __forceinline__ void tma_commit_and_wait_read()
+{
+    asm volatile( "cp.async.bulk.commit_group;" ::: "memory" );
+    asm volatile( "cp.async.bulk.wait_group.read 0;" ::: "memory" );
 }
 __device__ __forceinline__ void tma_wait( unsigned long long *bar, unsigned phase )
 {
@@ -558,7 +574,7 @@ template<int ORDER> struct CGDim {
     static constexpr int XSCR = 6*WX;                      // crosser scratch per lane group: S0[3][WX], DS[3][WX]
     static constexpr int NCELL = T::TX*T::TY*T::TZ;
     static constexpr int CPT = ( NCELL + DYN_THREADS - 1 )/DYN_THREADS;
-    static constexpr size_t BYTES = ( size_t )( 6*T::FBOX + 3*T::JVOL + XSCR*( DYN_THREADS/GRP ) + XQD*( DYN_THREADS/32 ) )*sizeof( double );
+    static constexpr size_t BYTES = ( size_t )( 6*T::FBOX + 3*T::JBOX + XSCR*( DYN_THREADS/GRP ) + XQD*( DYN_THREADS/32 ) )*sizeof( double );
     static constexpr unsigned TMA_BYTES = 6u*T::FVOL*sizeof( double );   // bytes the six box loads deliver
 };
 using TileO2 = CG<2>::T;
@@ -649,9 +665,9 @@ __device__ __forceinline__ void cross_pass( jbox_t *sJ, const double *xq, const 
                 const double Wx = S0y[aa]*Az + DSy[aa]*Bz;                                                       // Jx: W(j=aa,k=bb)
                 const double Wy = S0x[aa]*Az + DSx[aa]*Bz;                                                       // Jy: W(i=aa,k=bb)
                 const double Wz = S0x[aa]*( S0y[bb] + 0.5*DSy[bb] ) + DSx[aa]*( 0.5*S0y[bb] + third*DSy[bb] );   // Jz: W(i=aa,j=bb)
-                jbox_t *qx = xb + 0*T::JVOL + ( 1*T::JY + aa )*T::JZ + bb;      // flux points lo0+1..
-                jbox_t *qy = xb + 1*T::JVOL + ( aa*T::JY + 1 )*T::JZ + bb;      // flux points lo1+1..
-                jbox_t *qz = xb + 2*T::JVOL + ( aa*T::JY + bb )*T::JZ + 1;      // flux points lo2+1..
+                jbox_t *qx = xb + 0*T::JBOX + ( 1*T::JY + aa )*T::JZ + bb;      // flux points lo0+1..
+                jbox_t *qy = xb + 1*T::JBOX + ( aa*T::JY + 1 )*T::JZ + bb;      // flux points lo1+1..
+                jbox_t *qz = xb + 2*T::JBOX + ( aa*T::JY + bb )*T::JZ + 1;      // flux points lo2+1..
 #pragma unroll
                 for( int f=0; f<NW; f++ ) {
                     jadd_scaled( qx + f*T::JY*T::JZ, Cx[f]*Wx );
@@ -673,7 +689,7 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
     extern __shared__ __align__( 128 ) double smem[];
     double *sF = smem;
     jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FBOX );
-    double *xscr = smem + 6*T::FBOX + 3*T::JVOL + D::XSCR*( threadIdx.x/GRP );      // this lane group's crosser scratch
+    double *xscr = smem + 6*T::FBOX + 3*T::JBOX + D::XSCR*( threadIdx.x/GRP );      // this lane group's crosser scratch
     __shared__ __align__( 8 ) unsigned long long tma_bar;
     __shared__ int cell_first[NCELL];
     __shared__ int cell_cnt[NCELL];
@@ -688,8 +704,9 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
     const int tx = b / a.tiles[1];
     const int c0[3] = { tx*T::TX, ty*T::TY, tz*T::TZ };
 
-    // the box starts at an even z index (16-B aligned rows): one element early when o - H is odd (order 2)
-    const int zs = ( c0[2] + g.o[2] - T::H ) & 1;
+    // the boxes start at an even z index (16-B aligned rows): one element early when the natural start is odd
+    const int zs = ( c0[2] + g.o[2] - T::H ) & 1;          // field boxes
+    const int zj = ( c0[2] + g.o[2] - T::H - 1 ) & 1;      // J box
     // ---- TMA: one elected thread asks for the six E/B_m stencil boxes of the tile (box index s <-> array
     //      index c0 + o - H + s); they land while the CTA sets up its cell runs
     if( tid == 0 ) tma_bar_init( &tma_bar, 1 );
@@ -746,7 +763,7 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
 
     // ---- the six field boxes arrive by TMA (issued before the per-cell set-up, see above); clear the J box
     //      meanwhile and wait for the boxes.  Out-of-range box elements are zero-filled by the TMA unit.
-    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) sJ[t] = 0ull;
+    for( int t = tid; t < 3*T::JBOX; t += DYN_THREADS ) sJ[t] = 0ull;
     tma_wait( &tma_bar, 0 );
     __syncthreads();
 
@@ -765,13 +782,13 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
         idx += up4 ? D::N1 : 0;  ok = ok && idx < NV;
         const int f = idx / ( NW*NW ), aa = ( idx / NW ) % NW, bb = idx % NW;
         // Jx: flux i = 2+f, (j,k) = (1+aa, 1+bb);  Jy: flux j = 2+f, (i,k) = (1+aa, 1+bb);  Jz: flux k = 2+f, (i,j) = (1+aa, 1+bb)
-        joff[0][r] = ok ? 0*T::JVOL + ( ( 2+f )*T::JY + ( 1+aa ) )*T::JZ + ( 1+bb ) : -1;
-        joff[1][r] = ok ? 1*T::JVOL + ( ( 1+aa )*T::JY + ( 2+f ) )*T::JZ + ( 1+bb ) : -1;
-        joff[2][r] = ok ? 2*T::JVOL + ( ( 1+aa )*T::JY + ( 1+bb ) )*T::JZ + ( 2+f ) : -1;
+        joff[0][r] = ok ? 0*T::JBOX + ( ( 2+f )*T::JY + ( 1+aa ) )*T::JZ + ( 1+bb ) : -1;
+        joff[1][r] = ok ? 1*T::JBOX + ( ( 1+aa )*T::JY + ( 2+f ) )*T::JZ + ( 1+bb ) : -1;
+        joff[2][r] = ok ? 2*T::JBOX + ( ( 1+aa )*T::JY + ( 1+bb ) )*T::JZ + ( 2+f ) : -1;
     }
     const int fstride[3] = { NSL*T::JY*T::JZ, NSL*T::JZ, NSL };      // J-box stride of one flux pass per component
 
-    double *xq = smem + 6*T::FBOX + 3*T::JVOL + D::XSCR*( DYN_THREADS/GRP ) + XQD*( tid >> 5 );   // this warp's queue
+    double *xq = smem + 6*T::FBOX + 3*T::JBOX + D::XSCR*( DYN_THREADS/GRP ) + XQD*( tid >> 5 );   // this warp's queue
     int *xqm = reinterpret_cast<int *>( xq + 9*XQ );
     int qh = 0, qn = 0;                                       // queue head / pending entries (warp-uniform)
 
@@ -869,7 +886,7 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
             cr[0] = charge_weight*g.d_ov_dt[0]; cr[1] = charge_weight*g.d_ov_dt[1]; cr[2] = charge_weight*g.d_ov_dt[2];
             fast = same;
         }
-        jbox_t *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
+        jbox_t *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2] + zj;
         // two rounds of the same cell often sit in neighbouring groups of the warp: their sums are added up
         // below instead of letting their adds collide on identical addresses
         const int mycell = have ? cellt : -1 - gid;
@@ -938,7 +955,7 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
             qn += __popc( done );
             __syncwarp();
             while( qn >= 4 || ( xmask && qn > 0 ) ) {
-                cross_pass<ORDER>( sJ, xq, xqm, xscr, qh, qn, gl, lane >> 3, a.jscale );
+                cross_pass<ORDER>( sJ + zj, xq, xqm, xscr, qh, qn, gl, lane >> 3, a.jscale );
                 const int took = qn < 4 ? qn : 4;
                 qh = ( qh + took ) % XQ;
                 qn -= took;
@@ -946,33 +963,32 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
         }
     }
     while( qn > 0 ) {                                                     // drain what is left in the queue
-        cross_pass<ORDER>( sJ, xq, xqm, xscr, qh, qn, gl, lane >> 3, a.jscale );
+        cross_pass<ORDER>( sJ + zj, xq, xqm, xscr, qh, qn, gl, lane >> 3, a.jscale );
         const int took = qn < 4 ? qn : 4;
         qh = ( qh + took ) % XQ;
         qn -= took;
     }
     __syncthreads();
 
-    // ---- flush the J box
-    const int js[3] = { c0[0] + g.o[0] - T::H - 1, c0[1] + g.o[1] - T::H - 1, c0[2] + g.o[2] - T::H - 1 };
-    for( int t = tid; t < 3*T::JVOL; t += DYN_THREADS ) {
+    // ---- flush the J box: convert the fixed-point sums to double in place, then ONE elected thread hands the three
+    //      boxes to the TMA unit, which adds them into Jx, Jy, Jz in HBM (cp.reduce.async.bulk.tensor .add)
+    for( int t = tid; t < 3*T::JBOX; t += DYN_THREADS ) {
         const long long iv = ( long long )sJ[t];
-        if( iv == 0 ) continue;
-        const double v = ( double )iv*a.jinv;
-        const int c = t / T::JVOL;
-        int r = t - c*T::JVOL;
-        const int k = r % T::JZ; r /= T::JZ;
-        const int j = r % T::JY;
-        const int i = r / T::JY;
-        const int gi = js[0]+i, gj = js[1]+j, gk = js[2]+k;
-        if( gi >= 0 && gj >= 0 && gk >= 0 && gi < g.ax && gj < g.ay && gk < g.az )
-            atomicAdd( a.J[c] + gi*g.sx + gj*g.sy + gk, v );
+        reinterpret_cast<double *>( sJ )[t] = ( double )iv*a.jinv;
+    }
+    tma_store_fence();            // make the generic-proxy writes visible to the async proxy
+    __syncthreads();
+    if( tid == 0 ) {
+#pragma unroll
+        for( int c=0; c<3; c++ )
+            tma_reduce_add_3d( &tm.j[c], sJ + c*T::JBOX, c0[2] + g.o[2] - T::H - 1 - zj, c0[1] + g.o[1] - T::H - 1, c0[0] + g.o[0] - T::H - 1 );
+        tma_commit_and_wait_read();      // shared memory may be released once the TMA unit has read the boxes
     }
 }
 
 // Tensor maps of the six gathered fields for a given box: element (k,j,i) innermost first, row pitch AZ*8 B
 // (a multiple of 128 B by construction of the padded layout), out-of-bounds elements read as zero.
-static int field_maps( sb200_patch *p, int fx, int fy, int fz, FieldMaps &out )
+static int field_maps( sb200_patch *p, int fx, int fy, int fz, int jx, int jy, int jz, FieldMaps &out )
 {
     typedef CUresult ( *encode_t )( CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -997,6 +1013,13 @@ static int field_maps( sb200_patch *p, int fx, int fy, int fz, FieldMaps &out )
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
         SB200_CHECK( r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for a field box" );
     }
+    const cuuint32_t jbox[3] = { ( cuuint32_t )jz, ( cuuint32_t )jy, ( cuuint32_t )jx };
+    for( int c=0; c<3; c++ ) {
+        const CUresult r = encode( &out.j[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p->f[SB200_JX+c], dims, strides, jbox, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+        SB200_CHECK( r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for a J box" );
+    }
     return 0;
 }
 
@@ -1005,7 +1028,7 @@ static int launch_cg( sb200_patch *p, const DynArgs &a, int ntiles )
 {
     using T = typename CG<ORDER>::T;
     FieldMaps tm;
-    if( field_maps( p, T::FX, T::FY, T::FZ, tm ) ) return 1;
+    if( field_maps( p, T::FX, T::FY, T::FZ, T::JX, T::JY, T::JZ, tm ) ) return 1;
     auto kern = k_dynamics_cg<ORDER, PUSHER, SCRATCH>;
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )CGDim<ORDER>::BYTES ) );
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
