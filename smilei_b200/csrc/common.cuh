@@ -120,6 +120,7 @@ int launch_maxwell( sb200_patch *p );
 int launch_center_shell( sb200_patch *p );
 int launch_dynamics( sb200_patch *p, int ispec, int flags );
 int launch_sort( sb200_patch *p, int ispec );
+int launch_rho( sb200_patch *p, int ispec );
 int launch_energy( sb200_patch *p, double *ukin, double *uelm );
 int ensure_spare( sb200_patch *p, size_t cap );
 int ensure_perm( sb200_patch *p, size_t cap );

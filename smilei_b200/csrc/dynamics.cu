@@ -1051,7 +1051,6 @@ static int launch_cg_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int p
 int launch_dynamics( sb200_patch *p, int ispec, int flags )
 {
     SpeciesDev &s = p->sp[ispec];
-    SB200_CHECK( !( flags & SB200_DYN_DIAG_RHO ), "sb200_dynamics: SB200_DYN_DIAG_RHO is not built yet (diag-step rho deposit)" );
     SB200_CUDA( cudaMemsetAsync( p->leave_counts + 8*ispec, 0, 8*sizeof( int ), p->stream ) );
     if( s.n == 0 ) return 0;
     const GridDev &g = p->gd;

@@ -393,7 +393,10 @@ int sb200_dynamics( sb200_patch *p, int ispec, int flags )
     SB200_CHECK( p && ispec >= 0 && ispec < p->nspec, "sb200_dynamics: bad species index" );
     SB200_CHECK( p->sp[ispec].sorted || p->sp[ispec].n == 0, "sb200_dynamics: species must be cell-sorted (call sb200_sort)" );
     SB200_CUDA( cudaSetDevice( p->device ) );
-    return launch_dynamics( p, ispec, flags );
+    if( launch_dynamics( p, ispec, flags ) ) return 1;
+    // diag step: rho from the new positions (currentsAndDensity, Projector3D2Order.cpp:509-519)
+    if( flags & SB200_DYN_DIAG_RHO ) return launch_rho( p, ispec );
+    return 0;
 }
 
 int sb200_scratch_get( sb200_patch *p, double *Epart, double *Bpart, double *invgf, int *iold, double *deltaold, size_t n )

@@ -396,3 +396,42 @@ def test_particle_exchange_self_periodic(sb, orc):
     for k in ("px", "py", "pz", "w", "q"):
         assert np.array_equal(after[k], before[k][final]), k
     p.close()
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_diag_step_rho_deposit(sb, orc, order):
+    """SB200_DYN_DIAG_RHO: rho as Projector3D2Order::currentsAndDensity deposits it (a12).  The oracle's
+    order-2 routine is the reference's; for order 4 rho is checked through its defining property
+    rho[node] = sum_p q w/V S1x S1y S1z (total charge and a direct numpy evaluation)."""
+    n, cell, dt = (12, 10, 14), (0.07, 0.08, 0.09), 0.03
+    g = ol.make_grid(n, order, cell, dt)
+    p = make_patch(sb, n, order, cell, dt, 1)
+    rng = np.random.default_rng(90 + order)
+    F = ol.random_fields(g, rng, scale=0.05)
+    for k, v in F.items():
+        p.field_set(k, v)
+    N = 20000
+    P = ol.random_particles(g, rng, N, p_scale=0.5)
+    # keep everybody at least 3 cells from the faces so that no contribution falls outside the array
+    for i, c in enumerate("xyz"):
+        P[c] = np.ascontiguousarray(cell[i] * (3.2 + rng.random(N) * (n[i] - 6.4)))
+    p.species_config(0, 1.0, "boris", N)
+    p.species_set(0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+    p.sort(0)
+    S = p.species_get(0)
+    p.restart_rhoJ()
+    p.dynamics(0, flags=2)
+    out = p.species_get(0)
+    rho = p.field_get("rho")
+    V = cell[0] * cell[1] * cell[2]
+    total = np.sum(out["q"] * out["w"]) / V
+    assert abs(rho.sum() - total) <= 1e-11 * abs(total)
+    if order == 2:
+        E, B, iold, delta = orc.interp(g, 2, F, S["x"], S["y"], S["z"])
+        orc.push(g, 0, 1.0, S["x"], S["y"], S["z"], S["px"], S["py"], S["pz"], S["q"], E, B)
+        J = {k: np.zeros(ol.field_dims(g, k)) for k in ("Jx", "Jy", "Jz", "rho")}
+        orc.project_rho_o2(g, J, S["x"], S["y"], S["z"], S["q"], S["w"], iold, delta)
+        assert rel(rho, J["rho"]) <= TOL_DEPOSIT
+        for k in ("Jx", "Jy", "Jz"):
+            assert rel(p.field_get(k), J[k]) <= TOL_DEPOSIT, k
+    p.close()
