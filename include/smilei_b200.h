@@ -164,6 +164,10 @@ int  sb200_leaving_count( sb200_patch *p, int ispec, int counts[6] );
  * src/Patch/Patch.cpp:633-650).  *n_packed receives the record count (HOST). */
 int  sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wrap,
                          double *dev_buf, size_t max_records, size_t *n_packed );
+/* Same, for a caller that already knows the count (from sb200_leaving_count): no device->host round trip.
+ * Fails if the hint exceeds what the tag list can hold (then use sb200_leaving_pack). */
+int  sb200_leaving_pack_known( sb200_patch *p, int ispec, int dim, int side, double wrap,
+                               double *dev_buf, size_t max_records, size_t n_known );
 /* Append `n` records to the species, tagging them again (a corner particle is forwarded
  * in the next dimension, Patch::cornersParticles src/Patch/Patch.cpp:727-800). */
 int  sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, size_t n );

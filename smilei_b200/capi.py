@@ -30,7 +30,7 @@ SYMBOLS = (
     "sb200_field_size", "sb200_field_set", "sb200_field_get", "sb200_field_device_ptr", "sb200_restart_rhoJ",
     "sb200_dynamics", "sb200_scratch_get", "sb200_maxwell", "sb200_center_B", "sb200_sort", "sb200_energy",
     "sb200_halo_plane_elems", "sb200_halo_pack", "sb200_halo_unpack", "sb200_halo_sum_self",
-    "sb200_halo_exchange_self", "sb200_leaving_count", "sb200_leaving_pack", "sb200_arriving_unpack",
+    "sb200_halo_exchange_self", "sb200_leaving_count", "sb200_leaving_pack", "sb200_leaving_pack_known", "sb200_arriving_unpack",
     "sb200_debug_flags", "sb200_species_init_thermal", "sb200_launch_count",
 )
 
@@ -115,6 +115,7 @@ class Patch:
             pass
 
     def set_stream(self, cuda_stream):
+        self.own_stream = bool(cuda_stream)
         _check(lib().sb200_patch_set_stream(self._h, C.c_void_p(cuda_stream)), "sb200_patch_set_stream")
 
     def synchronize(self):
@@ -257,6 +258,11 @@ class Patch:
         _check(lib().sb200_leaving_pack(self._h, ispec, dim, side, C.c_double(wrap), C.c_void_p(dev_ptr),
                                         C.c_size_t(max_records), C.byref(n)), "sb200_leaving_pack")
         return n.value
+
+    def leaving_pack_known(self, ispec, dim, side, wrap, dev_ptr, max_records, n_known):
+        _check(lib().sb200_leaving_pack_known(self._h, ispec, dim, side, C.c_double(wrap), C.c_void_p(dev_ptr),
+                                              C.c_size_t(max_records), C.c_size_t(n_known)), "sb200_leaving_pack_known")
+        return n_known
 
     def arriving_unpack(self, ispec, dev_ptr, n):
         _check(lib().sb200_arriving_unpack(self._h, ispec, C.c_void_p(dev_ptr), C.c_size_t(n)),

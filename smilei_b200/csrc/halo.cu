@@ -329,6 +329,27 @@ int sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wra
     return 0;
 }
 
+int sb200_leaving_pack_known( sb200_patch *p, int ispec, int dim, int side, double wrap, double *dev_buf, size_t max_records, size_t n_known )
+{
+    SB200_CHECK( p && ispec >= 0 && ispec < p->nspec && dim >= 0 && dim < 3 && ( side==0 || side==1 ), "sb200_leaving_pack_known: bad arguments" );
+    SpeciesDev &s = p->sp[ispec];
+    SB200_CHECK( n_known <= s.leave_cap && n_known <= 200000, "sb200_leaving_pack_known: too many leavers for the tag list (use sb200_leaving_pack)" );
+    SB200_CHECK( n_known <= max_records, "sb200_leaving_pack_known: buffer too small for the leaving particles" );
+    if( n_known == 0 ) return 0;
+    SB200_CHECK( dev_buf, "sb200_leaving_pack_known: null buffer" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    const int tag = -2 - 2*dim - side;
+    const GridDev &g = p->gd;
+    const double hi = g.cell[dim]*( double )( g.n[dim]*g.npatch[dim] );
+    ConstCols in;
+    for( int c=0; c<7; c++ ) in.c[c] = s.col[c];
+    in.q = s.q;
+    k_rank_pack<<<( unsigned )( ( n_known + 255 )/256 ), 256, 0, p->stream>>>( in, s.leave_idx + ( size_t )( -tag-2 )*s.leave_cap, ( int )n_known, dim, wrap, 0., hi, dev_buf );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    return 0;
+}
+
 int sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, size_t n )
 {
     SB200_CHECK( p && ispec >= 0 && ispec < p->nspec, "sb200_arriving_unpack: bad arguments" );

@@ -91,22 +91,25 @@ class Exchanger:
         for w in dist.batch_isend_irecv(p2p):
             w.wait()
 
-    def _exchange_slabs(self, dim, to_lo, to_hi):
-        """Send `to_lo` to the -dim neighbour and `to_hi` to the +dim one; returns
-        (from_lo, from_hi) = what those neighbours sent to me."""
+    def _exchange_slabs(self, dim, to_lo, to_hi, size_from_lo=None, size_from_hi=None):
+        """Send `to_lo` to the -dim neighbour and `to_hi` to the +dim one; returns (from_lo, from_hi) = what
+        those neighbours sent to me.  By default the exchange is symmetric (I receive from a side as much as
+        I send to it); for particle records the incoming sizes are given."""
         lo, hi = self.nbr[dim]
         n_lo, n_hi = to_lo.numel(), to_hi.numel()
+        m_lo = n_hi if size_from_lo is None else size_from_lo     # the -dim neighbour sends me ITS to_hi block
+        m_hi = n_lo if size_from_hi is None else size_from_hi
         if lo == hi:
             # one peer on both sides: [payload for its +side | payload for its -side] in one message
             send = self._buf(("s2", dim), n_lo + n_hi)[:n_lo + n_hi]
             send[:n_lo].copy_(to_lo)
             send[n_lo:].copy_(to_hi)
-            recv = self._buf(("r2", dim), n_lo + n_hi)[:n_lo + n_hi]
+            recv = self._buf(("r2", dim), m_hi + m_lo)[:m_hi + m_lo]
             self._sendrecv([(lo, send, recv)])
             # the peer's first block was meant for its -dim neighbour's +side = my +side
-            return recv[n_lo:], recv[:n_lo]
-        from_lo = self._buf(("rl", dim), n_hi)[:n_hi]   # the -dim neighbour sends me its to_hi block
-        from_hi = self._buf(("rh", dim), n_lo)[:n_lo]
+            return recv[m_hi:], recv[:m_hi]
+        from_lo = self._buf(("rl", dim), m_lo)[:m_lo]
+        from_hi = self._buf(("rh", dim), m_hi)[:m_hi]
         self._sendrecv([(lo, to_lo, from_lo), (hi, to_hi, from_hi)])
         return from_lo, from_hi
 
@@ -172,58 +175,61 @@ class Exchanger:
     # ------------------------------------------------------------------ particles
     def exchange_particles(self, n_species):
         """x, then y, then z; arrivals are re-tagged on unpack so corner particles are forwarded in
-        the next dimension (Patch::cornersParticles)."""
+        the next dimension (Patch::cornersParticles).  All species travel together: per dimension one
+        message with the counts and one with the records per neighbour."""
         p = self.patch
+        pack = getattr(p, "leaving_pack_known", None)
         for dim in range(3):
             L = self.cell[dim] * float(self.n[dim] * self.npatch[dim])      # Patch.cpp:626
             wrap_lo = L if self.pcoord[dim] == 0 else 0.                     # Patch.cpp:636-642
             wrap_hi = -L if self.pcoord[dim] == self.npatch[dim] - 1 else 0.  # Patch.cpp:643-649
-            for s in range(n_species):
-                counts = p.leaving_count(s)                       # Patch::exchNbrOfParticles: sizes first
-                c_lo, c_hi = counts[2 * dim], counts[2 * dim + 1]
-                if self.npatch[dim] == 1:
-                    self._ensure_pcap(max(c_lo, c_hi))
+            counts = [p.leaving_count(s) for s in range(n_species)]          # Patch::exchNbrOfParticles: sizes first
+            c_lo = [c[2 * dim] for c in counts]
+            c_hi = [c[2 * dim + 1] for c in counts]
+            if self.npatch[dim] == 1:
+                for s in range(n_species):
+                    self._ensure_pcap(max(c_lo[s], c_hi[s]))
                     to_lo = self._buf(("pl", dim), RECORD * self._pcap)
                     to_hi = self._buf(("ph", dim), RECORD * self._pcap)
-                    k_lo = p.leaving_pack(s, dim, 0, wrap_lo, to_lo.data_ptr(), self._pcap)
-                    k_hi = p.leaving_pack(s, dim, 1, wrap_hi, to_hi.data_ptr(), self._pcap)
-                    assert (k_lo, k_hi) == (c_lo, c_hi), ("leaving counts disagree", k_lo, k_hi, c_lo, c_hi)
-                    p.arriving_unpack(s, to_lo.data_ptr(), k_lo)
-                    p.arriving_unpack(s, to_hi.data_ptr(), k_hi)
-                    continue
-                cnt_lo = torch.tensor([float(c_lo)], dtype=torch.float64, device=self.device)
-                cnt_hi = torch.tensor([float(c_hi)], dtype=torch.float64, device=self.device)
-                r_lo, r_hi = self._exchange_slabs(dim, cnt_lo, cnt_hi)
-                n_from_lo, n_from_hi = int(r_lo.item()), int(r_hi.item())
-                # every message of this (dim, species) round is padded to one size known to both ends
-                pad = max(c_lo, c_hi, n_from_lo, n_from_hi, 1)
-                self._ensure_pcap(pad)
-                to_lo = self._buf(("pl", dim), RECORD * self._pcap)
-                to_hi = self._buf(("ph", dim), RECORD * self._pcap)
-                k_lo = p.leaving_pack(s, dim, 0, wrap_lo, to_lo.data_ptr(), self._pcap)
-                k_hi = p.leaving_pack(s, dim, 1, wrap_hi, to_hi.data_ptr(), self._pcap)
-                assert (k_lo, k_hi) == (c_lo, c_hi), ("leaving counts disagree", k_lo, k_hi, c_lo, c_hi)
-                self._sync_patch_stream()
-                lo, hi = self.nbr[dim]
-                if lo == hi:
-                    from_lo, from_hi = self._exchange_slabs(dim, to_lo[:RECORD * pad], to_hi[:RECORD * pad])
-                else:
-                    # sizes differ per neighbour pair: send what I have, receive what was announced
-                    from_lo = self._buf(("prl", dim), RECORD * max(n_from_lo, 1))[:RECORD * max(n_from_lo, 1)]
-                    from_hi = self._buf(("prh", dim), RECORD * max(n_from_hi, 1))[:RECORD * max(n_from_hi, 1)]
-                    self._sendrecv([(lo, to_lo[:RECORD * max(c_lo, 1)], from_lo),
-                                    (hi, to_hi[:RECORD * max(c_hi, 1)], from_hi)])
+                    pack(s, dim, 0, wrap_lo, to_lo.data_ptr(), self._pcap, c_lo[s])
+                    pack(s, dim, 1, wrap_hi, to_hi.data_ptr(), self._pcap, c_hi[s])
+                    p.arriving_unpack(s, to_lo.data_ptr(), c_lo[s])
+                    p.arriving_unpack(s, to_hi.data_ptr(), c_hi[s])
+                continue
+            cnt_lo = torch.tensor([float(v) for v in c_lo], dtype=torch.float64, device=self.device)
+            cnt_hi = torch.tensor([float(v) for v in c_hi], dtype=torch.float64, device=self.device)
+            r_lo, r_hi = self._exchange_slabs(dim, cnt_lo, cnt_hi)
+            n_from_lo = [int(v) for v in r_lo.cpu().tolist()]
+            n_from_hi = [int(v) for v in r_hi.cpu().tolist()]
+            # per direction, every species block is padded to the largest count of that direction, which both
+            # ends of the link know: what I send to -dim is what that neighbour announced-to-receive, etc.
+            pad_to_lo, pad_to_hi = max(max(c_lo), 1), max(max(c_hi), 1)
+            pad_from_lo, pad_from_hi = max(max(n_from_lo), 1), max(max(n_from_hi), 1)
+            to_lo = self._buf(("pl", dim), RECORD * pad_to_lo * n_species)[:RECORD * pad_to_lo * n_species]
+            to_hi = self._buf(("ph", dim), RECORD * pad_to_hi * n_species)[:RECORD * pad_to_hi * n_species]
+            for s in range(n_species):
+                pack(s, dim, 0, wrap_lo, to_lo[RECORD * pad_to_lo * s:].data_ptr(), pad_to_lo, c_lo[s])
+                pack(s, dim, 1, wrap_hi, to_hi[RECORD * pad_to_hi * s:].data_ptr(), pad_to_hi, c_hi[s])
+            self._sync_patch_stream()
+            from_lo, from_hi = self._exchange_slabs(dim, to_lo, to_hi, RECORD * pad_from_lo * n_species,
+                                                    RECORD * pad_from_hi * n_species)
+            for s in range(n_species):
                 # arrivals from the -dim neighbour first, then from the +dim one (deterministic order)
-                p.arriving_unpack(s, from_lo.data_ptr(), n_from_lo)
-                p.arriving_unpack(s, from_hi.data_ptr(), n_from_hi)
-                self._sync_patch_stream()
+                p.arriving_unpack(s, from_lo[RECORD * pad_from_lo * s:].data_ptr(), n_from_lo[s])
+                p.arriving_unpack(s, from_hi[RECORD * pad_from_hi * s:].data_ptr(), n_from_hi[s])
+            self._sync_patch_stream()
 
     def _ensure_pcap(self, need):
         if need > self._pcap:
             self._pcap = int(need * 1.5) + 16
 
     def _sync_patch_stream(self):
-        # pack kernels run on the patch's stream; the collective runs on torch's: order them
+        # Pack / unpack kernels run on the patch's stream and the collective on torch's current stream.  On
+        # the GPU both are the legacy default stream (the library's default, and torch's default stream), so
+        # everything is already stream-ordered and no host synchronisation is needed; a patch on its own
+        # stream, or the CPU stand-in of the tests, synchronises here.
+        if self.device.type == "cuda" and not getattr(self.patch, "own_stream", False):
+            return
         sync = getattr(self.patch, "synchronize", None)
         if sync is not None:
             sync()

@@ -180,6 +180,11 @@ class OraclePatch:
         _view(ptr, k * RECORD)[:] = rec.reshape(-1)
         return k
 
+    def leaving_pack_known(self, ispec, dim, side, wrap, ptr, max_records, n_known):
+        k = self.leaving_pack(ispec, dim, side, wrap, ptr, max_records)
+        assert k == n_known
+        return k
+
     def arriving_unpack(self, ispec, ptr, n):
         if n == 0:
             return

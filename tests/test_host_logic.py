@@ -204,3 +204,19 @@ def test_two_ranks_gloo_match_single_rank(single_rank_reference, rank_grid):
         assert len(a["x"]) == len(b["x"]) == 12 ** 3 * 6
         for k in a:
             assert np.allclose(a[k], b[k], rtol=0, atol=1e-11), k
+
+
+def test_three_ranks_gloo_distinct_neighbours():
+    """3 ranks along x: the -x and +x neighbours are different peers (separate messages, per-direction sizes)."""
+    n = (18, 12, 12)
+    ref = _launch((1, 1, 1), n, 4)
+    three = _launch((3, 1, 1), n, 4)
+    for (it_a, uk_a, ue_a), (it_b, uk_b, ue_b) in zip(ref["hist"], three["hist"]):
+        assert np.allclose(uk_a, uk_b, rtol=1e-11, atol=0)
+        assert abs(ue_a - ue_b) <= 1e-9 * abs(ue_a)
+    for ispec in range(2):
+        a = _canonical(ref["parts"], ispec)
+        b = _canonical(three["parts"], ispec)
+        assert len(a["x"]) == len(b["x"]) == 18 * 12 * 12 * 6
+        for k in a:
+            assert np.allclose(a[k], b[k], rtol=0, atol=1e-11), k
