@@ -61,6 +61,8 @@ struct SpeciesDev {
     short  *q = nullptr;
     int    *key = nullptr;
     int    *first = nullptr;       // ncells+1, valid after sort
+    int    *count = nullptr;       // ncells+1: histogram of the NEW keys, filled by the dynamics kernel / arrivals
+    bool   count_valid = false;
     bool   sorted = false;
     int    maxcount = 0;       // most particles in one cell (after the last sort)
     double qwmax = 0.;         // max |charge*weight| seen in this species
@@ -98,7 +100,6 @@ struct sb200_patch {
     sb200::ParticleBuf spare;
     size_t            ncells = 0;
     // sort workspace
-    int              *count = nullptr;       // ncells+1
     int              *cursor = nullptr;      // ncells
     int              *perm = nullptr;        // capacity
     size_t            perm_cap = 0;

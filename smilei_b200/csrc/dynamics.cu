@@ -95,6 +95,7 @@ struct DynArgs {
     const int *first;
     const double *F[6];       // Ex Ey Ez Bxm Bym Bzm
     double *J[3];
+    int    *count;            // histogram of the new cell keys (input of the next sort)
     int    *leave_counts;
     int    *leave_idx;        // [6][leave_cap]
     int     leave_cap;
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
             }
         }
         int key = tag;
-        if( tag == 0 ) key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2];
+        if( tag == 0 ) { key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2]; atomicAdd( &a.count[key], 1 ); }
         else note_leaver( a, tag, ip );
         a.key[ip] = key;
 
@@ -878,7 +879,7 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
                 for( int s=0; s<NW; s++ ) DS[d][s] = w1[s] - S0[d][s];
             }
             int key = tag;
-            if( tag == 0 ) key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2];
+            if( tag == 0 ) { key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2]; atomicAdd( &a.count[key], 1 ); }
             else note_leaver( a, tag, ip );
             a.key[ip] = key;
 
@@ -1052,6 +1053,8 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
 {
     SpeciesDev &s = p->sp[ispec];
     SB200_CUDA( cudaMemsetAsync( p->leave_counts + 8*ispec, 0, 8*sizeof( int ), p->stream ) );
+    SB200_CUDA( cudaMemsetAsync( s.count, 0, ( p->ncells+1 )*sizeof( int ), p->stream ) );
+    s.count_valid = true;
     if( s.n == 0 ) return 0;
     const GridDev &g = p->gd;
     const bool scratch = ( flags & SB200_DYN_KEEP_SCRATCH ) != 0;
@@ -1072,6 +1075,7 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     const int fid[6] = { SB200_EX, SB200_EY, SB200_EZ, SB200_BXM, SB200_BYM, SB200_BZM };
     for( int c=0; c<6; c++ ) a.F[c] = p->f[fid[c]];
     a.J[0] = p->f[SB200_JX]; a.J[1] = p->f[SB200_JY]; a.J[2] = p->f[SB200_JZ];
+    a.count = s.count;
     a.leave_counts = p->leave_counts + 8*ispec;
     a.leave_idx = s.leave_idx;
     a.leave_cap = ( int )s.leave_cap;

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__( CP_T ) k_leave_write( ConstCols in, const int
 struct MutCols { double *c[7]; short *q; int *key; };
 
 __global__ void __launch_bounds__( 256 ) k_arrive( GridDev g, MutCols out, size_t n0, const double *__restrict__ buf, size_t n,
-        int *__restrict__ leave_counts, int *__restrict__ leave_idx, int leave_cap )
+        int *__restrict__ leave_counts, int *__restrict__ leave_idx, int leave_cap, int *__restrict__ count )
 {
     for( size_t t = blockIdx.x*( size_t )blockDim.x + threadIdx.x; t < n; t += ( size_t )gridDim.x*blockDim.x ) {
         const double *r = buf + t*SB200_PARTICLE_RECORD_DOUBLES;
@@ -161,6 +161,8 @@ __global__ void __launch_bounds__( 256 ) k_arrive( GridDev g, MutCols out, size_
         if( k < 0 ) {
             const int c = atomicAdd( &leave_counts[-k-2], 1 );
             if( c < leave_cap ) leave_idx[( size_t )( -k-2 )*leave_cap + c] = ( int )i;
+        } else if( count ) {
+            atomicAdd( &count[k], 1 );
         }
     }
 }
@@ -362,7 +364,7 @@ int sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, siz
     for( int c=0; c<7; c++ ) out.c[c] = s.col[c];
     out.q = s.q; out.key = s.key;
     const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*8 ? ( n + 255 )/256 : 148*8 );
-    k_arrive<<<blocks, 256, 0, p->stream>>>( p->gd, out, s.n, dev_buf, n, p->leave_counts + 8*ispec, s.leave_idx, ( int )s.leave_cap );
+    k_arrive<<<blocks, 256, 0, p->stream>>>( p->gd, out, s.n, dev_buf, n, p->leave_counts + 8*ispec, s.leave_idx, ( int )s.leave_cap, s.count_valid ? s.count : nullptr );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     const size_t n0 = s.n;

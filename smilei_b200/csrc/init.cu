@@ -92,6 +92,7 @@ extern "C" int sb200_species_init_thermal( sb200_patch *p, int ispec, const int 
     SB200_CUDA( cudaGetLastError() );
     s.n = n;
     s.sorted = false;
+    s.count_valid = false;
     SB200_CUDA( cudaMemsetAsync( s.d_qwmax, 0, sizeof( unsigned long long ), p->stream ) );
     return update_qwmax( p, ispec, 0, n );
 }

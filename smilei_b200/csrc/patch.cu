@@ -160,7 +160,6 @@ int sb200_patch_create( sb200_patch **out, const sb200_grid *grid, int n_species
         SB200_CUDA( cudaMalloc( &p->f[f], p->falloc*sizeof( double ) ) );
         SB200_CUDA( cudaMemset( p->f[f], 0, p->falloc*sizeof( double ) ) );
     }
-    SB200_CUDA( cudaMalloc( &p->count, ( p->ncells+1 )*sizeof( int ) ) );
     SB200_CUDA( cudaMalloc( &p->cursor, ( p->ncells+1 )*sizeof( int ) ) );
     SB200_CUDA( cudaMalloc( &p->red, 4096*sizeof( double ) ) );
     SB200_CUDA( cudaMalloc( &p->leave_counts, 8*( n_species+1 )*sizeof( int ) ) );
@@ -181,11 +180,12 @@ int sb200_patch_destroy( sb200_patch *p )
     for( int s=0; s<p->nspec; s++ ) {
         free_particle_cols( p->sp[s].col, &p->sp[s].q, &p->sp[s].key );
         if( p->sp[s].first ) cudaFree( p->sp[s].first );
+        if( p->sp[s].count ) cudaFree( p->sp[s].count );
         if( p->sp[s].d_qwmax ) cudaFree( p->sp[s].d_qwmax );
         if( p->sp[s].leave_idx ) cudaFree( p->sp[s].leave_idx );
     }
     free_particle_cols( p->spare.col, &p->spare.q, &p->spare.key );
-    void *misc[] = { p->count, p->cursor, p->perm, p->blocksums, p->stage, p->red, p->leave_counts, p->iflags, p->d_maxcount,
+    void *misc[] = { p->cursor, p->perm, p->blocksums, p->stage, p->red, p->leave_counts, p->iflags, p->d_maxcount,
                      p->sc_E, p->sc_B, p->sc_invgf, p->sc_delta, p->sc_iold };
     for( void *m : misc ) if( m ) cudaFree( m );
     delete[] p->sp;
@@ -237,6 +237,10 @@ int sb200_species_config( sb200_patch *p, int ispec, double mass, int pusher, si
         SB200_CUDA( cudaMalloc( &s.d_qwmax, sizeof( unsigned long long ) ) );
         SB200_CUDA( cudaMemset( s.d_qwmax, 0, sizeof( unsigned long long ) ) );
     }
+    if( !s.count ) {
+        SB200_CUDA( cudaMalloc( &s.count, ( p->ncells+1 )*sizeof( int ) ) );
+        SB200_CUDA( cudaMemset( s.count, 0, ( p->ncells+1 )*sizeof( int ) ) );
+    }
     if( !s.first ) {
         SB200_CUDA( cudaMalloc( &s.first, ( p->ncells+1 )*sizeof( int ) ) );
         SB200_CUDA( cudaMemset( s.first, 0, ( p->ncells+1 )*sizeof( int ) ) );
@@ -260,6 +264,7 @@ int sb200_species_set( sb200_patch *p, int ispec,
     SB200_CUDA( cudaMemsetAsync( s.key, 0, n*sizeof( int ), p->stream ) );
     SB200_CUDA( cudaMemsetAsync( s.d_qwmax, 0, sizeof( unsigned long long ), p->stream ) );
     s.n = n;
+    s.count_valid = false;
     if( update_qwmax( p, ispec, 0, n ) ) return 1;
     SB200_CUDA( cudaStreamSynchronize( p->stream ) );
     s.sorted = false;

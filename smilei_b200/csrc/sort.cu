@@ -116,31 +116,67 @@ int exclusive_scan_int( sb200_patch *p, int *data, size_t n )
 }
 
 // ---------------------------------------------------------------- scatter / per-cell order / gather
+// slot of particle i in the run of its new cell.  Lanes of a warp holding the same key take consecutive slots
+// in lane (= index) order from ONE atomic on the cell's cursor, so a cell whose particles sit in one warp
+// comes out already ordered; k_cell_sort repairs the cells that straddle warps or received movers.
 __global__ void __launch_bounds__( 256 ) k_scatter_idx( const int *__restrict__ key, const int *__restrict__ first,
         int *__restrict__ cursor, int *__restrict__ perm, size_t n )
 {
-    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < n; i += ( size_t )gridDim.x*blockDim.x ) {
-        const int k = key[i];
-        if( k < 0 ) continue;
-        const int slot = first[k] + atomicAdd( &cursor[k], 1 );
-        perm[slot] = ( int )i;
+    const int lane = threadIdx.x & 31;
+    const size_t nround = ( n + 31 )/32*32;
+    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < nround; i += ( size_t )gridDim.x*blockDim.x ) {
+        const int k = i < n ? key[i] : -1;
+        const unsigned peers = __match_any_sync( 0xffffffffu, k );
+        const int leader = __ffs( peers ) - 1;
+        const int rank = __popc( peers & ( ( 1u << lane ) - 1u ) );
+        int base = 0;
+        if( lane == leader && k >= 0 ) base = atomicAdd( &cursor[k], __popc( peers ) );
+        base = __shfl_sync( 0xffffffffu, base, leader );
+        if( k >= 0 ) perm[first[k] + base + rank] = ( int )i;
     }
 }
 
-__global__ void __launch_bounds__( 128 ) k_cell_sort( const int *__restrict__ first, int *__restrict__ perm, int ncells )
+// Restore ascending index order inside every cell's run of perm (the atomic cursor of k_scatter_idx serves
+// slots in arbitrary order).  A warp takes 32 consecutive cells = one contiguous stretch of perm, reads it
+// coalesced and looks for inversions between neighbours of the same cell; particles of a cell mostly arrive
+// in order, so only the rare cell with an inversion is then insertion-sorted by its lane.
+__global__ void __launch_bounds__( 256 ) k_cell_sort( const int *__restrict__ first, int *__restrict__ perm, int ncells )
 {
-    for( int c = blockIdx.x*blockDim.x + threadIdx.x; c < ncells; c += gridDim.x*blockDim.x ) {
-        const int b = first[c], e = first[c+1];
-        for( int i = b+1; i < e; i++ ) {
-            const int v = perm[i];
-            int j = i-1;
-            while( j >= b ) {
-                const int u = perm[j];
-                if( u <= v ) break;
-                perm[j+1] = u;
-                j--;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = ( gridDim.x*blockDim.x ) >> 5;
+    for( int w = ( blockIdx.x*blockDim.x + threadIdx.x ) >> 5; w*32 < ncells; w += nwarps ) {
+        const int c = w*32 + lane;
+        const int cb = first[min( c, ncells )], ce = first[min( c+1, ncells )];
+        const int base = __shfl_sync( 0xffffffffu, cb, 0 ), end = __shfl_sync( 0xffffffffu, ce, 31 );
+        unsigned bad = 0;
+        for( int j0 = base; j0 < end; j0 += 32 ) {
+            const int j = j0 + lane;
+            const int v = j < end ? perm[j] : 0x7fffffff;
+            int vn = __shfl_down_sync( 0xffffffffu, v, 1 );
+            if( lane == 31 ) vn = j+1 < end ? perm[j+1] : 0x7fffffff;
+            // cell of position j among the warp's 32 cells: the number of run ends <= j
+            int k = 0;
+#pragma unroll
+            for( int st=16; st>0; st>>=1 ) {
+                const int probe = __shfl_sync( 0xffffffffu, ce, k + st - 1 );
+                if( probe <= j ) k += st;
             }
-            perm[j+1] = v;
+            const int kend = __shfl_sync( 0xffffffffu, ce, k & 31 );
+            const bool inv = j+1 < end && k < 32 && j+1 < kend && v > vn;
+            bad |= __reduce_or_sync( 0xffffffffu, inv ? ( 1u << k ) : 0u );
+        }
+        if( ( bad >> lane ) & 1u ) {
+            for( int i = cb+1; i < ce; i++ ) {
+                const int v = perm[i];
+                int j = i-1;
+                while( j >= cb ) {
+                    const int u = perm[j];
+                    if( u <= v ) break;
+                    perm[j+1] = u;
+                    j--;
+                }
+                perm[j+1] = v;
+            }
         }
     }
 }
@@ -180,14 +216,34 @@ int update_qwmax( sb200_patch *p, int ispec, size_t first, size_t n )
 
 struct Cols { double *c[7]; short *q; int *key; };
 
+// out[c][j] = in[c][perm[j]] for the 9 columns.  Four consecutive output slots per thread: 36 independent
+// loads in flight per thread and 32-B stores; perm is the identity plus small shifts except around movers, so
+// the reads are almost as contiguous as the writes.
 __global__ void __launch_bounds__( 256 ) k_gather( Cols in, Cols out, const int *__restrict__ perm, size_t n )
 {
-    for( size_t j = blockIdx.x*( size_t )blockDim.x + threadIdx.x; j < n; j += ( size_t )gridDim.x*blockDim.x ) {
-        const int s = perm[j];
+    const size_t nq = ( n + 3 )/4;
+    for( size_t t = blockIdx.x*( size_t )blockDim.x + threadIdx.x; t < nq; t += ( size_t )gridDim.x*blockDim.x ) {
+        const size_t j = 4*t;
+        if( j + 3 < n ) {
+            const int4 s = *reinterpret_cast<const int4 *>( perm + j );
 #pragma unroll
-        for( int c=0; c<7; c++ ) out.c[c][j] = in.c[c][s];
-        out.q[j] = in.q[s];
-        out.key[j] = in.key[s];
+            for( int c=0; c<7; c++ ) {
+                const double a0 = in.c[c][s.x], a1 = in.c[c][s.y], a2 = in.c[c][s.z], a3 = in.c[c][s.w];
+                *reinterpret_cast<double4 *>( out.c[c] + j ) = make_double4( a0, a1, a2, a3 );
+            }
+            const short q0 = in.q[s.x], q1 = in.q[s.y], q2 = in.q[s.z], q3 = in.q[s.w];
+            *reinterpret_cast<short4 *>( out.q + j ) = make_short4( q0, q1, q2, q3 );
+            const int k0 = in.key[s.x], k1 = in.key[s.y], k2 = in.key[s.z], k3 = in.key[s.w];
+            *reinterpret_cast<int4 *>( out.key + j ) = make_int4( k0, k1, k2, k3 );
+        } else {
+            for( size_t jj = j; jj < n; jj++ ) {
+                const int s = perm[jj];
+#pragma unroll
+                for( int c=0; c<7; c++ ) out.c[c][jj] = in.c[c][s];
+                out.q[jj] = in.q[s];
+                out.key[jj] = in.key[s];
+            }
+        }
     }
 }
 
@@ -196,7 +252,10 @@ int launch_sort( sb200_patch *p, int ispec )
     SpeciesDev &s = p->sp[ispec];
     const size_t n = s.n;
     const int ncells = ( int )p->ncells;
-    SB200_CUDA( cudaMemsetAsync( p->count, 0, ( p->ncells+1 )*sizeof( int ), p->stream ) );
+    // the histogram of the new keys was accumulated by the dynamics kernel and the arrival unpack when the
+    // species went through a step; a freshly imported species gets it here
+    const bool have_hist = s.sorted && s.count_valid;
+    if( !have_hist ) SB200_CUDA( cudaMemsetAsync( s.count, 0, ( p->ncells+1 )*sizeof( int ), p->stream ) );
     SB200_CUDA( cudaMemsetAsync( p->cursor, 0, ( p->ncells+1 )*sizeof( int ), p->stream ) );
     SB200_CUDA( cudaMemsetAsync( p->iflags, 0, 8*sizeof( int ), p->stream ) );
     if( n > 0 ) {
@@ -206,13 +265,15 @@ int launch_sort( sb200_patch *p, int ispec )
         // keys written by the fused dynamics kernel / arriving_unpack are already final; a
         // freshly imported species (keys all 0, unsorted) gets them computed here
         const int recompute = s.sorted ? 0 : 1;
-        k_keys_hist<<<blocks, 256, 0, p->stream>>>( p->gd, s.col[0], s.col[1], s.col[2], s.key, p->count, n, recompute, ncells, p->iflags );
-        sb200::g_launches++;
-        SB200_CUDA( cudaGetLastError() );
+        if( !have_hist ) {
+            k_keys_hist<<<blocks, 256, 0, p->stream>>>( p->gd, s.col[0], s.col[1], s.col[2], s.key, s.count, n, recompute, ncells, p->iflags );
+            sb200::g_launches++;
+            SB200_CUDA( cudaGetLastError() );
+        }
     }
     // first = exclusive scan(count) over ncells+1 entries (last = total kept)
-    if( exclusive_scan_int( p, p->count, p->ncells+1 ) ) return 1;
-    SB200_CUDA( cudaMemcpyAsync( s.first, p->count, ( p->ncells+1 )*sizeof( int ), cudaMemcpyDeviceToDevice, p->stream ) );
+    SB200_CUDA( cudaMemcpyAsync( s.first, s.count, ( p->ncells+1 )*sizeof( int ), cudaMemcpyDeviceToDevice, p->stream ) );
+    if( exclusive_scan_int( p, s.first, p->ncells+1 ) ) return 1;
     int kept = 0, flags[8], maxcount = 0;
     unsigned long long qwbits = 0;
     SB200_CUDA( cudaMemsetAsync( p->d_maxcount, 0, sizeof( int ), p->stream ) );
@@ -228,7 +289,7 @@ int launch_sort( sb200_patch *p, int ispec )
         k_scatter_idx<<<blocks, 256, 0, p->stream>>>( s.key, s.first, p->cursor, p->perm, n );
         sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
-        k_cell_sort<<<148*16, 128, 0, p->stream>>>( s.first, p->perm, ncells );
+        k_cell_sort<<<148*8, 256, 0, p->stream>>>( s.first, p->perm, ncells );
         sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
     }
@@ -238,7 +299,8 @@ int launch_sort( sb200_patch *p, int ispec )
         Cols in, out;
         for( int c=0; c<7; c++ ) { in.c[c] = s.col[c]; out.c[c] = p->spare.col[c]; }
         in.q = s.q; in.key = s.key; out.q = p->spare.q; out.key = p->spare.key;
-        const unsigned blocks = ( unsigned )( ( ( size_t )kept + 255 )/256 < 148*16 ? ( ( size_t )kept + 255 )/256 : 148*16 );
+        const size_t nq = ( ( size_t )kept + 3 )/4;
+        const unsigned blocks = ( unsigned )( ( nq + 255 )/256 < 148*32 ? ( nq + 255 )/256 : 148*32 );
         k_gather<<<blocks, 256, 0, p->stream>>>( in, out, p->perm, ( size_t )kept );
         sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
@@ -250,6 +312,7 @@ int launch_sort( sb200_patch *p, int ispec )
     }
     s.n = ( size_t )kept;
     s.sorted = true;
+    s.count_valid = false;
     s.maxcount = maxcount;
     { double v; memcpy( &v, &qwbits, sizeof( v ) ); s.qwmax = v; }
     return 0;
