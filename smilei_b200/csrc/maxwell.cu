@@ -161,39 +161,62 @@ __global__ void __launch_bounds__( 256 ) k_faraday_center( GridDev g,
 }
 
 // centerMagneticFields on the ghost planes the B exchange may have overwritten:
-// B_m (holding B_old there) <- (B + B_m)*0.5.  One thread per (component, shell point).
-__global__ void __launch_bounds__( 256 ) k_center_shell( GridDev g,
+// B_m (holding B_old there) <- (B + B_m)*0.5.  Only the shell is enumerated: for a component with dual
+// dimensions (a,b) the shell is { a in an edge } U { a interior, b in an edge }, an edge being the first and
+// last `o` planes of the dual extent; the third dimension is primal and runs over its full extent.
+struct ShellGeom {
+    int ext[2][3];        // per region: extents of the local box (x,y,z order)
+    int edge[2][3];       // per region and dim: 1 = local index enumerates the 2*o edge planes, 0 = interior/full
+    int off[2][3];        // per region and dim: offset added to an interior/full local index
+    int dimsz[3];         // real extent of the component per dim
+    int o[3];
+    long long count[2];
+};
+
+__global__ void __launch_bounds__( 256 ) k_center_shell( ShellGeom sg0, ShellGeom sg1, ShellGeom sg2, long long sx, long long sy,
         const double *__restrict__ Bx, const double *__restrict__ By, const double *__restrict__ Bz,
         double *__restrict__ Bxm, double *__restrict__ Bym, double *__restrict__ Bzm )
 {
-    const long long per = ( long long )g.ax*g.ay*g.az;
-    const long long total = 3*per;
+    const int c = blockIdx.y;
+    const ShellGeom &sg = c == 0 ? sg0 : c == 1 ? sg1 : sg2;
+    const double *B = c == 0 ? Bx : c == 1 ? By : Bz;
+    double *M = c == 0 ? Bxm : c == 1 ? Bym : Bzm;
+    const long long total = sg.count[0] + sg.count[1];
     for( long long t = blockIdx.x*( long long )blockDim.x + threadIdx.x; t < total; t += ( long long )gridDim.x*blockDim.x ) {
-        const int c = ( int )( t / per );
-        const long long u = t - c*per;
-        const int k = ( int )( u % g.az );
-        const long long r = u / g.az;
-        const int j = ( int )( r % g.ay );
-        const int i = ( int )( r / g.ay );
-        const int dm0 = c==0 ? g.p[0] : g.d[0], dm1 = c==1 ? g.p[1] : g.d[1], dm2 = c==2 ? g.p[2] : g.d[2];
-        if( i >= dm0 || j >= dm1 || k >= dm2 ) continue;
-        const bool sh = ( c!=0 && in_shell( i, g.o[0], g.d[0] ) ) || ( c!=1 && in_shell( j, g.o[1], g.d[1] ) ) || ( c!=2 && in_shell( k, g.o[2], g.d[2] ) );
-        if( !sh ) continue;
-        const long long idx = i*g.sx + j*g.sy + k;
-        const double *B = c==0 ? Bx : c==1 ? By : Bz;
-        double *M = c==0 ? Bxm : c==1 ? Bym : Bzm;
+        const int r = t < sg.count[0] ? 0 : 1;
+        long long u = r == 0 ? t : t - sg.count[0];
+        int loc[3];
+        loc[2] = ( int )( u % sg.ext[r][2] ); u /= sg.ext[r][2];
+        loc[1] = ( int )( u % sg.ext[r][1] );
+        loc[0] = ( int )( u / sg.ext[r][1] );
+        int gi[3];
+#pragma unroll
+        for( int d=0; d<3; d++ )
+            gi[d] = sg.edge[r][d] ? ( loc[d] < sg.o[d] ? loc[d] : sg.dimsz[d] - 2*sg.o[d] + loc[d] ) : loc[d] + sg.off[r][d];
+        const long long idx = gi[0]*sx + gi[1]*sy + gi[2];
         M[idx] = __dmul_rn( __dadd_rn( B[idx], M[idx] ), 0.5 );
     }
 }
 
+// persistent grid: exactly as many CTAs as are resident at once (SMs x occupancy), each striding over the box
+template<class K> static int resident_grid( K kern )
+{
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice( &dev );
+    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, kern, 256, 0 );
+    return sms*( per_sm > 0 ? per_sm : 1 );
+}
+
 int launch_maxwell( sb200_patch *p )
 {
-    const int blocks = 148*8;
+    static const int blocks_a = resident_grid( k_ampere ), blocks_f = resident_grid( k_faraday_center );
+    const int blocks = blocks_a;
     k_ampere<<<blocks, 256, 0, p->stream>>>( p->gd, p->f[SB200_EX], p->f[SB200_EY], p->f[SB200_EZ],
             p->f[SB200_BX], p->f[SB200_BY], p->f[SB200_BZ], p->f[SB200_JX], p->f[SB200_JY], p->f[SB200_JZ] );
             sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
-    k_faraday_center<<<blocks, 256, 0, p->stream>>>( p->gd, p->f[SB200_EX], p->f[SB200_EY], p->f[SB200_EZ],
+    k_faraday_center<<<blocks_f, 256, 0, p->stream>>>( p->gd, p->f[SB200_EX], p->f[SB200_EY], p->f[SB200_EZ],
             p->f[SB200_BX], p->f[SB200_BY], p->f[SB200_BZ], p->f[SB200_BXM], p->f[SB200_BYM], p->f[SB200_BZM] );
             sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
@@ -202,9 +225,31 @@ int launch_maxwell( sb200_patch *p )
 
 int launch_center_shell( sb200_patch *p )
 {
-    k_center_shell<<<148*8, 256, 0, p->stream>>>( p->gd, p->f[SB200_BX], p->f[SB200_BY], p->f[SB200_BZ],
+    const GridDev &g = p->gd;
+    ShellGeom sg[3];
+    long long most = 0;
+    for( int c=0; c<3; c++ ) {
+        // component c (Bx,By,Bz) is primal along c and dual along the two others, da < db
+        const int da = c == 0 ? 1 : 0, db = c == 2 ? 1 : 2;
+        ShellGeom &q = sg[c];
+        for( int d=0; d<3; d++ ) { q.dimsz[d] = d == c ? g.p[d] : g.d[d]; q.o[d] = g.o[d]; }
+        for( int r=0; r<2; r++ )
+            for( int d=0; d<3; d++ ) { q.ext[r][d] = q.dimsz[d]; q.edge[r][d] = 0; q.off[r][d] = 0; }
+        // region 0: a in the edges, b and c full
+        q.ext[0][da] = 2*g.o[da]; q.edge[0][da] = 1;
+        // region 1: a interior, b in the edges, c full
+        q.ext[1][da] = q.dimsz[da] - 2*g.o[da]; q.off[1][da] = g.o[da];
+        q.ext[1][db] = 2*g.o[db]; q.edge[1][db] = 1;
+        for( int r=0; r<2; r++ ) q.count[r] = ( long long )q.ext[r][0]*q.ext[r][1]*q.ext[r][2];
+        if( q.count[0] + q.count[1] > most ) most = q.count[0] + q.count[1];
+    }
+    long long nb = ( most + 255 )/256;
+    if( nb > 148*8 ) nb = 148*8;
+    if( nb < 1 ) nb = 1;
+    dim3 grid( ( unsigned )nb, 3 );
+    k_center_shell<<<grid, 256, 0, p->stream>>>( sg[0], sg[1], sg[2], g.sx, g.sy, p->f[SB200_BX], p->f[SB200_BY], p->f[SB200_BZ],
             p->f[SB200_BXM], p->f[SB200_BYM], p->f[SB200_BZM] );
-            sb200::g_launches++;
+    sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }
