@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: keep NCCL's version / debug banner off it
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "particle pushes/s (gather+push+deposit, whole PIC step incl. Yee + sort + exchange)"
 UNIT = "pushes/s"

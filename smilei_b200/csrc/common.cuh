@@ -69,6 +69,13 @@ struct SpeciesDev {
     int    *leave_idx = nullptr;   // [6][leave_cap] indices of the particles tagged -2..-7, in the order the atomics served them
     size_t leave_cap = 0;
     unsigned long long *d_qwmax = nullptr;   // device copy kept up to date by imports / arrivals (bits of a positive double)
+    // Deferred gather: sb200_sort leaves the columns where they are and only produces the sorted order
+    // perm[j] = index of the particle that belongs in slot j.  The next dynamics kernel reads its particles
+    // through perm and writes them, pushed, at their sorted slots of the spare column set (one pass over the
+    // particle data per step instead of two); any other consumer calls materialize() first.
+    int    *perm = nullptr;
+    size_t perm_cap = 0;
+    bool   perm_pending = false;
 };
 
 struct ParticleBuf {               // spare SoA set the sort scatters into, then swaps with the species
@@ -125,6 +132,8 @@ int launch_rho( sb200_patch *p, int ispec );
 int launch_energy( sb200_patch *p, double *ukin, double *uelm );
 int ensure_spare( sb200_patch *p, size_t cap );
 int ensure_perm( sb200_patch *p, size_t cap );
+void swap_with_spare( sb200_patch *p, SpeciesDev &s );
+int materialize( sb200_patch *p, int ispec );                    // apply a pending sort permutation to the columns (k_gather + swap)
 int ensure_stage( sb200_patch *p, size_t elems );
 int exclusive_scan_int( sb200_patch *p, int *data, size_t n );   // in place, device
 int update_qwmax( sb200_patch *p, int ispec, size_t first, size_t n );   // fold |q*w| of particles [first, first+n) into d_qwmax

@@ -89,9 +89,12 @@ __device__ __forceinline__ void jadd_scaled( jbox_t *p, double vs )
 __device__ __forceinline__ void jadd( jbox_t *p, double v, double jscale ) { jadd_scaled( p, v*jscale ); }
 
 struct DynArgs {
-    double *col[7];
+    double *col[7];           // columns written (pushed particles at their sorted slots)
     short  *q;
     int    *key;
+    const double *in[7];      // columns read: == col unless a sort order is pending, then the unsorted set read through perm
+    const short  *qin;
+    const int    *perm;       // pending sort order (slot -> source index) or nullptr
     const int *first;
     const double *F[6];       // Ex Ey Ez Bxm Bym Bzm
     double *J[3];
@@ -813,10 +816,12 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
         int shifts = 0;                       // (shift+1) per dimension, 2 bits each
         bool fast = false;
         if( active ) {
-            double pos[3] = { a.col[0][ip], a.col[1][ip], a.col[2][ip] };
-            double px = a.col[3][ip], py = a.col[4][ip], pz = a.col[5][ip];
-            const double weight = a.col[6][ip];
-            const short charge = a.q[ip];
+            const size_t is = a.perm ? ( size_t )a.perm[ip] : ip;       // deferred gather of the sort (sort.cu)
+            double pos[3] = { a.in[0][is], a.in[1][is], a.in[2][is] };
+            double px = a.in[3][is], py = a.in[4][is], pz = a.in[5][is];
+            const double weight = a.in[6][is];
+            const short charge = a.qin[is];
+            if( a.perm ) { a.col[6][ip] = weight; a.q[ip] = charge; }
 
             double cd[3][NW];
             int sp[3], sd[3];
@@ -1069,9 +1074,22 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
         SB200_CUDA( cudaMalloc( &p->sc_iold, 3*s.n*sizeof( int ) ) );
         p->sc_cap = s.n;
     }
+    // SB200_DYN_GENERAL=1 selects the general one-thread-per-particle kernel: A/B checks only
+    static const bool general = getenv( "SB200_DYN_GENERAL" ) != nullptr;
+    if( general && materialize( p, ispec ) ) return 1;
     DynArgs a;
-    for( int c=0; c<7; c++ ) a.col[c] = s.col[c];
-    a.q = s.q; a.key = s.key; a.first = s.first;
+    const bool deferred = s.perm_pending;      // read through the pending sort order, write the sorted spare set
+    if( deferred ) {
+        if( ensure_spare( p, s.cap ) ) return 1;
+        for( int c=0; c<7; c++ ) { a.in[c] = s.col[c]; a.col[c] = p->spare.col[c]; }
+        a.qin = s.q; a.q = p->spare.q; a.key = p->spare.key; a.perm = s.perm;
+        swap_with_spare( p, s );               // from here on s.col is the set the kernel writes
+        s.perm_pending = false;
+    } else {
+        for( int c=0; c<7; c++ ) { a.in[c] = s.col[c]; a.col[c] = s.col[c]; }
+        a.qin = s.q; a.q = s.q; a.key = s.key; a.perm = nullptr;
+    }
+    a.first = s.first;
     const int fid[6] = { SB200_EX, SB200_EY, SB200_EZ, SB200_BXM, SB200_BYM, SB200_BZM };
     for( int c=0; c<6; c++ ) a.F[c] = p->f[fid[c]];
     a.J[0] = p->f[SB200_JX]; a.J[1] = p->f[SB200_JY]; a.J[2] = p->f[SB200_JZ];
@@ -1094,8 +1112,6 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
         a.jscale = ldexp( 1.0, 61 - e );                // bound*jscale < 2^61
         a.jinv = ldexp( 1.0, e - 61 );
     }
-    // SB200_DYN_GENERAL=1 selects the general one-thread-per-particle kernel: A/B checks only
-    static const bool general = getenv( "SB200_DYN_GENERAL" ) != nullptr;
     if( !general ) {
         if( g.order == 2 ) {
             using T = CG<2>::T;

@@ -72,6 +72,7 @@ int launch_energy( sb200_patch *p, double *ukin, double *uelm )
     std::vector<double> host( p->nspec + 6, 0. );
     if( ukin ) {
         for( int s=0; s<p->nspec; s++ ) {
+            if( materialize( p, s ) ) return 1;       // the sum tree is defined on the sorted order
             SpeciesDev &S = p->sp[s];
             k_ukin<<<RED_BLOCKS, RED_T, 0, p->stream>>>( S.col[3], S.col[4], S.col[5], S.col[6], S.n, partial );
             sb200::g_launches++;

@@ -285,6 +285,7 @@ int sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wra
     SpeciesDev &s = p->sp[ispec];
     *n_packed = 0;
     if( s.n == 0 ) return 0;
+    if( materialize( p, ispec ) ) return 1;
     const int tag = -2 - 2*dim - side;
     const GridDev &g = p->gd;
     const double hi = g.cell[dim]*( double )( g.n[dim]*g.npatch[dim] );   // Patch.cpp:626: cell_length*global_size
@@ -340,6 +341,7 @@ int sb200_leaving_pack_known( sb200_patch *p, int ispec, int dim, int side, doub
     if( n_known == 0 ) return 0;
     SB200_CHECK( dev_buf, "sb200_leaving_pack_known: null buffer" );
     SB200_CUDA( cudaSetDevice( p->device ) );
+    if( materialize( p, ispec ) ) return 1;
     const int tag = -2 - 2*dim - side;
     const GridDev &g = p->gd;
     const double hi = g.cell[dim]*( double )( g.n[dim]*g.npatch[dim] );
@@ -360,6 +362,7 @@ int sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, siz
     SB200_CHECK( dev_buf, "sb200_arriving_unpack: null buffer" );
     SB200_CHECK( s.n + n <= s.cap, "sb200_arriving_unpack: species capacity exceeded" );
     SB200_CUDA( cudaSetDevice( p->device ) );
+    if( materialize( p, ispec ) ) return 1;
     MutCols out;
     for( int c=0; c<7; c++ ) out.c[c] = s.col[c];
     out.q = s.q; out.key = s.key;

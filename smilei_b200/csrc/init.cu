@@ -93,6 +93,7 @@ extern "C" int sb200_species_init_thermal( sb200_patch *p, int ispec, const int 
     s.n = n;
     s.sorted = false;
     s.count_valid = false;
+    s.perm_pending = false;
     SB200_CUDA( cudaMemsetAsync( s.d_qwmax, 0, sizeof( unsigned long long ), p->stream ) );
     return update_qwmax( p, ispec, 0, n );
 }

@@ -183,6 +183,7 @@ int sb200_patch_destroy( sb200_patch *p )
         if( p->sp[s].count ) cudaFree( p->sp[s].count );
         if( p->sp[s].d_qwmax ) cudaFree( p->sp[s].d_qwmax );
         if( p->sp[s].leave_idx ) cudaFree( p->sp[s].leave_idx );
+        if( p->sp[s].perm ) cudaFree( p->sp[s].perm );
     }
     free_particle_cols( p->spare.col, &p->spare.q, &p->spare.key );
     void *misc[] = { p->cursor, p->perm, p->blocksums, p->stage, p->red, p->leave_counts, p->iflags, p->d_maxcount,
@@ -265,6 +266,7 @@ int sb200_species_set( sb200_patch *p, int ispec,
     SB200_CUDA( cudaMemsetAsync( s.d_qwmax, 0, sizeof( unsigned long long ), p->stream ) );
     s.n = n;
     s.count_valid = false;
+    s.perm_pending = false;
     if( update_qwmax( p, ispec, 0, n ) ) return 1;
     SB200_CUDA( cudaStreamSynchronize( p->stream ) );
     s.sorted = false;
@@ -279,6 +281,7 @@ int sb200_species_get( sb200_patch *p, int ispec,
     SpeciesDev &s = p->sp[ispec];
     SB200_CHECK( n <= s.n, "sb200_species_get: asking for more particles than the species holds" );
     SB200_CUDA( cudaSetDevice( p->device ) );
+    if( materialize( p, ispec ) ) return 1;
     double *dst[7] = { x, y, z, px, py, pz, w };
     for( int c=0; c<7; c++ ) if( dst[c] ) SB200_CUDA( cudaMemcpyAsync( dst[c], s.col[c], n*sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
     if( q ) SB200_CUDA( cudaMemcpyAsync( q, s.q, n*sizeof( short ), cudaMemcpyDeviceToHost, p->stream ) );
@@ -298,6 +301,8 @@ int sb200_species_device_ptr( sb200_patch *p, int ispec, int column, void **dev_
 {
     SB200_CHECK( p && dev_ptr && ispec >= 0 && ispec < p->nspec, "sb200_species_device_ptr: bad arguments" );
     SpeciesDev &s = p->sp[ispec];
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    if( materialize( p, ispec ) ) return 1;
     if( column >= 0 && column < 7 ) *dev_ptr = s.col[column];
     else if( column == 7 ) *dev_ptr = s.q;
     else if( column == 8 ) *dev_ptr = s.key;
@@ -400,7 +405,7 @@ int sb200_dynamics( sb200_patch *p, int ispec, int flags )
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( launch_dynamics( p, ispec, flags ) ) return 1;
     // diag step: rho from the new positions (currentsAndDensity, Projector3D2Order.cpp:509-519)
-    if( flags & SB200_DYN_DIAG_RHO ) return launch_rho( p, ispec );
+    if( flags & SB200_DYN_DIAG_RHO ) return launch_rho( p, ispec );      // (the dynamics kernel consumed any pending sort order)
     return 0;
 }
 

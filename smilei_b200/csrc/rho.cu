@@ -68,6 +68,7 @@ __global__ void __launch_bounds__( 256 ) k_deposit_rho( GridDev g, const double 
 
 int launch_rho( sb200_patch *p, int ispec )
 {
+    if( materialize( p, ispec ) ) return 1;
     SpeciesDev &s = p->sp[ispec];
     if( s.n == 0 ) return 0;
     const unsigned blocks = ( unsigned )( ( s.n + 255 )/256 < 148*16 ? ( s.n + 255 )/256 : 148*16 );

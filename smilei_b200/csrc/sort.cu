@@ -216,6 +216,15 @@ int update_qwmax( sb200_patch *p, int ispec, size_t first, size_t n )
 
 struct Cols { double *c[7]; short *q; int *key; };
 
+// exchange the species' column set with the patch's spare set
+void swap_with_spare( sb200_patch *p, SpeciesDev &s )
+{
+    for( int c=0; c<7; c++ ) { double *t = s.col[c]; s.col[c] = p->spare.col[c]; p->spare.col[c] = t; }
+    { short *t = s.q; s.q = p->spare.q; p->spare.q = t; }
+    { int *t = s.key; s.key = p->spare.key; p->spare.key = t; }
+    const size_t tc = s.cap; s.cap = p->spare.cap; p->spare.cap = tc;
+}
+
 // out[c][j] = in[c][perm[j]] for the 9 columns.  Four consecutive output slots per thread: 36 independent
 // loads in flight per thread and 32-B stores; perm is the identity plus small shifts except around movers, so
 // the reads are almost as contiguous as the writes.
@@ -247,9 +256,40 @@ __global__ void __launch_bounds__( 256 ) k_gather( Cols in, Cols out, const int 
     }
 }
 
+static int ensure_species_perm( SpeciesDev &s )
+{
+    if( s.perm_cap >= s.cap && s.perm ) return 0;
+    if( s.perm ) cudaFree( s.perm );
+    s.perm = nullptr; s.perm_cap = 0;
+    SB200_CUDA( cudaMalloc( &s.perm, ( s.cap > 0 ? s.cap : 1 )*sizeof( int ) ) );
+    s.perm_cap = s.cap;
+    return 0;
+}
+
+// Apply a pending sort permutation: out[c][j] = in[c][perm[j]] into the spare set, then swap the sets.
+int materialize( sb200_patch *p, int ispec )
+{
+    SpeciesDev &s = p->sp[ispec];
+    if( !s.perm_pending ) return 0;
+    s.perm_pending = false;
+    if( s.n == 0 ) return 0;
+    if( ensure_spare( p, s.cap ) ) return 1;
+    Cols in, out;
+    for( int c=0; c<7; c++ ) { in.c[c] = s.col[c]; out.c[c] = p->spare.col[c]; }
+    in.q = s.q; in.key = s.key; out.q = p->spare.q; out.key = p->spare.key;
+    const size_t nq = ( s.n + 3 )/4;
+    const unsigned blocks = ( unsigned )( ( nq + 255 )/256 < 148*32 ? ( nq + 255 )/256 : 148*32 );
+    k_gather<<<blocks, 256, 0, p->stream>>>( in, out, s.perm, s.n );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    swap_with_spare( p, s );
+    return 0;
+}
+
 int launch_sort( sb200_patch *p, int ispec )
 {
     SpeciesDev &s = p->sp[ispec];
+    if( materialize( p, ispec ) ) return 1;          // a sort on top of an unapplied sort: apply the first one
     const size_t n = s.n;
     const int ncells = ( int )p->ncells;
     // the histogram of the new keys was accumulated by the dynamics kernel and the arrival unpack when the
@@ -259,8 +299,7 @@ int launch_sort( sb200_patch *p, int ispec )
     SB200_CUDA( cudaMemsetAsync( p->cursor, 0, ( p->ncells+1 )*sizeof( int ), p->stream ) );
     SB200_CUDA( cudaMemsetAsync( p->iflags, 0, 8*sizeof( int ), p->stream ) );
     if( n > 0 ) {
-        if( ensure_spare( p, s.cap ) ) return 1;
-        if( ensure_perm( p, s.cap ) ) return 1;
+        if( ensure_species_perm( s ) ) return 1;
         const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*16 ? ( n + 255 )/256 : 148*16 );
         // keys written by the fused dynamics kernel / arriving_unpack are already final; a
         // freshly imported species (keys all 0, unsorted) gets them computed here
@@ -286,31 +325,18 @@ int launch_sort( sb200_patch *p, int ispec )
     SB200_CUDA( cudaMemcpyAsync( flags, p->iflags, 8*sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
     if( n > 0 ) {
         const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*16 ? ( n + 255 )/256 : 148*16 );
-        k_scatter_idx<<<blocks, 256, 0, p->stream>>>( s.key, s.first, p->cursor, p->perm, n );
+        k_scatter_idx<<<blocks, 256, 0, p->stream>>>( s.key, s.first, p->cursor, s.perm, n );
         sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
-        k_cell_sort<<<148*8, 256, 0, p->stream>>>( s.first, p->perm, ncells );
+        k_cell_sort<<<148*8, 256, 0, p->stream>>>( s.first, s.perm, ncells );
         sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
     }
     SB200_CUDA( cudaStreamSynchronize( p->stream ) );
     SB200_CHECK( flags[0] == 0, "sb200_sort: particles outside the patch without a leaving tag (positions must lie in [min,max) of the patch)" );
-    if( kept > 0 ) {
-        Cols in, out;
-        for( int c=0; c<7; c++ ) { in.c[c] = s.col[c]; out.c[c] = p->spare.col[c]; }
-        in.q = s.q; in.key = s.key; out.q = p->spare.q; out.key = p->spare.key;
-        const size_t nq = ( ( size_t )kept + 3 )/4;
-        const unsigned blocks = ( unsigned )( ( nq + 255 )/256 < 148*32 ? ( nq + 255 )/256 : 148*32 );
-        k_gather<<<blocks, 256, 0, p->stream>>>( in, out, p->perm, ( size_t )kept );
-        sb200::g_launches++;
-        SB200_CUDA( cudaGetLastError() );
-        // swap the species storage with the spare set
-        for( int c=0; c<7; c++ ) { double *t = s.col[c]; s.col[c] = p->spare.col[c]; p->spare.col[c] = t; }
-        { short *t = s.q; s.q = p->spare.q; p->spare.q = t; }
-        { int *t = s.key; s.key = p->spare.key; p->spare.key = t; }
-        const size_t tc = s.cap; s.cap = p->spare.cap; p->spare.cap = tc;
-    }
+    // the columns stay where they are: the next dynamics kernel reads them through perm (materialize() for anyone else)
     s.n = ( size_t )kept;
+    s.perm_pending = kept > 0;
     s.sorted = true;
     s.count_valid = false;
     s.maxcount = maxcount;
