@@ -109,6 +109,7 @@ struct DynArgs {
     double  one_over_mass;
     double  jscale, jinv;     // fixed-point scale of the J box and its inverse
     int     tiles[3];
+    int     norank;           // A/B switch: hand cells out in z-row order instead of by rank of their particle count
 };
 
 // a particle tagged for exchange: count it and remember its index (sb200_leaving_pack orders the list)
@@ -556,10 +557,10 @@ constexpr int XQD = 9*XQ + XQ/2;                         // doubles per warp que
 
 template<int ORDER> struct CG;
 template<> struct CG<2> {
-    using T = Tile<2, 4, 8, 8>;
+    using T = Tile<2, 4, 4, 8>;
     static constexpr int NSL = 2;      // flux points reduced together
     static constexpr int MINB = 2;     // CTAs per SM asked of the compiler
-    static constexpr int LOG2CELLS = 8;
+    static constexpr int LOG2CELLS = 7;
 };
 template<> struct CG<4> {
     using T = Tile<4, 4, 4, 8>;
@@ -992,6 +993,389 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
     }
 }
 
+
+// =================================================================================================
+// Order-2 production kernel: cell groups of FOUR lanes and a two-phase deposit.
+//
+// The shuffle transpose-reduction of k_dynamics_cg costs more issue slots than the arithmetic it sums
+// (FSEL + SHFL were 20 % of all instructions).  Here the particles of a cell are still walked by one lane
+// group, but the per-cell sums are formed differently:
+//   phase 1  lane = one particle: gather, push, tag, key, new shape; the lane leaves what the deposit needs
+//            — per dimension M = (S0+S1)/2 and DS = S1-S0 on the 3 nodes, and the two flux coefficients per
+//            component — in a 24-double record of the warp's staging area in shared memory;
+//   phase 2  lane = one current COMPONENT of the cell (lanes 0..2 of the group): it walks the group's staged
+//            records and accumulates its 2 x 3 x 3 values in registers,
+//                J_c[f][j][k] += Cf_c[f] * ( M_a[j] M_b[k] + DS_a[j] DS_b[k] / 12 )
+//            (the Esirkepov weight S0S0 + (DS S0 + S0 DS)/2 + DS DS/3 rewritten around the mid-point shape).
+//            The registers persist over all rounds of the cell; 18 fixed-point adds per (cell, component)
+//            reach the J box when the cell is finished.  No shuffles, no selects, no redundant flops.
+// A lane group owns whole cells (cell = group + 64 m), so there is no search for the cell of a work item.
+// Particles that change cell stage zero flux coefficients and take the warp's crosser queue (cross_pass).
+// =================================================================================================
+namespace o2 {
+using T = CG<2>::T;
+constexpr int G4 = 4;                                    // lanes per cell group
+constexpr int NGRP = DYN_THREADS/G4;                     // 64 groups per CTA
+constexpr int NCELL = T::TX*T::TY*T::TZ;                 // 128 cells per tile
+constexpr int CELLS_PER_GROUP = NCELL/NGRP;
+static_assert( NCELL % NGRP == 0 && NCELL <= 256, "whole cells per lane group; cell ranks fit a byte" );
+constexpr int REC = 26;                                  // doubles per staged record: 24 used, padded so that the 4 records of a group fall in distinct banks
+constexpr int GSTAGE = G4*REC;                           // doubles per group
+constexpr int WSTAGE = 8*GSTAGE;                         // doubles per warp
+constexpr size_t BYTES = ( size_t )( 6*T::FBOX + 3*T::JBOX + WSTAGE*( DYN_THREADS/32 ) + XQD*( DYN_THREADS/32 ) )*sizeof( double );
+constexpr unsigned TMA_BYTES = 6u*T::FVOL*sizeof( double );
+static_assert( 4*CGDim<2>::XSCR <= WSTAGE, "the crosser scratch of a warp aliases its staging area" );
+}
+
+template<int PUSHER, bool SCRATCH>
+__global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev g, const DynArgs a, const __grid_constant__ FieldMaps tm )
+{
+    using namespace o2;
+    constexpr int NW = 3;
+    extern __shared__ __align__( 128 ) double smem[];
+    double *sF = smem;
+    jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FBOX );
+    __shared__ __align__( 8 ) unsigned long long tma_bar;
+    __shared__ int cell_first[NCELL];
+    __shared__ int cell_cnt[NCELL];
+    __shared__ unsigned char cell_order[NCELL];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    int b = blockIdx.x;
+    const int tz = b % a.tiles[2]; b /= a.tiles[2];
+    const int ty = b % a.tiles[1];
+    const int tx = b / a.tiles[1];
+    const int c0[3] = { tx*T::TX, ty*T::TY, tz*T::TZ };
+    const int zs = ( c0[2] + g.o[2] - T::H ) & 1;          // field boxes start on an even z index
+    const int zj = ( c0[2] + g.o[2] - T::H - 1 ) & 1;      // J box too
+
+    if( tid == 0 ) tma_bar_init( &tma_bar, 1 );
+    __syncthreads();
+    if( tid == 0 ) {
+        tma_expect( &tma_bar, TMA_BYTES );
+#pragma unroll
+        for( int c=0; c<6; c++ )
+            tma_load_3d( sF + c*T::FBOX, &tm.m[c], &tma_bar, c0[2] + g.o[2] - T::H - zs, c0[1] + g.o[1] - T::H, c0[0] + g.o[0] - T::H );
+    }
+    int mine = 0;
+    if( tid < NCELL ) {
+        const int lz = tid % T::TZ, ly = ( tid / T::TZ ) % T::TY, lx = tid / ( T::TZ*T::TY );
+        const int ix = c0[0]+lx, iy = c0[1]+ly, iz = c0[2]+lz;
+        int beg = 0, cnt = 0;
+        if( ix < g.ncell[0] && iy < g.ncell[1] && iz < g.ncell[2] ) {
+            const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + iz;
+            beg = a.first[cell];
+            cnt = a.first[cell+1] - beg;
+        }
+        cell_first[tid] = beg;
+        cell_cnt[tid] = cnt;
+        mine = cnt;
+    }
+    for( int t = tid; t < 3*T::JBOX; t += DYN_THREADS ) sJ[t] = 0ull;
+    const int any = __syncthreads_or( mine );
+    tma_wait( &tma_bar, 0 );          // the boxes must have landed before this CTA's shared memory is used or released
+    if( !any ) return;
+    // The 8 lane groups of a warp walk their cells in lockstep, so a round costs the warp as much as its
+    // fullest cell needs.  Cells are therefore handed out by RANK of their particle count (fullest first):
+    // the 8 cells a warp works on together hold almost the same number of particles.
+    if( tid < NCELL ) {
+        int rank = tid;
+        if( !a.norank ) {
+            rank = 0;
+            for( int u=0; u<NCELL; u++ ) {
+                const int c = cell_cnt[u];
+                rank += ( c > mine || ( c == mine && u < tid ) ) ? 1 : 0;
+            }
+        }
+        cell_order[rank] = ( unsigned char )tid;
+    }
+    __syncthreads();
+
+    const int gl = lane & ( G4-1 );                       // lane in the group = particle slot (phase 1) = component (phase 2)
+    const int gw = lane >> 2;                             // group in the warp
+    double *wstage = smem + 6*T::FBOX + 3*T::JBOX + WSTAGE*warp;
+    double *rec = wstage + gw*GSTAGE + gl*REC;            // this lane's record (phase 1)
+    double *xscr = wstage + CGDim<2>::XSCR*( lane >> 3 ); // crosser scratch of the 8-lane group: aliases the staging area
+    double *xq = smem + 6*T::FBOX + 3*T::JBOX + WSTAGE*( DYN_THREADS/32 ) + XQD*warp;
+    int *xqm = reinterpret_cast<int *>( xq + 9*XQ );
+    int qh = 0, qn = 0;
+
+    // phase-2 geometry of this lane: component c = gl (lane 3 idles), transverse dimensions (da, db)
+    const int cc = gl < 3 ? gl : 0;
+    const int da = cc == 0 ? 1 : 0, db = cc == 2 ? 1 : 2;
+    const double *p2a = wstage + gw*GSTAGE + 6*da, *p2b = wstage + gw*GSTAGE + 6*db, *p2c = wstage + gw*GSTAGE + 18 + 2*cc;
+    // J-box strides of the flux index and of the two transverse indices, and the offset of (f,j,k) = (0,0,0)
+    const int sf_ = cc == 0 ? T::JY*T::JZ : ( cc == 1 ? T::JZ : 1 );
+    const int sa_ = cc == 0 ? T::JZ : T::JY*T::JZ;
+    const int sb_ = cc == 2 ? T::JZ : 1;
+    const int jo_ = cc*T::JBOX + 2*sf_ + sa_ + sb_;
+
+#pragma unroll 1
+    for( int m = 0; m < CELLS_PER_GROUP; m++ ) {
+        const int cellt = cell_order[m*NGRP + ( tid >> 2 )];
+        const int cl[3] = { cellt / ( T::TZ*T::TY ), ( cellt / T::TZ ) % T::TY, cellt % T::TZ };
+        const int cnt = cell_cnt[cellt];
+        const size_t first = ( size_t )cell_first[cellt];
+        int nr = ( cnt + G4 - 1 )/G4;
+        nr = __reduce_max_sync( 0xffffffffu, nr );        // rounds of the warp's fullest cell
+        double acc[2][NW][NW];
+#pragma unroll
+        for( int f=0; f<2; f++ )
+#pragma unroll
+            for( int j=0; j<NW; j++ )
+#pragma unroll
+                for( int k=0; k<NW; k++ ) acc[f][j][k] = 0.;
+
+#pragma unroll 1
+        for( int r = 0; r < nr; r++ ) {
+            const int slot = r*G4 + gl;
+            const bool active = slot < cnt;
+            const size_t ip = first + ( size_t )( active ? slot : 0 );
+            double cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
+            int shifts = 0, xmeta = 0;
+            double xe = 0., xc = 0.;
+            bool fast = false, one = false;
+            // ---------------- phase 1: one particle per lane
+            if( active ) {
+                const size_t is = a.perm ? ( size_t )a.perm[ip] : ip;
+                double pos[3] = { a.in[0][is], a.in[1][is], a.in[2][is] };
+                double px = a.in[3][is], py = a.in[4][is], pz = a.in[5][is];
+                const double weight = a.in[6][is];
+                const short charge = a.qin[is];
+                if( a.perm ) { a.col[6][ip] = weight; a.q[ip] = charge; }
+
+                double S0[3][NW], cd[3][NW];
+                int sp[3], sd[3];
+#pragma unroll
+                for( int d=0; d<3; d++ ) {
+                    const double pn = __dmul_rn( pos[d], g.dxi[d] );       // no contraction into the subtraction below: deltaold is bit-exact
+                    const int ipn = ( int )round( pn );
+                    xdelta[d] = pn - ( double )ipn;
+                    Shape<2>::w( xdelta[d], S0[d] );
+                    const int idn = ( int )round( pn + 0.5 );
+                    const double dd = pn - ( double )idn + 0.5;
+                    Shape<2>::w( dd, cd[d] );
+                    if( ipn - g.begin[d] - g.o[d] - c0[d] != cl[d] ) atomicAdd( &a.iflags[1], 1 );
+                    sp[d] = cl[d] + T::H + ( d == 2 ? zs : 0 );
+                    sd[d] = sp[d] + ( idn - ipn );
+                }
+                const double Ex = gather<T>( sF+0*T::FBOX, cd[0], S0[1], S0[2], sd[0], sp[1], sp[2] );
+                const double Ey = gather<T>( sF+1*T::FBOX, S0[0], cd[1], S0[2], sp[0], sd[1], sp[2] );
+                const double Ez = gather<T>( sF+2*T::FBOX, S0[0], S0[1], cd[2], sp[0], sp[1], sd[2] );
+                const double Bx = gather<T>( sF+3*T::FBOX, S0[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+                const double By = gather<T>( sF+4*T::FBOX, cd[0], S0[1], cd[2], sd[0], sp[1], sd[2] );
+                const double Bz = gather<T>( sF+5*T::FBOX, cd[0], cd[1], S0[2], sd[0], sd[1], sp[2] );
+
+                const double cmd = ( double )charge*a.one_over_mass*g.dts2;
+                double dxp, dyp, dzp, invgf;
+                push<PUSHER>( cmd, g.dt, px, py, pz, Ex, Ey, Ez, Bx, By, Bz, dxp, dyp, dzp, invgf );
+                const double npos[3] = { pos[0] + dxp, pos[1] + dyp, pos[2] + dzp };
+                a.col[0][ip] = npos[0]; a.col[1][ip] = npos[1]; a.col[2][ip] = npos[2];
+                a.col[3][ip] = px; a.col[4][ip] = py; a.col[5][ip] = pz;
+                if( SCRATCH ) {
+                    a.sc_E[0*a.n+ip] = Ex; a.sc_E[1*a.n+ip] = Ey; a.sc_E[2*a.n+ip] = Ez;
+                    a.sc_B[0*a.n+ip] = Bx; a.sc_B[1*a.n+ip] = By; a.sc_B[2*a.n+ip] = Bz;
+                    a.sc_invgf[ip] = invgf;
+#pragma unroll
+                    for( int d=0; d<3; d++ ) {
+                        a.sc_iold[d*a.n+ip] = cl[d] + c0[d] + g.o[d];
+                        a.sc_delta[d*a.n+ip] = xdelta[d];
+                    }
+                }
+
+                const double charge_weight = g.inv_cell_volume*( double )charge*weight;
+                cr[0] = charge_weight*g.d_ov_dt[0]; cr[1] = charge_weight*g.d_ov_dt[1]; cr[2] = charge_weight*g.d_ov_dt[2];
+
+                // new shape, tag / next key; the record of the deposit: per dimension M[3], DS[3] on the HOME nodes
+                // (the 3 nodes of S0) and the flux coefficients at the 2 home flux points.  A particle that moved to
+                // the next node along a dimension has S1 shifted by one node: two of its three weights still fall on
+                // home nodes, the third (s1e) on the node just outside; the flux running sum (Projector3D2Order.cpp:
+                // 215-228) starts one node earlier when the shift is negative.
+                int nkey[3], tag = 0, nx = 0;
+                double cf[3][2];
+#pragma unroll
+                for( int d=0; d<3; d++ ) {
+                    const double pn = __dmul_rn( npos[d], g.dxi[d] );
+                    const int ipn = ( int )round( pn );
+                    double w1[NW];
+                    Shape<2>::w( pn - ( double )ipn, w1 );
+                    const int shift = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );
+                    shifts |= ( shift+1 ) << ( 2*d );
+                    nkey[d] = ( int )( ( double )ipn - g.min_loc_round[d] );
+                    if( tag == 0 ) {
+                        if( npos[d] < g.xmin[d] ) tag = -2 - 2*d;
+                        else if( npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
+                    }
+                    xnpos[d] = pn;
+                    double s1a = w1[0], s1b = w1[1], s1c = w1[2], s1e = 0.;
+                    if( shift > 0 ) { s1e = w1[2]; s1c = w1[1]; s1b = w1[0]; s1a = 0.; }
+                    else if( shift < 0 ) { s1e = w1[0]; s1a = w1[1]; s1b = w1[2]; s1c = 0.; }
+                    const double ds0 = s1a - S0[d][0], ds1 = s1b - S0[d][1], ds2 = s1c - S0[d][2];
+                    double2 *r2 = reinterpret_cast<double2 *>( rec + 6*d );
+                    r2[0] = make_double2( S0[d][0] + 0.5*ds0, S0[d][1] + 0.5*ds1 );
+                    r2[1] = make_double2( S0[d][2] + 0.5*ds2, ds0 );
+                    r2[2] = make_double2( ds1, ds2 );
+                    cf[d][0] = -cr[d]*( ( shift < 0 ? s1e : 0. ) + ds0 );
+                    cf[d][1] = cf[d][0] - cr[d]*ds1;
+                    if( shift != 0 ) {
+                        nx++;
+                        xmeta = d | ( shift > 0 ? 4 : 0 );
+                        xe = s1e;
+                        xc = shift > 0 ? cf[d][1] - cr[d]*ds2 : -cr[d]*s1e;     // flux coefficient at the point outside the home window
+                    }
+                }
+                int key = tag;
+                if( tag == 0 ) { key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2]; atomicAdd( &a.count[key], 1 ); }
+                else note_leaver( a, tag, ip );
+                a.key[ip] = key;
+                fast = nx == 0;
+                one = nx == 1;
+                const bool home = nx <= 1;           // phase 2 deposits the home part; particles that changed node in 2+ dimensions go to the queue whole
+                double2 *r2 = reinterpret_cast<double2 *>( rec + 18 );
+                r2[0] = home ? make_double2( cf[0][0], cf[0][1] ) : make_double2( 0., 0. );
+                r2[1] = home ? make_double2( cf[1][0], cf[1][1] ) : make_double2( 0., 0. );
+                r2[2] = home ? make_double2( cf[2][0], cf[2][1] ) : make_double2( 0., 0. );
+            } else {
+                double2 *r2 = reinterpret_cast<double2 *>( rec );
+#pragma unroll
+                for( int i=0; i<12; i++ ) r2[i] = make_double2( 0., 0. );
+            }
+            __syncwarp();
+            // ---------------- phase 2: one current component of the cell per lane
+            if( gl < 3 ) {
+#pragma unroll
+                for( int pp=0; pp<G4; pp++ ) {
+                    const double2 *qa = reinterpret_cast<const double2 *>( p2a + pp*REC );
+                    const double2 *qb = reinterpret_cast<const double2 *>( p2b + pp*REC );
+                    const double2 a0 = qa[0], a1 = qa[1], a2 = qa[2];
+                    const double2 b0 = qb[0], b1 = qb[1], b2 = qb[2];
+                    const double2 cf = *reinterpret_cast<const double2 *>( p2c + pp*REC );
+                    const double Ma[NW] = { a0.x, a0.y, a1.x }, Da[NW] = { a1.y, a2.x, a2.y };
+                    const double Mb[NW] = { b0.x, b0.y, b1.x };
+                    const double twelfth = 1./12.;
+                    const double Db[NW] = { b1.y*twelfth, b2.x*twelfth, b2.y*twelfth };
+#pragma unroll
+                    for( int j=0; j<NW; j++ )
+#pragma unroll
+                        for( int k=0; k<NW; k++ ) {
+                            const double W = Ma[j]*Mb[k] + Da[j]*Db[k];
+                            acc[0][j][k] += cf.x*W;
+                            acc[1][j][k] += cf.y*W;
+                        }
+                }
+            }
+            __syncwarp();
+            // ---------------- particles that moved to the next node in ONE dimension: what falls outside the home
+            //                  window is 21 values — 9 of the flux component at the outer flux point, 2 x 3 of each
+            //                  other component on the outer node plane.  An 8-lane octet takes one such particle.
+            for( unsigned rem = __ballot_sync( 0xffffffffu, active && one ); rem; ) {
+                const unsigned srcu = __fns( rem, 0, ( lane >> 3 ) + 1 );
+                const bool work = srcu != 0xffffffffu;
+                const int src = work ? ( int )srcu : 0;
+                const int meta = __shfl_sync( 0xffffffffu, xmeta, src );
+                const double se = __shfl_sync( 0xffffffffu, xe, src );
+                const double cx = __shfl_sync( 0xffffffffu, xc, src );
+                const int cellx = __shfl_sync( 0xffffffffu, cellt, src );
+                if( work ) {
+                    const int d = meta & 3, up = meta >> 2;
+                    const int a1 = d == 0 ? 1 : 0, a2 = d == 2 ? 1 : 2;
+                    const int strd = d == 0 ? T::JY*T::JZ : ( d == 1 ? T::JZ : 1 );
+                    const int str1 = a1 == 0 ? T::JY*T::JZ : T::JZ;                 // a1 is x or y
+                    const int str2 = a2 == 1 ? T::JZ : 1;                           // a2 is y or z
+                    const double *rc = wstage + ( src >> 2 )*GSTAGE + ( src & 3 )*REC;
+                    jbox_t *jbx = sJ + zj + ( ( cellx / ( T::TZ*T::TY ) )*T::JY + ( cellx / T::TZ ) % T::TY )*T::JZ + cellx % T::TZ;
+                    const double twelfth = 1./12.;
+#pragma unroll
+                    for( int h=0; h<3; h++ ) {
+                        const int it = ( lane & 7 ) + 8*h;
+                        if( it < 21 ) {
+                            int comp, bdim, kk, off;
+                            double C, P, Q;
+                            if( it < 9 ) {                           // flux component d at the outer flux point, home (j,k)
+                                const int j = it/3;
+                                kk = it - 3*j;
+                                comp = d; bdim = a2;
+                                C = cx; P = rc[6*a1 + j]; Q = rc[6*a1 + 3 + j];
+                                off = ( up ? 4 : 1 )*strd + ( 1+j )*str1 + ( 1+kk )*str2;
+                            } else {                                 // component a1 / a2 on the outer node plane of d
+                                const int t = it - 9;
+                                const int second = t >= 6 ? 1 : 0;
+                                const int u = t - 6*second;
+                                const int f = u/3;
+                                kk = u - 3*f;
+                                comp = second ? a2 : a1; bdim = second ? a1 : a2;
+                                C = rc[18 + 2*comp + f]; P = 0.5*se; Q = se;
+                                off = ( 2+f )*( second ? str2 : str1 ) + ( up ? 4 : 0 )*strd + ( 1+kk )*( second ? str1 : str2 );
+                            }
+                            const double W = P*rc[6*bdim + kk] + Q*( rc[6*bdim + 3 + kk]*twelfth );
+                            jadd( jbx + comp*T::JBOX + off, C*W, a.jscale );
+                        }
+                    }
+                }
+#pragma unroll
+                for( int i=0; i<4; i++ ) rem &= rem - 1u;      // the four lowest set bits are done (x & (x-1) of 0 stays 0)
+            }
+            __syncwarp();
+            // ---------------- particles that moved in 2 or 3 dimensions: the warp's queue, 4 at a time (cross_pass)
+            unsigned xmask = __ballot_sync( 0xffffffffu, active && !fast && !one );
+            while( xmask ) {
+                const int room = XQ - qn;
+                const int rank = __popc( xmask & ( ( 1u << lane ) - 1u ) );
+                const bool mineq = ( ( xmask >> lane ) & 1u ) && rank < room;
+                if( mineq ) {
+                    const int e = ( qh + qn + rank ) % XQ;
+#pragma unroll
+                    for( int d=0; d<3; d++ ) { xq[( 0+d )*XQ+e] = xdelta[d]; xq[( 3+d )*XQ+e] = xnpos[d]; xq[( 6+d )*XQ+e] = cr[d]; }
+                    xqm[e] = cellt | ( shifts << 16 );
+                }
+                const unsigned done = __ballot_sync( 0xffffffffu, mineq );
+                xmask &= ~done;
+                qn += __popc( done );
+                __syncwarp();
+                while( qn >= 4 || ( xmask && qn > 0 ) ) {
+                    cross_pass<2>( sJ + zj, xq, xqm, xscr, qh, qn, lane & 7, lane >> 3, a.jscale );
+                    const int took = qn < 4 ? qn : 4;
+                    qh = ( qh + took ) % XQ;
+                    qn -= took;
+                }
+            }
+        }
+        // ---------------- the cell is finished: its sums go to the J box
+        if( gl < 3 && cnt > 0 ) {
+            jbox_t *jb = sJ + zj + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2] + jo_;
+#pragma unroll
+            for( int f=0; f<2; f++ )
+#pragma unroll
+                for( int j=0; j<NW; j++ )
+#pragma unroll
+                    for( int k=0; k<NW; k++ ) jadd( jb + f*sf_ + j*sa_ + k*sb_, acc[f][j][k], a.jscale );
+        }
+    }
+    while( qn > 0 ) {
+        cross_pass<2>( sJ + zj, xq, xqm, xscr, qh, qn, lane & 7, lane >> 3, a.jscale );
+        const int took = qn < 4 ? qn : 4;
+        qh = ( qh + took ) % XQ;
+        qn -= took;
+    }
+    __syncthreads();
+
+    // ---------------- flush the J box (as k_dynamics_cg)
+    for( int t = tid; t < 3*T::JBOX; t += DYN_THREADS ) {
+        const long long iv = ( long long )sJ[t];
+        reinterpret_cast<double *>( sJ )[t] = ( double )iv*a.jinv;
+    }
+    tma_store_fence();
+    __syncthreads();
+    if( tid == 0 ) {
+#pragma unroll
+        for( int c=0; c<3; c++ )
+            tma_reduce_add_3d( &tm.j[c], sJ + c*T::JBOX, c0[2] + g.o[2] - T::H - 1 - zj, c0[1] + g.o[1] - T::H - 1, c0[0] + g.o[0] - T::H - 1 );
+        tma_commit_and_wait_read();
+    }
+}
+
 // Tensor maps of the six gathered fields for a given box: element (k,j,i) innermost first, row pitch AZ*8 B
 // (a multiple of 128 B by construction of the padded layout), out-of-bounds elements read as zero.
 static int field_maps( sb200_patch *p, int fx, int fy, int fz, int jx, int jy, int jz, FieldMaps &out )
@@ -1042,6 +1426,30 @@ static int launch_cg( sb200_patch *p, const DynArgs &a, int ntiles )
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
+}
+
+template<int PUSHER, bool SCRATCH>
+static int launch_o2( sb200_patch *p, const DynArgs &a, int ntiles )
+{
+    using T = o2::T;
+    FieldMaps tm;
+    if( field_maps( p, T::FX, T::FY, T::FZ, T::JX, T::JY, T::JZ, tm ) ) return 1;
+    auto kern = k_dynamics_o2<PUSHER, SCRATCH>;
+    SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )o2::BYTES ) );
+    SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
+    kern<<<ntiles, DYN_THREADS, o2::BYTES, p->stream>>>( p->gd, a, tm );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    return 0;
+}
+
+static int launch_o2_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int pusher, bool scratch )
+{
+    switch( pusher ) {
+        case SB200_PUSHER_BORIS: return scratch ? launch_o2<SB200_PUSHER_BORIS, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_BORIS, false>( p, a, ntiles );
+        case SB200_PUSHER_VAY: return scratch ? launch_o2<SB200_PUSHER_VAY, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_VAY, false>( p, a, ntiles );
+        default: return scratch ? launch_o2<SB200_PUSHER_HIGUERACARY, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_HIGUERACARY, false>( p, a, ntiles );
+    }
 }
 
 template<int ORDER>
@@ -1100,6 +1508,7 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     a.iflags = p->iflags;
     a.sc_E = p->sc_E; a.sc_B = p->sc_B; a.sc_invgf = p->sc_invgf; a.sc_delta = p->sc_delta; a.sc_iold = p->sc_iold;
     a.n = s.n;
+    { static const bool nr = getenv( "SB200_DYN_NORANK" ) != nullptr; a.norank = nr ? 1 : 0; }
     a.one_over_mass = 1.0/s.mass;                      // Pusher.cpp:20
     {
         // |J box entry| <= (particles whose window can reach a node) * max|q w|/V * max(d/dt): a node is reached
@@ -1118,7 +1527,10 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
             a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
             a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
             a.tiles[2] = ( g.ncell[2] + T::TZ - 1 )/T::TZ;
-            return launch_cg_pusher<2>( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
+            // SB200_DYN_CG=1: the shuffle-reduction kernel instead of the two-phase one (A/B checks only)
+            static const bool old_cg = getenv( "SB200_DYN_CG" ) != nullptr;
+            if( old_cg ) return launch_cg_pusher<2>( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
+            return launch_o2_pusher( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
         }
         using T = CG<4>::T;
         a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
