@@ -109,7 +109,6 @@ struct DynArgs {
     double  one_over_mass;
     double  jscale, jinv;     // fixed-point scale of the J box and its inverse
     int     tiles[3];
-    int     norank;           // A/B switch: hand cells out in z-row order instead of by rank of their particle count
 };
 
 // a particle tagged for exchange: count it and remember its index (sb200_leaving_pack orders the list)
@@ -1038,7 +1037,6 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
     __shared__ __align__( 8 ) unsigned long long tma_bar;
     __shared__ int cell_first[NCELL];
     __shared__ int cell_cnt[NCELL];
-    __shared__ unsigned char cell_order[NCELL];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -1077,22 +1075,22 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
     const int any = __syncthreads_or( mine );
     tma_wait( &tma_bar, 0 );          // the boxes must have landed before this CTA's shared memory is used or released
     if( !any ) return;
-    // The 8 lane groups of a warp walk their cells in lockstep, so a round costs the warp as much as its
-    // fullest cell needs.  Cells are therefore handed out by RANK of their particle count (fullest first):
-    // the 8 cells a warp works on together hold almost the same number of particles.
-    if( tid < NCELL ) {
-        int rank = tid;
-        if( !a.norank ) {
-            rank = 0;
-            for( int u=0; u<NCELL; u++ ) {
-                const int c = cell_cnt[u];
-                rank += ( c > mine || ( c == mine && u < tid ) ) ? 1 : 0;
-            }
+    // Pull the tile's particle columns into L2 while the CTA finishes its set-up: one thread per cell asks for
+    // the lines its cell's particles sit in (through the pending sort order their source slots are the old
+    // slots of the same particles, i.e. one short stretch per cell plus the few that moved in).
+    if( tid < NCELL && mine > 0 ) {
+        size_t lo = ( size_t )cell_first[tid], hi = lo + ( size_t )mine - 1;
+        if( a.perm ) {
+            const size_t p0 = ( size_t )a.perm[lo], p1 = ( size_t )a.perm[hi];
+            asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.perm + lo + 32 ) );
+            lo = p0 < p1 ? p0 : p1; hi = p0 < p1 ? p1 : p0;
+            if( hi - lo > 64 ) hi = lo + 64;                 // movers from far away: not worth chasing
         }
-        cell_order[rank] = ( unsigned char )tid;
+#pragma unroll
+        for( int c=0; c<7; c++ )
+            for( size_t i = lo & ~( size_t )15; i <= hi; i += 16 ) asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.in[c] + i ) );
+        asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.qin + lo ) );
     }
-    __syncthreads();
-
     const int gl = lane & ( G4-1 );                       // lane in the group = particle slot (phase 1) = component (phase 2)
     const int gw = lane >> 2;                             // group in the warp
     double *wstage = smem + 6*T::FBOX + 3*T::JBOX + WSTAGE*warp;
@@ -1114,7 +1112,7 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
 
 #pragma unroll 1
     for( int m = 0; m < CELLS_PER_GROUP; m++ ) {
-        const int cellt = cell_order[m*NGRP + ( tid >> 2 )];
+        const int cellt = m*NGRP + ( tid >> 2 );
         const int cl[3] = { cellt / ( T::TZ*T::TY ), ( cellt / T::TZ ) % T::TY, cellt % T::TZ };
         const int cnt = cell_cnt[cellt];
         const size_t first = ( size_t )cell_first[cellt];
@@ -1508,7 +1506,6 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     a.iflags = p->iflags;
     a.sc_E = p->sc_E; a.sc_B = p->sc_B; a.sc_invgf = p->sc_invgf; a.sc_delta = p->sc_delta; a.sc_iold = p->sc_iold;
     a.n = s.n;
-    { static const bool nr = getenv( "SB200_DYN_NORANK" ) != nullptr; a.norank = nr ? 1 : 0; }
     a.one_over_mass = 1.0/s.mass;                      // Pusher.cpp:20
     {
         // |J box entry| <= (particles whose window can reach a node) * max|q w|/V * max(d/dt): a node is reached
