@@ -138,20 +138,27 @@ __global__ void __launch_bounds__( 256 ) k_scatter_idx( const int *__restrict__ 
 
 // Restore ascending index order inside every cell's run of perm (the atomic cursor of k_scatter_idx serves
 // slots in arbitrary order).  A warp takes 32 consecutive cells = one contiguous stretch of perm, reads it
-// coalesced and looks for inversions between neighbours of the same cell; particles of a cell mostly arrive
-// in order, so only the rare cell with an inversion is then insertion-sorted by its lane.
+// coalesced into shared memory and looks for inversions between neighbours of the same cell; particles of a
+// cell mostly arrive in order.  Each lane then insertion-sorts its own cell in shared memory (the runs are
+// nearly ordered, so this is a handful of moves) and the warp writes the stretch back coalesced.
 __global__ void __launch_bounds__( 256 ) k_cell_sort( const int *__restrict__ first, int *__restrict__ perm, int ncells )
 {
+    constexpr int SW = 1024;                       // entries of a warp's stretch kept in shared memory
+    __shared__ int stretch[8][SW + SW/16 + 1];     // skewed: entry p sits at p + p/16, so lanes working on cells of ~16 entries hit different banks
     const int lane = threadIdx.x & 31;
+    int *sm = stretch[threadIdx.x >> 5];
     const int nwarps = ( gridDim.x*blockDim.x ) >> 5;
     for( int w = ( blockIdx.x*blockDim.x + threadIdx.x ) >> 5; w*32 < ncells; w += nwarps ) {
         const int c = w*32 + lane;
         const int cb = first[min( c, ncells )], ce = first[min( c+1, ncells )];
         const int base = __shfl_sync( 0xffffffffu, cb, 0 ), end = __shfl_sync( 0xffffffffu, ce, 31 );
+        const bool staged = end - base <= SW;
         unsigned bad = 0;
+        __syncwarp();
         for( int j0 = base; j0 < end; j0 += 32 ) {
             const int j = j0 + lane;
             const int v = j < end ? perm[j] : 0x7fffffff;
+            if( staged && j < end ) { const int q = j - base; sm[q + ( q >> 4 )] = v; }
             int vn = __shfl_down_sync( 0xffffffffu, v, 1 );
             if( lane == 31 ) vn = j+1 < end ? perm[j+1] : 0x7fffffff;
             // cell of position j among the warp's 32 cells: the number of run ends <= j
@@ -165,19 +172,39 @@ __global__ void __launch_bounds__( 256 ) k_cell_sort( const int *__restrict__ fi
             const bool inv = j+1 < end && k < 32 && j+1 < kend && v > vn;
             bad |= __reduce_or_sync( 0xffffffffu, inv ? ( 1u << k ) : 0u );
         }
+        if( bad == 0 ) continue;
+        __syncwarp();
         if( ( bad >> lane ) & 1u ) {
-            for( int i = cb+1; i < ce; i++ ) {
-                const int v = perm[i];
-                int j = i-1;
-                while( j >= cb ) {
-                    const int u = perm[j];
-                    if( u <= v ) break;
-                    perm[j+1] = u;
-                    j--;
+            if( staged ) {
+                const int b0 = cb - base, e0 = ce - base;
+                for( int i = b0+1; i < e0; i++ ) {
+                    const int v = sm[i + ( i >> 4 )];
+                    int j = i-1;
+                    while( j >= b0 ) {
+                        const int u = sm[j + ( j >> 4 )];
+                        if( u <= v ) break;
+                        sm[j+1 + ( ( j+1 ) >> 4 )] = u;
+                        j--;
+                    }
+                    sm[j+1 + ( ( j+1 ) >> 4 )] = v;
                 }
-                perm[j+1] = v;
+            } else {
+                for( int i = cb+1; i < ce; i++ ) {
+                    const int v = perm[i];
+                    int j = i-1;
+                    while( j >= cb ) {
+                        const int u = perm[j];
+                        if( u <= v ) break;
+                        perm[j+1] = u;
+                        j--;
+                    }
+                    perm[j+1] = v;
+                }
             }
         }
+        __syncwarp();
+        if( staged )
+            for( int q = lane; q < end - base; q += 32 ) perm[base + q] = sm[q + ( q >> 4 )];
     }
 }
 
