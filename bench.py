@@ -24,8 +24,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: keep NCCL's version / debug banner off it
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries print banners on fd 1 (NCCL's "NCCL version ..." line comes
+# from C code), so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 METRIC = "particle pushes/s (gather+push+deposit, whole PIC step incl. Yee + sort + exchange)"
 UNIT = "pushes/s"
@@ -168,7 +175,7 @@ def run_reference_arm(args):
         return
     r = cpu_reference_run(2, 0, args.steps, args.warmup)
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsmilei_ref.so not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libsmilei_ref.so not built"})
         return
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["t_step"] * 1e3, "higher_is_better": True,
@@ -178,7 +185,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -332,7 +339,7 @@ def main():
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                     "sample": r["sample"]}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     sim.close()
     if world > 1:
         dist.barrier()

@@ -2,7 +2,7 @@
 //
 // Device data layout:
 //  * every field component lives in its own HBM array of identical padded shape
-//    (AX, AY, AZ) = (d[0], d[1], roundup(d[2],16)), element (i,j,k) at (i*AY+j)*AZ+k, where
+//    (AX, AY, AZ) = (d[0], d[1], roundup(d[2],8)), element (i,j,k) at (i*AY+j)*AZ+k, where
 //    d = n+2*oversize+2 is the reference's dual dimension.  Only the sub-box
 //    [0,dims_c) of component c is meaningful; the padding is kept at zero.  A common
 //    shape means one index expression serves all 13 arrays and rows start 128-B aligned.

@@ -22,12 +22,12 @@ __global__ void __launch_bounds__( 256 ) k_ampere( GridDev g,
         const double *__restrict__ Jx, const double *__restrict__ Jy, const double *__restrict__ Jz )
 {
     const int halfz = g.az >> 1;
-    const long long total = ( long long )g.ax*g.ay*halfz;
+    const unsigned total = ( unsigned )( g.ax*g.ay )*( unsigned )halfz;      // < 2^32 (checked by launch_maxwell): 32-bit divisions, the 64-bit ones are emulated
     const double mdt = -g.dt;
     const double ddx = g.dt_ov_d[0], ddy = g.dt_ov_d[1], ddz = g.dt_ov_d[2];
-    for( long long t = blockIdx.x*( long long )blockDim.x + threadIdx.x; t < total; t += ( long long )gridDim.x*blockDim.x ) {
-        const int kh = ( int )( t % halfz );
-        const long long r = t / halfz;
+    for( unsigned t = blockIdx.x*blockDim.x + threadIdx.x; t < total; t += gridDim.x*blockDim.x ) {
+        const int kh = ( int )( t % ( unsigned )halfz );
+        const unsigned r = t / ( unsigned )halfz;
         const int j = ( int )( r % g.ay );
         const int i = ( int )( r / g.ay );
         const int k = kh*2;
@@ -84,11 +84,11 @@ __global__ void __launch_bounds__( 256 ) k_faraday_center( GridDev g,
         double *__restrict__ Bxm, double *__restrict__ Bym, double *__restrict__ Bzm )
 {
     const int halfz = g.az >> 1;
-    const long long total = ( long long )g.ax*g.ay*halfz;
+    const unsigned total = ( unsigned )( g.ax*g.ay )*( unsigned )halfz;      // < 2^32 (checked by launch_maxwell): 32-bit divisions, the 64-bit ones are emulated
     const double ddx = g.dt_ov_d[0], ddy = g.dt_ov_d[1], ddz = g.dt_ov_d[2];
-    for( long long t = blockIdx.x*( long long )blockDim.x + threadIdx.x; t < total; t += ( long long )gridDim.x*blockDim.x ) {
-        const int kh = ( int )( t % halfz );
-        const long long r = t / halfz;
+    for( unsigned t = blockIdx.x*blockDim.x + threadIdx.x; t < total; t += gridDim.x*blockDim.x ) {
+        const int kh = ( int )( t % ( unsigned )halfz );
+        const unsigned r = t / ( unsigned )halfz;
         const int j = ( int )( r % g.ay );
         const int i = ( int )( r / g.ay );
         const int k = kh*2;
@@ -173,22 +173,24 @@ struct ShellGeom {
     long long count[2];
 };
 
-__global__ void __launch_bounds__( 256 ) k_center_shell( ShellGeom sg0, ShellGeom sg1, ShellGeom sg2, long long sx, long long sy,
-        const double *__restrict__ Bx, const double *__restrict__ By, const double *__restrict__ Bz,
-        double *__restrict__ Bxm, double *__restrict__ Bym, double *__restrict__ Bzm )
+struct ShellArgs { ShellGeom sg[3]; const double *B[3]; double *M[3]; };
+
+__global__ void __launch_bounds__( 256 ) k_center_shell( const __grid_constant__ ShellArgs sa, long long sx, long long sy )
 {
-    const int c = blockIdx.y;
-    const ShellGeom &sg = c == 0 ? sg0 : c == 1 ? sg1 : sg2;
-    const double *B = c == 0 ? Bx : c == 1 ? By : Bz;
-    double *M = c == 0 ? Bxm : c == 1 ? Bym : Bzm;
-    const long long total = sg.count[0] + sg.count[1];
-    for( long long t = blockIdx.x*( long long )blockDim.x + threadIdx.x; t < total; t += ( long long )gridDim.x*blockDim.x ) {
-        const int r = t < sg.count[0] ? 0 : 1;
-        long long u = r == 0 ? t : t - sg.count[0];
+    // everything is read from the constant bank with the block-uniform component index (no per-thread copy of the structs)
+    const ShellGeom &sg = sa.sg[blockIdx.y];
+    const double *__restrict__ B = sa.B[blockIdx.y];
+    double *__restrict__ M = sa.M[blockIdx.y];
+    // 32-bit index arithmetic: the shell holds far fewer than 2^31 points and 64-bit divisions are emulated
+    const unsigned c0 = ( unsigned )sg.count[0], total = c0 + ( unsigned )sg.count[1];
+    for( unsigned t = blockIdx.x*blockDim.x + threadIdx.x; t < total; t += gridDim.x*blockDim.x ) {
+        const int r = t < c0 ? 0 : 1;
+        unsigned u = r == 0 ? t : t - c0;
         int loc[3];
-        loc[2] = ( int )( u % sg.ext[r][2] ); u /= sg.ext[r][2];
-        loc[1] = ( int )( u % sg.ext[r][1] );
-        loc[0] = ( int )( u / sg.ext[r][1] );
+        const unsigned e2 = ( unsigned )sg.ext[r][2], e1 = ( unsigned )sg.ext[r][1];
+        loc[2] = ( int )( u % e2 ); u /= e2;
+        loc[1] = ( int )( u % e1 );
+        loc[0] = ( int )( u / e1 );
         int gi[3];
 #pragma unroll
         for( int d=0; d<3; d++ )
@@ -211,6 +213,7 @@ template<class K> static int resident_grid( K kern )
 int launch_maxwell( sb200_patch *p )
 {
     static const int blocks_a = resident_grid( k_ampere ), blocks_f = resident_grid( k_faraday_center );
+    SB200_CHECK( ( double )p->gd.ax*p->gd.ay*( p->gd.az/2 ) < 4.0e9, "sb200_maxwell: patch too large for 32-bit point indices" );
     const int blocks = blocks_a;
     k_ampere<<<blocks, 256, 0, p->stream>>>( p->gd, p->f[SB200_EX], p->f[SB200_EY], p->f[SB200_EZ],
             p->f[SB200_BX], p->f[SB200_BY], p->f[SB200_BZ], p->f[SB200_JX], p->f[SB200_JY], p->f[SB200_JZ] );
@@ -226,7 +229,8 @@ int launch_maxwell( sb200_patch *p )
 int launch_center_shell( sb200_patch *p )
 {
     const GridDev &g = p->gd;
-    ShellGeom sg[3];
+    ShellArgs sa;
+    ShellGeom *sg = sa.sg;
     long long most = 0;
     for( int c=0; c<3; c++ ) {
         // component c (Bx,By,Bz) is primal along c and dual along the two others, da < db
@@ -247,8 +251,8 @@ int launch_center_shell( sb200_patch *p )
     if( nb > 148*8 ) nb = 148*8;
     if( nb < 1 ) nb = 1;
     dim3 grid( ( unsigned )nb, 3 );
-    k_center_shell<<<grid, 256, 0, p->stream>>>( sg[0], sg[1], sg[2], g.sx, g.sy, p->f[SB200_BX], p->f[SB200_BY], p->f[SB200_BZ],
-            p->f[SB200_BXM], p->f[SB200_BYM], p->f[SB200_BZM] );
+    for( int c=0; c<3; c++ ) { sa.B[c] = p->f[SB200_BX+c]; sa.M[c] = p->f[SB200_BXM+c]; }
+    k_center_shell<<<grid, 256, 0, p->stream>>>( sa, g.sx, g.sy );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;

@@ -39,7 +39,7 @@ static void fill_grid( const sb200_grid &g, GridDev &d )
     d.inv_cell_volume = 1./d.cell_volume;                 // Projector.cpp:7
     d.ax = d.d[0];
     d.ay = d.d[1];
-    d.az = ( d.d[2] + 15 )/16*16;
+    d.az = ( d.d[2] + 7 )/8*8;          // rows start on a 64-B boundary (two 32-B sectors); 16-B vector accesses and the TMA strides need az even
     d.sy = d.az;
     d.sx = ( long long )d.ay*d.az;
 }
