@@ -75,6 +75,17 @@ int  sb200_patch_synchronize( sb200_patch *p );
 /* Species::mass_, Species.pusher, and the SoA capacity to reserve
  * (src/Species/Species.cpp:260-307 initOperators, src/Particles/Particles.h:526-566). */
 int  sb200_species_config( sb200_patch *p, int ispec, double mass, int pusher, size_t capacity );
+/* Particle boundary conditions of the species at the six GLOBAL box sides, order xmin xmax ymin ymax zmin zmax
+ * (Species::boundary_conditions_, src/ParticleBC/PartBoundCond.cpp:99-245): SB200_PBC_PERIODIC (exchange with
+ * the neighbour across the box) or SB200_PBC_REMOVE (remove_particle_inf/sup,
+ * src/ParticleBC/BoundaryConditionType.cpp:204-294).  Sides of the patch that are not global box sides always
+ * tag for exchange (internal_inf/sup).  Default: all periodic. */
+#define SB200_PBC_PERIODIC 0
+#define SB200_PBC_REMOVE   1
+int  sb200_species_set_bc( sb200_patch *p, int ispec, const int bc[6] );
+/* mass * sum of w*(gamma-1) over the particles removed at the boundaries since the last reset
+ * (Species::nrj_bc_lost, src/Species/Species.cpp:757-762). */
+int  sb200_species_lost_energy( sb200_patch *p, int ispec, double *lost, int reset );
 /* HOST -> device import of the SoA columns (Particles::Position/Momentum/Weight/Charge). */
 int  sb200_species_set( sb200_patch *p, int ispec,
                         const double *x, const double *y, const double *z,
@@ -126,6 +137,17 @@ int  sb200_scratch_get( sb200_patch *p, double *Epart, double *Bpart, double *in
  * exchange, so that after sb200_center_B all of B_m equals the reference's
  * ElectroMagn3D::centerMagneticFields (src/ElectroMagn/ElectroMagn3D.cpp:1191-1293). */
 int  sb200_maxwell( sb200_patch *p );
+/* Silver-Mueller absorbing / injecting boundary on one GLOBAL box side (i_boundary = 0..5: xmin xmax ymin ymax
+ * zmin zmax): ElectroMagnBC3D_SM::apply (src/ElectroMagnBC/ElectroMagnBC3D_SM.cpp:141-376) with zero external
+ * fields.  `k` = EM_BCs_k of that side (incidence vector).  db1 / db2 are the summed laser amplitudes
+ * Laser::getAmplitude0/1 on the face (HOST arrays of n_p[axis1]*n_d[axis2] and n_d[axis1]*n_p[axis2] doubles,
+ * row-major as the reference's b1/b2; NULL = no laser).  is_boundary = { axis1 min, axis1 max, axis2 min,
+ * axis2 max }: 1 where the patch has no neighbour on that side of the face's own axes (Patch::isBoundary; the
+ * sweeps skip the first / last index there), axis1 = (axis0==0 ? 1 : 0), axis2 = (axis0==2 ? 1 : 2).
+ * A no-op on a patch that does not touch the side.  Call after the B halo exchange and before sb200_center_B
+ * (Smilei.cpp:649 finalizeSyncAndBCFields). */
+int  sb200_apply_SM( sb200_patch *p, int i_boundary, const double k[3], const int is_boundary[4],
+                     const double *db1, const double *db2 );
 int  sb200_center_B( sb200_patch *p );
 
 /* SpeciesV::computeParticleCellKeys histogram + SpeciesV::sortParticles

@@ -52,6 +52,10 @@ Tools/Tools.cpp
 Particles/Particles.cpp
 Species/SpeciesV.cpp
 ParticleBC/BoundaryConditionType.cpp
+ElectroMagnBC/ElectroMagnBC.cpp
+ElectroMagnBC/ElectroMagnBC3D.cpp
+ElectroMagnBC/ElectroMagnBC3D_SM.cpp
+Field/Field2D.cpp
 "
 pids=()
 for s in $SRCS; do

@@ -10,7 +10,8 @@
  *   Projector3D2Order / Projector3D4Order ::currentsAndDensityWrapper
  *   MA_Solver3D_norm / MF_Solver3D_Yee ::operator()
  *   ElectroMagn3D::saveMagneticFields / centerMagneticFields
- *   SpeciesV::computeParticleCellKeys, internal_inf / internal_sup, Field3D::norm2
+ *   SpeciesV::computeParticleCellKeys, internal_inf / internal_sup, remove_particle_inf / _sup, Field3D::norm2
+ *   ElectroMagnBC3D_SM (constructor + apply, with array-backed LaserProfile objects)
  * exactly as Species::dynamics / VectorPatch::solveMaxwell do.
  *
  * The big driver classes (Params, Patch, Species, SmileiMPI, ElectroMagn3D) cannot be
@@ -76,6 +77,8 @@
 #include "MA_Solver3D_norm.h"
 #include "MF_Solver3D_Yee.h"
 #include "BoundaryConditionType.h"
+#include "ElectroMagnBC3D_SM.h"
+#include "Laser.h"
 #undef private
 #undef protected
 
@@ -573,6 +576,89 @@ double ref_time_maxwell( const orc_grid *g, int npatches, int nsteps, int nthrea
     double t1 = omp_get_wtime();
     for( int ip=0; ip<npatches; ip++ ) free_ctx( ctx[ip] );
     return t1-t0;
+}
+
+/* PartBoundCond::apply (PartBoundCond.h:38-76) with remove_particle_inf/sup on the sides flagged in bc_remove and
+ * internal_inf/sup elsewhere; limits = patch bounds (PartBoundCond.cpp:44-69). */
+void ref_bc_apply( const orc_grid *g, const int *bc_remove, const double *x, const double *y, const double *z,
+                   const double *px, const double *py, const double *pz, const double *w, short *q,
+                   int *keys, int imin, int imax, double *energy_lost )
+{
+    Ctx *c = make_ctx( g, 1., 1 );
+    set_particles( c, x, y, z, px, py, pz, w, q, imax );
+    Particles &p = *c->species->particles;
+    std::vector<double> invgf;
+    double energy_tot = 0.;
+    int *ck = p.getPtrCellKeys();
+    for( int i=imin; i<imax; i++ ) ck[i] = 0;
+    for( int d=0; d<3; d++ ) {
+        double e = 0.;
+        if( bc_remove[2*d] ) remove_particle_inf( c->species, imin, imax, d, c->patch->min_local_[d], g->dt, invgf, NULL, e );
+        else internal_inf( c->species, imin, imax, d, c->patch->min_local_[d], g->dt, invgf, NULL, e );
+        energy_tot += e;
+        if( bc_remove[2*d+1] ) remove_particle_sup( c->species, imin, imax, d, c->patch->max_local_[d], g->dt, invgf, NULL, e );
+        else internal_sup( c->species, imin, imax, d, c->patch->max_local_[d], g->dt, invgf, NULL, e );
+        energy_tot += e;
+    }
+    std::memcpy( keys, ck, sizeof( int )*imax );
+    std::memcpy( q, p.Charge.data(), sizeof( short )*imax );
+    *energy_lost = energy_tot;
+    free_ctx( c );
+}
+
+} // extern "C"
+
+namespace {
+/* a LaserProfile whose amplitude on the face is read from an array (what Laser::getAmplitude0/1 returns is
+ * whatever the profile object computes; the reference sums it into b1/b2, ElectroMagnBC3D_SM.cpp:189-199,265-275) */
+struct ArrayProfile : public LaserProfile {
+    const double *a; int ld;
+    ArrayProfile( const double *a_, int ld_ ) : a( a_ ), ld( ld_ ) {}
+    double getAmplitude( std::vector<double>, double, int j, int k ) override { return a ? a[j*ld + k] : 0.; }
+};
+}
+
+extern "C" {
+
+void ref_apply_SM( const orc_grid *g, int i_boundary, const double *K, const int *is_boundary,
+                   const double *Ex, const double *Ey, const double *Ez, double *Bx, double *By, double *Bz,
+                   const double *db1, const double *db2 )
+{
+    Ctx *c = make_ctx( g, 1., 1 );
+    Params &P = *c->params;
+    Patch &pt = *c->patch;
+    ElectroMagn3D &E = *c->em;
+    const int axis0 = i_boundary/2, axis1 = axis0 == 0 ? 1 : 0, axis2 = axis0 == 2 ? 1 : 2;
+    new( &P.EM_BCs_k ) std::vector<std::vector<double>>( 6, std::vector<double>( K, K+3 ) );
+    new( &pt.size_ ) std::vector<unsigned int>( g->n, g->n+3 );
+    new( &pt.oversize ) std::vector<unsigned int>( g->o, g->o+3 );
+    new( &E.oversize ) std::vector<unsigned int>( g->o, g->o+3 );
+    /* Patch::isBoundary reads neighbor_[axis][side] == MPI_PROC_NULL */
+    new( &pt.neighbor_ ) std::vector<std::vector<int>>( 3, std::vector<int>( 2, 0 ) );
+    const bool at_side = ( i_boundary % 2 ) == 0 ? g->pcoord[axis0] == 0 : g->pcoord[axis0] == g->npatch[axis0]-1;
+    pt.neighbor_[axis0][i_boundary % 2] = at_side ? MPI_PROC_NULL : 0;
+    pt.neighbor_[axis1][0] = is_boundary[0] ? MPI_PROC_NULL : 0;
+    pt.neighbor_[axis1][1] = is_boundary[1] ? MPI_PROC_NULL : 0;
+    pt.neighbor_[axis2][0] = is_boundary[2] ? MPI_PROC_NULL : 0;
+    pt.neighbor_[axis2][1] = is_boundary[3] ? MPI_PROC_NULL : 0;
+    load( E.Ex_, Ex ); load( E.Ey_, Ey ); load( E.Ez_, Ez );
+    load( E.Bx_, Bx ); load( E.By_, By ); load( E.Bz_, Bz );
+    {
+        ElectroMagnBC3D_SM bc( P, &pt, ( unsigned int )i_boundary );
+        Laser *laser = NULL;
+        if( db1 || db2 ) {
+            const int n2d = g->n[axis2] + 2*g->o[axis2] + 2, n2p = n2d - 1;
+            laser = blank<Laser>();
+            new( &laser->profiles ) std::vector<LaserProfile *>();
+            laser->profiles.push_back( new ArrayProfile( db1, n2d ) );
+            laser->profiles.push_back( new ArrayProfile( db2, n2p ) );
+            bc.vecLaser.push_back( laser );
+        }
+        bc.apply( &E, 0., &pt );
+        bc.vecLaser.clear();        /* the Laser stand-in is not the destructor's to delete */
+    }
+    store( E.Bx_, Bx ); store( E.By_, By ); store( E.Bz_, Bz );
+    free_ctx( c );
 }
 
 } // extern "C"

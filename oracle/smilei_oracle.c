@@ -1070,3 +1070,162 @@ void orc_exchange_pair( const orc_grid *g, int dim, int dualx, int dualy, int du
                 L[idx+shift+gshift] = R[idx+gshift];
             }
 }
+
+/* ------------------------------------------------------------------------- */
+/* PartBoundCond::apply with `remove` conditions at global box sides
+ * (ParticleBC/PartBoundCond.h:38-76; remove_particle_inf/sup, ParticleBC/BoundaryConditionType.cpp:204-294;
+ * internal_inf/sup, :15-57).  bc_remove[2*d+s] != 0: side s of dimension d is a global box side with the
+ * `remove` condition (the limits are then max/min of the global and the patch bounds, PartBoundCond.cpp:44-69,
+ * i.e. the patch bounds).  energy_lost receives the reference's energy_tot (sum of w*(gamma-1)).            */
+void orc_bc_apply( const orc_grid *g, const int *bc_remove, const double *x, const double *y, const double *z,
+                   const double *px, const double *py, const double *pz, const double *w, short *q,
+                   int *cell_keys, int imin, int imax, double *energy_lost )
+{
+    double mn[3], mx[3];
+    int begin[3];
+    orc_patch_bounds( g, mn, mx, begin );
+    const double *position[3] = { x, y, z };
+    double energy_tot = 0.;
+    for( int ipart=imin; ipart<imax; ipart++ ) cell_keys[ipart] = 0;
+    for( int direction=0; direction<3; direction++ ) {
+        for( int side=0; side<2; side++ ) {
+            double change_in_energy = 0.0;
+            const double limit = side==0 ? mn[direction] : mx[direction];
+            for( int ipart=imin ; ipart<imax ; ipart++ ) {
+                const int beyond = side==0 ? ( position[direction][ipart] < limit ) : ( position[direction][ipart] >= limit );
+                if( bc_remove[2*direction+side] ) {
+                    if( beyond ) {
+                        const double LorentzFactor = sqrt( 1.0 + px[ipart]*px[ipart] + py[ipart]*py[ipart] + pz[ipart]*pz[ipart] );
+                        change_in_energy += w[ipart] * ( LorentzFactor - 1.0 );
+                        q[ipart] = 0;
+                        cell_keys[ipart] = -1;
+                    }
+                } else if( cell_keys[ipart] >= 0 && beyond ) {
+                    cell_keys[ipart] = ( side==0 ? -2 : -3 ) - 2 * direction;
+                }
+            }
+            energy_tot += change_in_energy;
+        }
+    }
+    *energy_lost = energy_tot;
+}
+
+/* ------------------------------------------------------------------------- */
+/* ElectroMagnBC3D_SM (ElectroMagnBC/ElectroMagnBC3D_SM.cpp): constructor coefficients (:61-75) and apply()
+ * (:141-376) with zero external fields (B_val = 0).  Fields in the reference's compact layout; db1 / db2 are
+ * the laser amplitude arrays b1 (n1p x n2d) and b2 (n1d x n2p) the reference fills from Laser::getAmplitude0/1,
+ * or NULL.  is_boundary = { isBoundary1min, isBoundary1max, isBoundary2min, isBoundary2max }.              */
+void orc_apply_SM( const orc_grid *g, int i_boundary, const double *K, const int *is_boundary,
+                   const double *Ex, const double *Ey, const double *Ez, double *Bx, double *By, double *Bz,
+                   const double *db1, const double *db2 )
+{
+    int n_p[3], n_d[3];
+    orc_dims( g, n_p, n_d );
+    const int axis0_ = i_boundary / 2;
+    const int axis1_ = axis0_ == 0 ? 1 : 0;
+    const int axis2_ = axis0_ == 2 ? 1 : 2;
+    const double sign_ = ( double )( i_boundary % 2 ) *2 - 1.;
+    /* acts only on a patch at that global side (patch->isBoundary( i_boundary_ ), :143) */
+    if( sign_ < 0 ? g->pcoord[axis0_] != 0 : g->pcoord[axis0_] != g->npatch[axis0_]-1 ) return;
+    int iB_[3] = { 0, 0, 0 };
+    if( sign_ > 0 ) {
+        iB_[axis0_] = n_p[axis0_] - 1;
+        iB_[axis1_] = n_d[axis0_] - 1;
+        iB_[axis2_] = n_d[axis0_] - 1;
+    }
+    double dt_ov_d[3];
+    for( int i=0; i<3; i++ ) dt_ov_d[i] = g->dt / g->cell[i];
+    const double Knorm = sqrt( K[0]*K[0] + K[1]*K[1] + K[2]*K[2] ) ;
+    const double omega = 1.;
+    const double k0 = omega*K[axis0_] / Knorm;
+    const double k1 = omega*K[axis1_] / Knorm;
+    const double k2 = omega*K[axis2_] / Knorm;
+    const double factor = 1.0 / ( k0 - sign_ * dt_ov_d[axis0_] );
+    const double Alpha_   = 2.0 * factor;
+    const double Beta_    = - ( k0 + sign_ * dt_ov_d[axis0_] ) * factor;
+    const double Gamma_   = 4.0 * k0 * factor;
+    const double Delta_   = - ( k1 + dt_ov_d[axis1_] ) * factor;
+    const double Epsilon_ = - ( k1 - dt_ov_d[axis1_] ) * factor;
+    const double Zeta_    = - ( k2 + dt_ov_d[axis2_] ) * factor;
+    const double Eta_     = - ( k2 - dt_ov_d[axis2_] ) * factor;
+
+    const double *E[3] = { Ex, Ey, Ez };
+    double *B[3] = { Bx, By, Bz };
+    const double *E1 = E[axis1_], *E2 = E[axis2_], *B0 = B[axis0_];
+    double *B1 = B[axis1_], *B2 = B[axis2_];
+    const unsigned int nz_p = n_p[2], nz_d = n_d[2];
+    const unsigned int nyz_pp = n_p[1]*n_p[2], nyz_pd = n_p[1]*n_d[2], nyz_dp = n_d[1]*n_p[2], nyz_dd = n_d[1]*n_d[2];
+    const unsigned int n1p = n_p[axis1_], n1d = n_d[axis1_], n2p = n_p[axis2_], n2d = n_d[axis2_];
+    const unsigned int p0 = iB_[axis0_];
+    const unsigned int p1 = iB_[axis1_] - sign_;
+    const unsigned int iB1 = iB_[axis1_];
+    const unsigned int b1min = is_boundary[0], b1max = is_boundary[1], b2min = is_boundary[2], b2max = is_boundary[3];
+#define DB1( j, k ) ( db1 ? db1[( j )*n2d + ( k )] : 0. )
+#define DB2( j, k ) ( db2 ? db2[( j )*n2p + ( k )] : 0. )
+    /* B1 */
+    if( axis0_ == 0 ) {
+        for( unsigned int j=b1min; j<n1p-b1max ; j++ )
+            for( unsigned int k=b2min ; k<n2d-b2max ; k++ )
+                B1[ iB1*nyz_pd + j*nz_d + k ]
+                    = Alpha_   *  E2[ p0*nyz_pd + j*nz_d + k ]
+                    + Beta_    *( B1[ p1*nyz_pd + j*nz_d + k ]-0. )
+                    + Gamma_   * DB1( j, k )
+                    + Delta_   *( B0[ p0*nyz_dd + (j+1)*nz_d + k ]-0. )
+                    + Epsilon_ *( B0[ p0*nyz_dd +  j   *nz_d + k ]-0. )
+                    + 0.;
+    } else if( axis0_ == 1 ) {
+        for( unsigned int i=b1min; i<n1p-b1max ; i++ )
+            for( unsigned int k=b2min ; k<n2d-b2max ; k++ )
+                B1[ i*nyz_dd + iB1*nz_d + k ]
+                    =-Alpha_   *  E2[ i*nyz_pd + p0*nz_d + k ]
+                    + Beta_    *( B1[ i*nyz_dd + p1*nz_d + k ]-0. )
+                    + Gamma_   * DB1( i, k )
+                    + Delta_   *( B0[ (i+1)*nyz_pd + p0*nz_d + k ]-0. )
+                    + Epsilon_ *( B0[  i   *nyz_pd + p0*nz_d + k ]-0. )
+                    + 0.;
+    } else {
+        for( unsigned int i=b1min; i<n1p-b1max ; i++ )
+            for( unsigned int j=b2min ; j<n2d-b2max ; j++ )
+                B1[ i*nyz_dd + j*nz_d + iB1 ]
+                    = Alpha_   *  E2[ i*nyz_dp + j*nz_p + p0 ]
+                    + Beta_    *( B1[ i*nyz_dd + j*nz_d + p1 ]-0. )
+                    + Gamma_   * DB1( i, j )
+                    + Delta_   *( B0[ (i+1)*nyz_dp + j*nz_p + p0 ]-0. )
+                    + Epsilon_ *( B0[  i   *nyz_dp + j*nz_p + p0 ]-0. )
+                    + 0.;
+    }
+    /* B2 */
+    if( axis0_ == 0 ) {
+        for( unsigned int j=b1min; j<n1d-b1max ; j++ )
+            for( unsigned int k=b2min; k<n2p-b2max ; k++ )
+                B2[ iB1*nyz_dp + j*nz_p + k ]
+                    = -Alpha_ *  E1[ p0*nyz_dp + j*nz_p + k ]
+                    +  Beta_  *( B2[ p1*nyz_dp + j*nz_p + k ]-0. )
+                    +  Gamma_ * DB2( j, k )
+                    +  Zeta_  *( B0[ p0*nyz_dd + j*nz_d + k+1 ]-0. )
+                    +  Eta_   *( B0[ p0*nyz_dd + j*nz_d + k   ]-0. )
+                    +  0.;
+    } else if( axis0_ == 1 ) {
+        for( unsigned int i=b1min; i<n1d-b1max ; i++ )
+            for( unsigned int k=b2min; k<n2p-b2max ; k++ )
+                B2[ i*nyz_dp + iB1*nz_p + k ]
+                    =  Alpha_ *  E1[ i*nyz_pp + p0*nz_p + k ]
+                    +  Beta_  *( B2[ i*nyz_dp + p1*nz_p + k ]-0. )
+                    +  Gamma_ * DB2( i, k )
+                    +  Zeta_  *( B0[ i*nyz_pd + p0*nz_d + k+1 ]-0. )
+                    +  Eta_   *( B0[ i*nyz_pd + p0*nz_d + k   ]-0. )
+                    +  0.;
+    } else {
+        for( unsigned int i=b1min; i<n1d-b1max ; i++ )
+            for( unsigned int j=b2min; j<n2p-b2max ; j++ )
+                B2[ i*nyz_pd + j*nz_d + iB1 ]
+                    = -Alpha_ *  E1[ i*nyz_pp + j*nz_p + p0 ]
+                    +  Beta_  *( B2[ i*nyz_pd + j*nz_d  + p1 ]-0. )
+                    +  Gamma_ * DB2( i, j )
+                    +  Zeta_  *( B0[ i*nyz_dp + (j+1)*nz_p + p0 ]-0. )
+                    +  Eta_   *( B0[ i*nyz_dp +  j   *nz_p + p0 ]-0. )
+                    +  0.;
+    }
+#undef DB1
+#undef DB2
+}

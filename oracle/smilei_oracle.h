@@ -59,6 +59,17 @@ void orc_push( const orc_grid *g, int pusher, double mass,
 void orc_bc_tag( const orc_grid *g, const double *x, const double *y, const double *z,
                  int *keys, int istart, int iend );
 
+/* a10b particle boundary conditions with `remove` at global box sides */
+void orc_bc_apply( const orc_grid *g, const int *bc_remove, const double *x, const double *y, const double *z,
+                   const double *px, const double *py, const double *pz, const double *w, short *q,
+                   int *cell_keys, int imin, int imax, double *energy_lost );
+
+/* Silver-Mueller boundary condition on one global box face (zero external fields) */
+void orc_apply_SM( const orc_grid *g, int i_boundary, const double *K, const int *is_boundary,
+                   const double *Ex, const double *Ey, const double *Ez, double *Bx, double *By, double *Bz,
+                   const double *db1, const double *db2 );
+
+
 /* a11-a14 deposit */
 void orc_project( const orc_grid *g, int order, double *Jx, double *Jy, double *Jz,
                   const double *x, const double *y, const double *z,

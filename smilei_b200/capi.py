@@ -17,6 +17,7 @@ FIELD_ID = {name: i for i, name in enumerate(FIELDS)}
 # namelist aliases (src/ElectroMagn/ElectroMagn.h:163-190)
 FIELD_ID.update({"Bx_m": FIELD_ID["Bxm"], "By_m": FIELD_ID["Bym"], "Bz_m": FIELD_ID["Bzm"], "Rho": FIELD_ID["rho"]})
 PUSHERS = {"boris": 0, "vay": 1, "higueracary": 2}
+PBC = {"periodic": 0, "remove": 1}
 DYN_KEEP_SCRATCH = 1
 DYN_DIAG_RHO = 2
 UNPACK_COPY, UNPACK_ADD = 0, 1
@@ -32,6 +33,7 @@ SYMBOLS = (
     "sb200_halo_plane_elems", "sb200_halo_pack", "sb200_halo_unpack", "sb200_halo_sum_self",
     "sb200_halo_exchange_self", "sb200_leaving_count", "sb200_leaving_pack", "sb200_leaving_pack_known", "sb200_arriving_unpack",
     "sb200_debug_flags", "sb200_species_init_thermal", "sb200_launch_count",
+    "sb200_species_set_bc", "sb200_species_lost_energy", "sb200_apply_SM",
 )
 
 
@@ -126,6 +128,26 @@ class Patch:
         pusher = PUSHERS[pusher] if isinstance(pusher, str) else int(pusher)
         _check(lib().sb200_species_config(self._h, ispec, C.c_double(mass), pusher, C.c_size_t(capacity)),
                "sb200_species_config")
+
+    def species_set_bc(self, ispec, bc):
+        """bc: six entries (xmin xmax ymin ymax zmin zmax), each 'periodic' / 'remove' or SB200_PBC_*."""
+        codes = [PBC[b] if isinstance(b, str) else int(b) for b in bc]
+        arr = (C.c_int * 6)(*codes)
+        _check(lib().sb200_species_set_bc(self._h, ispec, arr), "sb200_species_set_bc")
+
+    def species_lost_energy(self, ispec, reset=False):
+        v = C.c_double(0.)
+        _check(lib().sb200_species_lost_energy(self._h, ispec, C.byref(v), int(reset)), "sb200_species_lost_energy")
+        return v.value
+
+    def apply_SM(self, i_boundary, k, is_boundary=(0, 0, 0, 0), db1=None, db2=None):
+        """ElectroMagnBC3D_SM::apply on one global box side; db1/db2 = laser amplitudes on the face or None."""
+        kk = (C.c_double * 3)(*[float(v) for v in k])
+        isb = (C.c_int * 4)(*[int(v) for v in is_boundary])
+        a1 = None if db1 is None else np.ascontiguousarray(db1, dtype=np.float64)
+        a2 = None if db2 is None else np.ascontiguousarray(db2, dtype=np.float64)
+        _check(lib().sb200_apply_SM(self._h, int(i_boundary), kk, isb, None if a1 is None else _p(a1, np.float64),
+                                    None if a2 is None else _p(a2, np.float64)), "sb200_apply_SM")
 
     def species_set(self, ispec, x, y, z, px, py, pz, w, q):
         n = len(x)

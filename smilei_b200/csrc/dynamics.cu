@@ -109,6 +109,8 @@ struct DynArgs {
     double  one_over_mass;
     double  jscale, jinv;     // fixed-point scale of the J box and its inverse
     int     tiles[3];
+    int     bc_remove[6];     // 1: `remove` particle BC on this side (xmin xmax ymin ymax zmin zmax) AND the patch touches that global edge
+    double *lost;             // accumulates w*(gamma-1) of the removed particles
 };
 
 // a particle tagged for exchange: count it and remember its index (sb200_leaving_pack orders the list)
@@ -117,6 +119,31 @@ __device__ __forceinline__ void note_leaver( const DynArgs &a, int tag, size_t i
     const int t = -tag-2;
     const int c = atomicAdd( &a.leave_counts[t], 1 );
     if( c < a.leave_cap ) a.leave_idx[( size_t )t*a.leave_cap + c] = ( int )ip;
+}
+
+// PartBoundCond::apply on one particle (ParticleBC/PartBoundCond.h:38-76): the six boundary functions run in the
+// order xmin xmax ymin ymax zmin zmax.  internal_inf/sup (BoundaryConditionType.cpp:15-57) tag a particle for
+// exchange only while its key is still >= 0; remove_particle_inf/sup (:204-294) act whatever the key is: key = -1,
+// charge = 0 (so the projector that follows deposits nothing) and w*(gamma-1) is added to the lost energy — once per
+// boundary the particle is beyond, as in the reference.
+__device__ __forceinline__ int boundary_tag( const DynArgs &a, const GridDev &g, const double *npos, double px, double py, double pz,
+                                             double weight, size_t ip, bool &removed )
+{
+    int tag = 0, nrem = 0;
+#pragma unroll
+    for( int d=0; d<3; d++ ) {
+        if( a.bc_remove[2*d] ) { if( npos[d] < g.xmin[d] ) { tag = -1; nrem++; } }
+        else if( tag == 0 && npos[d] < g.xmin[d] ) tag = -2 - 2*d;
+        if( a.bc_remove[2*d+1] ) { if( npos[d] >= g.xmax[d] ) { tag = -1; nrem++; } }
+        else if( tag == 0 && npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
+    }
+    removed = nrem > 0;
+    if( removed ) {
+        const double gf = sqrt( 1.0 + px*px + py*py + pz*pz );
+        atomicAdd( a.lost, ( double )nrem*( weight*( gf - 1.0 ) ) );
+        a.q[ip] = 0;
+    }
+    return tag;
 }
 
 // separable gather of one component from its staged box: sum_i cx[i] sum_j cy[j] sum_k cz[k] F
@@ -415,7 +442,8 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
         // ---- S0 / S1 / DS on the Esirkepov window (Projector3D2Order.cpp:99-159)
         double S0[3][T::WD], DS[3][T::WD];
         int    nkey[3];
-        int    tag = 0;
+        bool   removed;
+        const int tag = boundary_tag( a, g, npos, px, py, pz, weight, ip, removed );
 #pragma unroll
         for( int d=0; d<3; d++ ) {
             const double pn = npos[d]*g.dxi[d];
@@ -431,19 +459,14 @@ __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, co
 #pragma unroll
             for( int s=0; s<T::WD; s++ ) DS[d][s] = S1[s] - S0[d][s];
             nkey[d] = ( int )( ( double )ipn - g.min_loc_round[d] );
-            // PartBoundCond::apply: x first, then y, then z; first hit wins
-            if( tag == 0 ) {
-                if( npos[d] < g.xmin[d] ) tag = -2 - 2*d;
-                else if( npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
-            }
         }
         int key = tag;
         if( tag == 0 ) { key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2]; atomicAdd( &a.count[key], 1 ); }
-        else note_leaver( a, tag, ip );
+        else if( tag < -1 ) note_leaver( a, tag, ip );
         a.key[ip] = key;
 
         // ---- currents (Esirkepov), accumulated in the tile's J box
-        const double charge_weight = g.inv_cell_volume*( double )charge*weight;
+        const double charge_weight = removed ? 0. : g.inv_cell_volume*( double )charge*weight;
         const double cr[3] = { charge_weight*g.d_ov_dt[0], charge_weight*g.d_ov_dt[1], charge_weight*g.d_ov_dt[2] };
         jbox_t *jb = sJ + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2];
         esirkepov_general<T>( jb, S0, DS, cr, a.jscale );
@@ -863,8 +886,9 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
             }
 
             // new shape factors, tag / next key
-            int nkey[3], tag = 0;
-            bool same = true;
+            int nkey[3];
+            bool same = true, removed;
+            const int tag = boundary_tag( a, g, npos, px, py, pz, weight, ip, removed );
 #pragma unroll
             for( int d=0; d<3; d++ ) {
                 const double pn = npos[d]*g.dxi[d];
@@ -875,20 +899,16 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
                 shifts |= ( shift+1 ) << ( 2*d );
                 same = same && shift == 0;
                 nkey[d] = ( int )( ( double )ipn - g.min_loc_round[d] );
-                if( tag == 0 ) {
-                    if( npos[d] < g.xmin[d] ) tag = -2 - 2*d;
-                    else if( npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
-                }
                 xnpos[d] = pn;
 #pragma unroll
                 for( int s=0; s<NW; s++ ) DS[d][s] = w1[s] - S0[d][s];
             }
             int key = tag;
             if( tag == 0 ) { key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2]; atomicAdd( &a.count[key], 1 ); }
-            else note_leaver( a, tag, ip );
+            else if( tag < -1 ) note_leaver( a, tag, ip );
             a.key[ip] = key;
 
-            const double charge_weight = g.inv_cell_volume*( double )charge*weight;
+            const double charge_weight = removed ? 0. : g.inv_cell_volume*( double )charge*weight;
             cr[0] = charge_weight*g.d_ov_dt[0]; cr[1] = charge_weight*g.d_ov_dt[1]; cr[2] = charge_weight*g.d_ov_dt[2];
             fast = same;
         }
@@ -1183,15 +1203,17 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
                     }
                 }
 
-                const double charge_weight = g.inv_cell_volume*( double )charge*weight;
+                bool removed;
+                const int tag = boundary_tag( a, g, npos, px, py, pz, weight, ip, removed );
+                const double charge_weight = removed ? 0. : g.inv_cell_volume*( double )charge*weight;
                 cr[0] = charge_weight*g.d_ov_dt[0]; cr[1] = charge_weight*g.d_ov_dt[1]; cr[2] = charge_weight*g.d_ov_dt[2];
 
-                // new shape, tag / next key; the record of the deposit: per dimension M[3], DS[3] on the HOME nodes
+                // new shape, next key; the record of the deposit: per dimension M[3], DS[3] on the HOME nodes
                 // (the 3 nodes of S0) and the flux coefficients at the 2 home flux points.  A particle that moved to
                 // the next node along a dimension has S1 shifted by one node: two of its three weights still fall on
                 // home nodes, the third (s1e) on the node just outside; the flux running sum (Projector3D2Order.cpp:
                 // 215-228) starts one node earlier when the shift is negative.
-                int nkey[3], tag = 0, nx = 0;
+                int nkey[3], nx = 0;
                 double cf[3][2];
 #pragma unroll
                 for( int d=0; d<3; d++ ) {
@@ -1202,10 +1224,6 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
                     const int shift = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );
                     shifts |= ( shift+1 ) << ( 2*d );
                     nkey[d] = ( int )( ( double )ipn - g.min_loc_round[d] );
-                    if( tag == 0 ) {
-                        if( npos[d] < g.xmin[d] ) tag = -2 - 2*d;
-                        else if( npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
-                    }
                     xnpos[d] = pn;
                     double s1a = w1[0], s1b = w1[1], s1c = w1[2], s1e = 0.;
                     if( shift > 0 ) { s1e = w1[2]; s1c = w1[1]; s1b = w1[0]; s1a = 0.; }
@@ -1226,7 +1244,7 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
                 }
                 int key = tag;
                 if( tag == 0 ) { key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2]; atomicAdd( &a.count[key], 1 ); }
-                else note_leaver( a, tag, ip );
+                else if( tag < -1 ) note_leaver( a, tag, ip );
                 a.key[ip] = key;
                 fast = nx == 0;
                 one = nx == 1;
@@ -1506,6 +1524,11 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     a.iflags = p->iflags;
     a.sc_E = p->sc_E; a.sc_B = p->sc_B; a.sc_invgf = p->sc_invgf; a.sc_delta = p->sc_delta; a.sc_iold = p->sc_iold;
     a.n = s.n;
+    for( int d=0; d<3; d++ ) {       // `remove` acts at the global box sides only (PartBoundCond.cpp:99-245: patch->isBoundary)
+        a.bc_remove[2*d]   = s.bc[2*d]   == SB200_PBC_REMOVE && p->gd.pcoord[d] == 0;
+        a.bc_remove[2*d+1] = s.bc[2*d+1] == SB200_PBC_REMOVE && p->gd.pcoord[d] == p->gd.npatch[d]-1;
+    }
+    a.lost = s.d_lost;
     a.one_over_mass = 1.0/s.mass;                      // Pusher.cpp:20
     {
         // |J box entry| <= (particles whose window can reach a node) * max|q w|/V * max(d/dt): a node is reached

@@ -184,6 +184,7 @@ int sb200_patch_destroy( sb200_patch *p )
         if( p->sp[s].d_qwmax ) cudaFree( p->sp[s].d_qwmax );
         if( p->sp[s].leave_idx ) cudaFree( p->sp[s].leave_idx );
         if( p->sp[s].perm ) cudaFree( p->sp[s].perm );
+        if( p->sp[s].d_lost ) cudaFree( p->sp[s].d_lost );
     }
     free_particle_cols( p->spare.col, &p->spare.q, &p->spare.key );
     void *misc[] = { p->cursor, p->perm, p->blocksums, p->stage, p->red, p->leave_counts, p->iflags, p->d_maxcount,
@@ -238,6 +239,10 @@ int sb200_species_config( sb200_patch *p, int ispec, double mass, int pusher, si
         SB200_CUDA( cudaMalloc( &s.d_qwmax, sizeof( unsigned long long ) ) );
         SB200_CUDA( cudaMemset( s.d_qwmax, 0, sizeof( unsigned long long ) ) );
     }
+    if( !s.d_lost ) {
+        SB200_CUDA( cudaMalloc( &s.d_lost, sizeof( double ) ) );
+        SB200_CUDA( cudaMemset( s.d_lost, 0, sizeof( double ) ) );
+    }
     if( !s.count ) {
         SB200_CUDA( cudaMalloc( &s.count, ( p->ncells+1 )*sizeof( int ) ) );
         SB200_CUDA( cudaMemset( s.count, 0, ( p->ncells+1 )*sizeof( int ) ) );
@@ -246,6 +251,30 @@ int sb200_species_config( sb200_patch *p, int ispec, double mass, int pusher, si
         SB200_CUDA( cudaMalloc( &s.first, ( p->ncells+1 )*sizeof( int ) ) );
         SB200_CUDA( cudaMemset( s.first, 0, ( p->ncells+1 )*sizeof( int ) ) );
     }
+    return 0;
+}
+
+int sb200_species_set_bc( sb200_patch *p, int ispec, const int bc[6] )
+{
+    SB200_CHECK( p && bc && ispec >= 0 && ispec < p->nspec, "sb200_species_set_bc: bad arguments" );
+    for( int i=0; i<6; i++ )
+        SB200_CHECK( bc[i] == SB200_PBC_PERIODIC || bc[i] == SB200_PBC_REMOVE,
+                     "sb200_species_set_bc: only `periodic` and `remove` particle boundary conditions are on this path" );
+    for( int i=0; i<6; i++ ) p->sp[ispec].bc[i] = bc[i];
+    return 0;
+}
+
+int sb200_species_lost_energy( sb200_patch *p, int ispec, double *lost, int reset )
+{
+    SB200_CHECK( p && lost && ispec >= 0 && ispec < p->nspec, "sb200_species_lost_energy: bad arguments" );
+    SpeciesDev &s = p->sp[ispec];
+    SB200_CHECK( s.d_lost, "sb200_species_lost_energy: species not configured" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    double v = 0.;
+    SB200_CUDA( cudaMemcpyAsync( &v, s.d_lost, sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
+    if( reset ) SB200_CUDA( cudaMemsetAsync( s.d_lost, 0, sizeof( double ), p->stream ) );
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    *lost = s.mass*v;
     return 0;
 }
 

@@ -103,6 +103,24 @@ class _Ops:
         self._f("bc_tag")(C.byref(g), _p(x), _p(y), _p(z), _p(keys), 0, n)
         return keys
 
+    def bc_apply(self, g, bc_remove, part):
+        """PartBoundCond::apply with `remove` on the flagged global sides.  Returns (keys, q_after, energy_lost)."""
+        n = len(part["x"])
+        keys = np.zeros(n, dtype=np.int32)
+        q = part["q"].copy()
+        lost = C.c_double(0.)
+        flags = (C.c_int * 6)(*[int(v) for v in bc_remove])
+        self._f("bc_apply")(C.byref(g), flags, _p(part["x"]), _p(part["y"]), _p(part["z"]), _p(part["px"]),
+                            _p(part["py"]), _p(part["pz"]), _p(part["w"]), _p(q), _p(keys), 0, n, C.byref(lost))
+        return keys, q, lost.value
+
+    def apply_SM(self, g, i_boundary, k, is_boundary, F, db1=None, db2=None):
+        """ElectroMagnBC3D_SM::apply on Bx, By, Bz of F (in place)."""
+        kk = (C.c_double * 3)(*[float(v) for v in k])
+        isb = (C.c_int * 4)(*[int(v) for v in is_boundary])
+        self._f("apply_SM")(C.byref(g), int(i_boundary), kk, isb, _p(F["Ex"]), _p(F["Ey"]), _p(F["Ez"]), _p(F["Bx"]),
+                            _p(F["By"]), _p(F["Bz"]), _p(db1), _p(db2))
+
     def project(self, g, order, J, x, y, z, q, w, iold, delta, istart=0, iend=None):
         n = len(x)
         iend = n if iend is None else iend

@@ -476,3 +476,87 @@ def test_diag_step_rho_deposit(sb, orc, order):
         for k in ("Jx", "Jy", "Jz"):
             assert rel(p.field_get(k), J[k]) <= TOL_DEPOSIT, k
     p.close()
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_dynamics_remove_boundary_condition(sb, orc, order):
+    """`remove` particle BC at global box sides (remove_particle_inf/sup): removed particles get key -1 and
+    charge 0, deposit nothing, and their w*(gamma-1) is accumulated; the other sides tag for exchange."""
+    n, cell, dt = (12, 10, 16), (0.07, 0.08, 0.07), 0.035
+    g = ol.make_grid(n, order, cell, dt)
+    rng = np.random.default_rng(900 + order)
+    F = ol.random_fields(g, rng, scale=0.3)
+    N = 30000
+    mass = 2.0
+    P = ol.random_particles(g, rng, N, p_scale=1.5, charge=-1)
+    sides = ("remove", "remove", "periodic", "remove", "remove", "periodic")
+    flags = [1 if s == "remove" else 0 for s in sides]
+    p = make_patch(sb, n, order, cell, dt, 1)
+    for k, v in F.items():
+        p.field_set(k, v)
+    p.species_config(0, mass, "boris", N)
+    p.species_set_bc(0, sides)
+    p.species_set(0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+    p.sort(0)
+    S = p.species_get(0)
+    p.dynamics(0)
+    assert p.debug_flags()[1] == 0
+    out = p.species_get(0)
+    # oracle: gather, push, PartBoundCond::apply with remove, deposit with the zeroed charges
+    E, B, iold, delta = orc.interp(g, order, F, S["x"], S["y"], S["z"])
+    orc.push(g, 0, mass, S["x"], S["y"], S["z"], S["px"], S["py"], S["pz"], S["q"], E, B)
+    # decide removal from the GPU's own positions (identical to 1e-12; a particle within rounding of a side
+    # could otherwise fall on different sides of it)
+    G = {k: out[k] for k in ("x", "y", "z", "px", "py", "pz")}
+    G["w"], G["q"] = S["w"], S["q"]
+    keys, q_after, lost = orc.bc_apply(g, flags, G)
+    assert (keys == -1).sum() > 100 and (keys < -1).sum() > 100
+    k2 = keys.copy()
+    orc.cell_keys(g, out["x"], out["y"], out["z"], keys=k2)
+    assert np.array_equal(out["key"], k2)
+    assert np.array_equal(out["q"], q_after)
+    assert abs(p.species_lost_energy(0) - mass * lost) <= 1e-11 * mass * lost
+    J = {k: F[k].copy() for k in ("Jx", "Jy", "Jz")}
+    orc.project(g, order, J, S["x"], S["y"], S["z"], q_after, S["w"], iold, delta)
+    for k in ("Jx", "Jy", "Jz"):
+        assert rel(p.field_get(k), J[k]) <= TOL_DEPOSIT, k
+    cnt = p.leaving_count(0)
+    assert cnt == [int((keys == -2 - t).sum()) for t in range(6)]
+    # the sort drops removed and leaving particles alike
+    p.sort(0)
+    assert p.species_count(0) == int((keys >= 0).sum())
+    p.close()
+
+
+@pytest.mark.parametrize("i_boundary", range(6))
+def test_silver_muller_bit_exact(sb, orc, i_boundary):
+    """sb200_apply_SM against ElectroMagnBC3D_SM::apply (oracle, pinned on the reference class): bit-exact."""
+    n, cell, dt = (12, 9, 17), (0.07, 0.08, 0.09), 0.03
+    g = ol.make_grid(n, 2, cell, dt)
+    rng = np.random.default_rng(300 + i_boundary)
+    F = ol.random_fields(g, rng, names=("Ex", "Ey", "Ez", "Bx", "By", "Bz"))
+    axis0 = i_boundary // 2
+    axis1, axis2 = (1 if axis0 == 0 else 0), (1 if axis0 == 2 else 2)
+    pd = [g.n[i] + 2 * g.o[i] + 1 for i in range(3)]
+    k = [0.1, 0.2, -0.15]
+    k[axis0] = 1.0 if i_boundary % 2 == 0 else -1.0
+    db1 = np.ascontiguousarray(rng.standard_normal((pd[axis1], pd[axis2] + 1)))
+    db2 = np.ascontiguousarray(rng.standard_normal((pd[axis1] + 1, pd[axis2])))
+    for isb, lasers in (((0, 0, 0, 0), True), ((1, 1, 1, 1), False), ((0, 1, 1, 0), True)):
+        p = make_patch(sb, n, 2, cell, dt, 0)
+        for name, v in F.items():
+            p.field_set(name, v)
+        p.apply_SM(i_boundary, k, isb, db1 if lasers else None, db2 if lasers else None)
+        X = {name: v.copy() for name, v in F.items()}
+        orc.apply_SM(g, i_boundary, k, isb, X, db1 if lasers else None, db2 if lasers else None)
+        for name in ("Bx", "By", "Bz"):
+            assert np.array_equal(p.field_get(name), X[name]), (name, isb)
+        p.close()
+    # a patch that does not touch the side is left alone
+    p = make_patch(sb, n, 2, cell, dt, 0, pcoord=(1, 1, 1), npatch=(3, 3, 3))
+    for name, v in F.items():
+        p.field_set(name, v)
+    p.apply_SM(i_boundary, k, (0, 0, 0, 0), None, None)
+    for name in ("Bx", "By", "Bz"):
+        assert np.array_equal(p.field_get(name), F[name])
+    p.close()

@@ -167,3 +167,51 @@ def test_norm2_bit_exact(libs, pcoord, npatch):
     for name in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "rho"):
         f = np.ascontiguousarray(rng.standard_normal(ol.field_dims(g, name)))
         assert orc.field_norm2(g, f, name) == ref.field_norm2(g, f, name)
+
+
+@pytest.mark.parametrize("sides", [(1, 0, 0, 0, 0, 0), (1, 1, 0, 0, 1, 0), (1, 1, 1, 1, 1, 1), (0, 0, 0, 1, 0, 0)])
+def test_remove_particle_bc(libs, sides):
+    """PartBoundCond::apply with remove_particle_inf/sup on some global sides, internal_inf/sup on the others:
+    keys, zeroed charges and the lost energy, bit for bit."""
+    orc, ref = libs
+    n, cell, dt = (6, 5, 7), (0.1, 0.12, 0.09), 0.05
+    g = ol.make_grid(n, 2, cell, dt)
+    rng = np.random.default_rng(77)
+    P = ol.random_particles(g, rng, 5000, p_scale=1.0)
+    mn, mx = ol.patch_bounds(g)
+    for i, c in enumerate("xyz"):       # spread beyond the patch on every side, corners included
+        P[c] = np.ascontiguousarray(mn[i] + (rng.random(5000) * 1.4 - 0.2) * (mx[i] - mn[i]))
+    a = orc.bc_apply(g, sides, P)
+    b = ref.bc_apply(g, sides, P)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[2] == b[2]
+    assert (a[0] == -1).sum() > 0 and (a[1] == 0).sum() == (a[0] == -1).sum()
+
+
+@pytest.mark.parametrize("i_boundary", range(6))
+@pytest.mark.parametrize("laser", [False, True])
+def test_silver_muller(libs, i_boundary, laser):
+    """ElectroMagnBC3D_SM constructor + apply on every face, oblique incidence vector, with and without injected
+    amplitudes, transverse sides mixed (one with a neighbour, one without): exact equality of Bx, By, Bz."""
+    orc, ref = libs
+    n, cell, dt = (6, 5, 7), (0.1, 0.12, 0.09), 0.05
+    g = ol.make_grid(n, 2, cell, dt)
+    rng = np.random.default_rng(5 + i_boundary)
+    F = ol.random_fields(g, rng, names=("Ex", "Ey", "Ez", "Bx", "By", "Bz"))
+    axis0 = i_boundary // 2
+    axis1, axis2 = (1 if axis0 == 0 else 0), (1 if axis0 == 2 else 2)
+    p = [g.n[i] + 2 * g.o[i] + 1 for i in range(3)]
+    k = [0.2, -0.3, 0.25]
+    k[axis0] = 1.0 if i_boundary % 2 == 0 else -1.0
+    db1 = np.ascontiguousarray(rng.standard_normal((p[axis1], p[axis2] + 1))) if laser else None
+    db2 = np.ascontiguousarray(rng.standard_normal((p[axis1] + 1, p[axis2]))) if laser else None
+    isb = (1, 0, 0, 1)
+    A = {k_: v.copy() for k_, v in F.items()}
+    B = {k_: v.copy() for k_, v in F.items()}
+    orc.apply_SM(g, i_boundary, k, isb, A, db1, db2)
+    ref.apply_SM(g, i_boundary, k, isb, B, db1, db2)
+    changed = 0
+    for name in ("Bx", "By", "Bz"):
+        assert np.array_equal(A[name], B[name]), name
+        changed += int((A[name] != F[name]).sum())
+    assert changed > 0
