@@ -48,7 +48,8 @@ def pcoord_to_rank(pcoord, npatch):
 class Exchanger:
     """Halo and particle exchange for ONE patch (this rank's) on a periodic Cartesian rank grid."""
 
-    def __init__(self, patch, n, oversize, cell_length, npatch, pcoord, device, group=None, particle_buffer=1 << 16):
+    def __init__(self, patch, n, oversize, cell_length, npatch, pcoord, device, group=None, particle_buffer=1 << 16,
+                 periodic=(True, True, True)):
         self.patch = patch
         self.n = tuple(n)
         self.o = tuple(oversize)
@@ -62,13 +63,21 @@ class Exchanger:
             assert dist.is_initialized(), "torch.distributed must be initialised for more than one patch"
             assert dist.get_world_size(group) == self.world
             assert pcoord_to_rank(self.pcoord, self.npatch) == dist.get_rank(group)
+        # a non-periodic dimension has no neighbour beyond the box (MPI_PROC_NULL in Patch::neighbor_): None
+        self.periodic = tuple(bool(v) for v in periodic)
         self.nbr = []
         for d in range(3):
             lo = list(self.pcoord)
             hi = list(self.pcoord)
             lo[d] -= 1
             hi[d] += 1
-            self.nbr.append((pcoord_to_rank(lo, self.npatch), pcoord_to_rank(hi, self.npatch)))
+            r_lo, r_hi = pcoord_to_rank(lo, self.npatch), pcoord_to_rank(hi, self.npatch)
+            if not self.periodic[d]:
+                if self.pcoord[d] == 0:
+                    r_lo = None
+                if self.pcoord[d] == self.npatch[d] - 1:
+                    r_hi = None
+            self.nbr.append((r_lo, r_hi))
         self._bufs = {}
         self._pcap = int(particle_buffer)
         self.bytes_sent = 0
@@ -99,6 +108,18 @@ class Exchanger:
         n_lo, n_hi = to_lo.numel(), to_hi.numel()
         m_lo = n_hi if size_from_lo is None else size_from_lo     # the -dim neighbour sends me ITS to_hi block
         m_hi = n_lo if size_from_hi is None else size_from_hi
+        if lo is None or hi is None:
+            # box side without neighbour: nothing goes or comes that way (callers skip that side's unpack)
+            from_lo = self._buf(("rl", dim), m_lo)[:0 if lo is None else m_lo]
+            from_hi = self._buf(("rh", dim), m_hi)[:0 if hi is None else m_hi]
+            ops = []
+            if lo is not None:
+                ops.append((lo, to_lo, from_lo))
+            if hi is not None:
+                ops.append((hi, to_hi, from_hi))
+            if ops:
+                self._sendrecv(ops)
+            return from_lo, from_hi
         if lo == hi:
             # one peer on both sides: [payload for its +side | payload for its -side] in one message
             send = self._buf(("s2", dim), n_lo + n_hi)[:n_lo + n_hi]
@@ -119,9 +140,11 @@ class Exchanger:
         p = self.patch
         for dim in range(3):
             if self.npatch[dim] == 1:
-                for f in fields:
-                    p.halo_sum_self(f, dim)
+                if self.periodic[dim]:
+                    for f in fields:
+                        p.halo_sum_self(f, dim)
                 continue
+            has_lo, has_hi = self.nbr[dim][0] is not None, self.nbr[dim][1] is not None
             sizes, gsp = [], []
             for f in fields:
                 g = 1 + 2 * self.o[dim] + _DUAL[f][dim]            # SyncVectorPatch.cpp:235-237,284
@@ -140,8 +163,10 @@ class Exchanger:
             off = 0
             for f, g, s in zip(fields, gsp, sizes):
                 # the -dim neighbour's [n,n+gsp) planes are my [0,gsp); the +dim one's [0,gsp) are my [n,n+gsp)
-                p.halo_unpack(f, dim, 0, g, from_lo[off:off + s].data_ptr(), UNPACK_ADD)
-                p.halo_unpack(f, dim, self.n[dim], g, from_hi[off:off + s].data_ptr(), UNPACK_ADD)
+                if has_lo:
+                    p.halo_unpack(f, dim, 0, g, from_lo[off:off + s].data_ptr(), UNPACK_ADD)
+                if has_hi:
+                    p.halo_unpack(f, dim, self.n[dim], g, from_hi[off:off + s].data_ptr(), UNPACK_ADD)
                 off += s
 
     # ------------------------------------------------------------------ B
@@ -152,9 +177,11 @@ class Exchanger:
             o = self.o[dim]
             gsp = o + 2
             if self.npatch[dim] == 1:
-                for f in comps:
-                    p.halo_exchange_self(f, dim)
+                if self.periodic[dim]:
+                    for f in comps:
+                        p.halo_exchange_self(f, dim)
                 continue
+            has_lo, has_hi = self.nbr[dim][0] is not None, self.nbr[dim][1] is not None
             sizes = [o * p.halo_plane_elems(f, dim) for f in comps]
             tot = sum(sizes)
             to_lo = self._buf(("bl", dim), tot)[:tot]
@@ -168,8 +195,10 @@ class Exchanger:
             from_lo, from_hi = self._exchange_slabs(dim, to_lo, to_hi)
             off = 0
             for f, s in zip(comps, sizes):
-                p.halo_unpack(f, dim, 0, o, from_lo[off:off + s].data_ptr(), UNPACK_COPY)
-                p.halo_unpack(f, dim, self.n[dim] + gsp, o, from_hi[off:off + s].data_ptr(), UNPACK_COPY)
+                if has_lo:
+                    p.halo_unpack(f, dim, 0, o, from_lo[off:off + s].data_ptr(), UNPACK_COPY)
+                if has_hi:
+                    p.halo_unpack(f, dim, self.n[dim] + gsp, o, from_hi[off:off + s].data_ptr(), UNPACK_COPY)
                 off += s
 
     # ------------------------------------------------------------------ particles
@@ -186,6 +215,10 @@ class Exchanger:
             counts = [p.leaving_count(s) for s in range(n_species)]          # Patch::exchNbrOfParticles: sizes first
             c_lo = [c[2 * dim] for c in counts]
             c_hi = [c[2 * dim + 1] for c in counts]
+            if self.npatch[dim] == 1 and not self.periodic[dim]:
+                # nobody to exchange with: the particle boundary condition (remove) has dealt with the leavers
+                assert not any(c_lo) and not any(c_hi), "particles tagged for exchange across a non-periodic box side"
+                continue
             if self.npatch[dim] == 1:
                 for s in range(n_species):
                     self._ensure_pcap(max(c_lo[s], c_hi[s]))
@@ -196,11 +229,12 @@ class Exchanger:
                     p.arriving_unpack(s, to_lo.data_ptr(), c_lo[s])
                     p.arriving_unpack(s, to_hi.data_ptr(), c_hi[s])
                 continue
+            has_lo, has_hi = self.nbr[dim][0] is not None, self.nbr[dim][1] is not None
             cnt_lo = torch.tensor([float(v) for v in c_lo], dtype=torch.float64, device=self.device)
             cnt_hi = torch.tensor([float(v) for v in c_hi], dtype=torch.float64, device=self.device)
             r_lo, r_hi = self._exchange_slabs(dim, cnt_lo, cnt_hi)
-            n_from_lo = [int(v) for v in r_lo.cpu().tolist()]
-            n_from_hi = [int(v) for v in r_hi.cpu().tolist()]
+            n_from_lo = [int(v) for v in r_lo.cpu().tolist()] if has_lo else [0] * n_species
+            n_from_hi = [int(v) for v in r_hi.cpu().tolist()] if has_hi else [0] * n_species
             # per direction, every species block is padded to the largest count of that direction, which both
             # ends of the link know: what I send to -dim is what that neighbour announced-to-receive, etc.
             pad_to_lo, pad_to_hi = max(max(c_lo), 1), max(max(c_hi), 1)
@@ -215,8 +249,10 @@ class Exchanger:
                                                     RECORD * pad_from_hi * n_species)
             for s in range(n_species):
                 # arrivals from the -dim neighbour first, then from the +dim one (deterministic order)
-                p.arriving_unpack(s, from_lo[RECORD * pad_from_lo * s:].data_ptr(), n_from_lo[s])
-                p.arriving_unpack(s, from_hi[RECORD * pad_from_hi * s:].data_ptr(), n_from_hi[s])
+                if has_lo:
+                    p.arriving_unpack(s, from_lo[RECORD * pad_from_lo * s:].data_ptr(), n_from_lo[s])
+                if has_hi:
+                    p.arriving_unpack(s, from_hi[RECORD * pad_from_hi * s:].data_ptr(), n_from_hi[s])
             self._sync_patch_stream()
 
     def _ensure_pcap(self, need):

@@ -16,14 +16,18 @@ _OUT_OF_SCOPE_BLOCKS = (
     "DiagTrackParticles", "DiagPerformances", "DiagRadiationSpectrum", "DiagNewParticles", "CurrentFilter",
     "FieldFilter", "MultipleDecomposition", "Collisions", "RadiationReaction", "MultiphotonBreitWheeler",
     "ParticleInjector", "ExternalField", "PrescribedField", "Antenna", "PartWall", "LaserEnvelope",
-    "Laser", "LaserGaussian3D", "LaserPlanar1D", "LaserGaussian2D", "LaserOffset", "LaserGaussianAM",
+    "LaserPlanar1D", "LaserGaussian2D", "LaserOffset", "LaserGaussianAM",
 )
 
 
 # spatial / temporal profile helpers of src/Python/pyprofiles.py: only `constant` is evaluated on the hot
 # path; the others are accepted so that namelists parse, and raise if something tries to evaluate them
-_PROFILE_HELPERS = ("trapezoidal", "gaussian", "polygonal", "cosine", "polynomial", "tconstant", "ttrapezoidal",
-                    "tgaussian", "tpolygonal", "tcosine", "tpolynomial", "tsin2plateau", "transformPolarization")
+_PROFILE_HELPERS = ("trapezoidal", "gaussian", "polygonal", "cosine", "polynomial", "tpolygonal", "tcosine",
+                    "tpolynomial")
+# Laser block (src/Python/pyinit.py:455-467)
+_LASER_DEFAULTS = dict(box_side="xmin", omega=1., chirp_profile=1., time_envelope=1., space_envelope=[1., 0.],
+                       phase=[0., 0.], delay_phase=[0., 0.], space_time_profile=None, space_time_profile_AM=None,
+                       file=None, _offset=None)
 
 
 def _opaque_profile(name):
@@ -95,8 +99,37 @@ def _fresh_namespace():
     ns["Vectorization"] = _make_block("Vectorization", _VECTO_DEFAULTS, singleton=True)
     ns["MovingWindow"] = _make_block("MovingWindow", _MW_DEFAULTS, singleton=True)
     ns["DiagScalar"] = _make_block("DiagScalar", _SCALAR_DEFAULTS)
+    ns["Laser"] = _make_block("Laser", _LASER_DEFAULTS)
     for b in _OUT_OF_SCOPE_BLOCKS:
         ns[b] = _make_block(b, {})
+    # time profiles and the Gaussian-beam helper of src/Python/pyprofiles.py, numpy-aware (smilei_b200/laser.py)
+    from . import laser as _laser
+
+    def _sim_time():
+        M = ns["Main"]
+        if not M._instances:
+            raise NamelistError("time profile defined before `Main()`")
+        m = M._instances[0]
+        if m.simulation_time is not None:
+            return float(m.simulation_time)
+        return float(m.number_of_timesteps) * float(m.timestep) if m.timestep is not None else 0.
+
+    ns["tconstant"] = _laser.tconstant
+    ns["ttrapezoidal"] = lambda *a, **k: _laser.ttrapezoidal(_sim_time(), *a, **k)
+    ns["tgaussian"] = lambda *a, **k: _laser.tgaussian(_sim_time(), *a, **k)
+    ns["tsin2plateau"] = lambda *a, **k: _laser.tsin2plateau(_sim_time(), *a, **k)
+    ns["transformPolarization"] = lambda phi, e: list(_laser.polarization(phi, e))
+
+    def _gaussian3d(**kw):
+        M = ns["Main"]
+        if not M._instances:
+            raise NamelistError("LaserGaussian3D profile has been defined before `Main()`")
+        m = M._instances[0]
+        gl = list(m.grid_length) if m.grid_length else [n * c for n, c in zip(m.number_of_cells, m.cell_length)]
+        if kw.get("time_envelope") is None:
+            kw["time_envelope"] = _laser.tconstant()
+        return _laser.gaussian3d_block(lambda **b: ns["Laser"](**b), gl, **kw)
+    ns["LaserGaussian3D"] = _gaussian3d
     # helpers namelists commonly use (src/Python/pyprofiles.py); only the constant profile matters here
     ns["constant"] = lambda v, **kw: (lambda *a: v)
     for helper in _PROFILE_HELPERS:
@@ -118,7 +151,13 @@ class SpeciesParams:
         self.mean_velocity = list(block.mean_velocity)
         self.charge_density = block.charge_density
         self.number_density = block.number_density
-        self.boundary_conditions = block.boundary_conditions
+        # Species::boundary_conditions_: [[xmin,xmax],[ymin,ymax],[zmin,zmax]], short forms expanded (pyinit / Params)
+        bcs = block.boundary_conditions
+        full = [list(bcs[min(i, len(bcs) - 1)]) for i in range(3)]
+        for bc in full:
+            if len(bc) == 1:
+                bc.append(bc[0])
+        self.boundary_conditions = full
         self.block = block
 
 
@@ -184,12 +223,23 @@ class Params:
         sc = ns["DiagScalar"]._instances
         self.scalar_every = sc[0].every if sc else None
         self.ignored_blocks = {b: len(ns[b]._instances) for b in _OUT_OF_SCOPE_BLOCKS if ns[b]._instances}
+        self.laser_blocks = list(ns["Laser"]._instances)
+        # EM_boundary_conditions_k: incidence vectors of the Silver-Mueller sides, default = the inward normals, one
+        # vector = the same on every side (Params.cpp:475-515)
+        ks = list(m.EM_boundary_conditions_k)
+        if len(ks) == 1:
+            ks = ks * 6
+        elif len(ks) not in (0, 6):
+            raise NamelistError("EM_boundary_conditions_k must be the same size as the number of faces.")
+        default_k = [[1., 0., 0.], [-1., 0., 0.], [0., 1., 0.], [0., -1., 0.], [0., 0., 1.], [0., 0., -1.]]
+        self.EM_BCs_k = [[float(v) for v in ks[i]] if i < len(ks) else default_k[i] for i in range(6)]
 
     def check_hot_path(self):
         """Raise for anything the B200 path does not cover (no silent fallback)."""
         for d in range(3):
-            if self.EM_BCs[d] != ["periodic", "periodic"]:
-                raise NamelistError(f"EM_boundary_conditions {self.EM_BCs[d]} along dim {d}: only periodic is on the B200 hot path")
+            bc = self.EM_BCs[d]
+            if bc != ["periodic", "periodic"] and any(b != "silver-muller" for b in bc):
+                raise NamelistError(f"EM_boundary_conditions {bc} along dim {d}: periodic and silver-muller are on the B200 hot path")
         if self.has_window:
             raise NamelistError("MovingWindow is a 'next' row of the hot-path scope (SURVEY §8f), not built")
         for s in self.species:
@@ -197,7 +247,19 @@ class Params:
                 raise NamelistError(f"pusher `{s.pusher}` is outside the B200 hot path (boris, vay, higueracary)")
             if s.mass <= 0:
                 raise NamelistError("photon species are outside the B200 hot path")
-        for key in ("Laser", "LaserGaussian3D", "Collisions", "RadiationReaction", "MultiphotonBreitWheeler", "ParticleInjector"):
+            for d in range(3):
+                em_periodic = self.EM_BCs[d][0] == "periodic"
+                for side in range(2):
+                    pbc = s.boundary_conditions[d][side]
+                    if pbc not in ("periodic", "remove"):
+                        raise NamelistError(f"particle boundary condition `{pbc}` is outside the B200 hot path (periodic, remove)")
+                    if em_periodic != (pbc == "periodic"):         # PartBoundCond.cpp:76-80
+                        raise NamelistError(f"species {s.name}: periodic EM boundaries along dim {d} go with periodic particle boundaries, and only with them")
+        for L in self.laser_blocks:
+            d = {"x": 0, "y": 1, "z": 2}[str(L.box_side)[0]]
+            if self.EM_BCs[d][0 if str(L.box_side).endswith("min") else 1] != "silver-muller":
+                raise NamelistError(f"Laser on {L.box_side} needs a silver-muller boundary there")
+        for key in ("Collisions", "RadiationReaction", "MultiphotonBreitWheeler", "ParticleInjector", "LaserOffset"):
             if key in self.ignored_blocks:
                 raise NamelistError(f"{key} blocks are outside the B200 hot path")
 

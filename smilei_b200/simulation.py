@@ -111,8 +111,22 @@ class Simulation:
         self.EMfields = ElectroMagn(params, self.patch)
         self.vecSpecies = [Species(params, sp, self.patch, i) for i, sp in enumerate(params.species)]
         self.smpi = _Smpi()
+        # box sides: periodic or open (Silver-Mueller fields, `remove` particles)
+        self.periodic = tuple(params.EM_BCs[d][0] == "periodic" for d in range(3))
         self.exchanger = Exchanger(self.patch, self.n, params.oversize, params.cell_length, self.rank_grid,
-                                   self.pcoord, self.device, group)
+                                   self.pcoord, self.device, group, periodic=self.periodic)
+        # Patch::isBoundary( axis, side ): no neighbour there
+        self.is_boundary = [[(not self.periodic[d]) and self.pcoord[d] == (0 if s == 0 else self.rank_grid[d] - 1)
+                             for s in range(2)] for d in range(3)]
+        # lasers enter through the Silver-Mueller faces this patch holds (ElectroMagnBC::vecLaser, LaserFactory)
+        from .laser import Laser
+        self.lasers = []
+        min_local = [self.pcoord[d] * (self.n[d] * params.cell_length[d]) for d in range(3)]
+        for block in getattr(params, "laser_blocks", []):
+            L = Laser(block, params)
+            if self.is_boundary[L.i_boundary_ // 2][L.i_boundary_ % 2]:
+                L.init_fields(self.n, params.oversize, params.cell_length, min_local)
+                self.lasers.append(L)
         self.itime = 0
 
     # ------------------------------------------------------------------ initial state
@@ -131,6 +145,7 @@ class Simulation:
         n = len(x)
         cap = int(max(n * self.capacity_factor, n + 4096)) if capacity is None else capacity
         self.patch.species_config(ispec, self.vecSpecies[ispec].mass_, self.vecSpecies[ispec].pusher, cap)
+        self._set_species_bc(ispec)
         self.patch.species_set(ispec, x, y, z, px, py, pz, w, q)
         self.patch.sort(ispec)                       # VectorPatch::initialParticleSorting (VectorPatch.cpp:300-320)
 
@@ -141,10 +156,34 @@ class Simulation:
         for sp in self.vecSpecies:
             T = sp.sparams.temperature[0] if temperature is None else temperature
             self.patch.species_config(sp.ispec, sp.mass_, sp.pusher, int(ncell * nppc * self.capacity_factor) + 4096)
+            self._set_species_bc(sp.ispec)
             q = int(sp.sparams.charge)
             # same seed for every species: identical positions => rho = 0 at t = 0, no Poisson solve needed
             self.patch.species_init_thermal(sp.ispec, ppc, density, q, T, seed)
             self.patch.sort(sp.ispec)
+
+    def _set_species_bc(self, ispec):
+        bc = self.vecSpecies[ispec].sparams.boundary_conditions
+        flat = [bc[d][s] for d in range(3) for s in range(2)]
+        if any(b != "periodic" for b in flat):
+            self.patch.species_set_bc(ispec, flat)
+
+    def boundaryConditions(self, time_dual):
+        """ElectroMagn::boundaryConditions (ElectroMagn.cpp:371-394): the six sides in order, Silver-Mueller where
+        the box is open; the laser amplitudes of a side are summed on the host (ElectroMagnBC3D_SM.cpp:189-199)."""
+        for ib in range(6):
+            axis0, side = ib // 2, ib % 2
+            if self.periodic[axis0] or not self.is_boundary[axis0][side]:
+                continue
+            axis1, axis2 = (1 if axis0 == 0 else 0), (1 if axis0 == 2 else 2)
+            isb = (self.is_boundary[axis1][0], self.is_boundary[axis1][1], self.is_boundary[axis2][0], self.is_boundary[axis2][1])
+            db1 = db2 = None
+            for L in self.lasers:
+                if L.i_boundary_ == ib:
+                    a0, a1 = L.amplitude(0, time_dual), L.amplitude(1, time_dual)
+                    db1 = a0 if db1 is None else db1 + a0
+                    db2 = a1 if db2 is None else db2 + a1
+            self.patch.apply_SM(ib, self.params.EM_BCs_k[ib], isb, db1, db2)
 
     # ------------------------------------------------------------------ one time step
     def step(self, diag_flag=False):
@@ -164,7 +203,9 @@ class Simulation:
         # ---- importAndSortParticles (Smilei.cpp:637)
         for sp in self.vecSpecies:
             p.sort(sp.ispec)
-        # ---- finalizeSyncAndBCFields (Smilei.cpp:649): periodic => no BC, centre B
+        # ---- finalizeSyncAndBCFields (Smilei.cpp:649): boundary conditions on the open sides, then centre B
+        if not all(self.periodic):
+            self.boundaryConditions((self.itime + 1.5) * self.params.timestep)     # time_dual of this step (Smilei.cpp:172,488)
         self.EMfields.centerMagneticFields()
         self.itime += 1
 

@@ -31,7 +31,7 @@ class OraclePatch:
         self.orc = ol.Oracle()
         self.F = {k: np.zeros(ol.field_dims(self.g, k)) for k in
                   ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm", "Jx", "Jy", "Jz", "rho")}
-        self.sp = [dict(mass=1., pusher=0, P=None, first=None) for _ in range(n_species)]
+        self.sp = [dict(mass=1., pusher=0, P=None, first=None, bc=[0] * 6, lost=0.) for _ in range(n_species)]
         self.ncells = (n[0] + 1) * (n[1] + 1) * (n[2] + 1)
         self.mn, self.mx = ol.patch_bounds(self.g)
 
@@ -46,6 +46,21 @@ class OraclePatch:
         from smilei_b200.capi import PUSHERS
         self.sp[ispec]["mass"] = mass
         self.sp[ispec]["pusher"] = PUSHERS[pusher] if isinstance(pusher, str) else int(pusher)
+
+    def species_set_bc(self, ispec, bc):
+        from smilei_b200.capi import PBC
+        self.sp[ispec]["bc"] = [PBC[b] if isinstance(b, str) else int(b) for b in bc]
+
+    def species_lost_energy(self, ispec, reset=False):
+        v = self.sp[ispec]["mass"] * self.sp[ispec]["lost"]
+        if reset:
+            self.sp[ispec]["lost"] = 0.
+        return v
+
+    def apply_SM(self, i_boundary, k, is_boundary=(0, 0, 0, 0), db1=None, db2=None):
+        a1 = None if db1 is None else np.ascontiguousarray(db1, dtype=np.float64)
+        a2 = None if db2 is None else np.ascontiguousarray(db2, dtype=np.float64)
+        self.orc.apply_SM(self.g, i_boundary, k, is_boundary, self.F, a1, a2)
 
     def species_set(self, ispec, x, y, z, px, py, pz, w, q):
         P = dict(x=x, y=y, z=z, px=px, py=py, pz=pz, w=w)
@@ -88,7 +103,15 @@ class OraclePatch:
         g, o = self.g, self.orc
         E, B, iold, delta = o.interp(g, self.order, self.F, P["x"], P["y"], P["z"])
         o.push(g, s["pusher"], s["mass"], P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["q"], E, B)
-        tags = o.bc_tag(g, P["x"], P["y"], P["z"])
+        if any(s["bc"]):
+            # `remove` only acts where the patch touches the global box side (PartBoundCond.cpp:99-245)
+            eff = [s["bc"][2 * d + sd] == 1 and g.pcoord[d] == (0 if sd == 0 else g.npatch[d] - 1)
+                   for d in range(3) for sd in range(2)]
+            tags, q_after, lost = o.bc_apply(g, eff, P)
+            P["q"] = q_after
+            s["lost"] += lost
+        else:
+            tags = o.bc_tag(g, P["x"], P["y"], P["z"])
         o.project(g, self.order, self.F, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
         keys = tags.copy()
         o.cell_keys(g, P["x"], P["y"], P["z"], keys=keys)

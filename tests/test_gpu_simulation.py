@@ -126,3 +126,61 @@ def test_two_gpus_nccl_match_oracle_single_rank(rank_grid):
         assert len(a["x"]) == len(b["x"])
         for k in a:
             assert np.allclose(a[k], b[k], rtol=0, atol=1e-11), k
+
+
+LASER_NAMELIST = """
+Main(geometry="3Dcartesian", interpolation_order=2, timestep=0.04, number_of_timesteps=40,
+     cell_length=[0.1, 0.25, 0.25], number_of_cells=[24, 12, 12], number_of_patches=[1, 1, 1],
+     EM_boundary_conditions=[["silver-muller"], ["silver-muller"], ["periodic"]])
+LaserGaussian3D(box_side="xmin", a0=1.5, omega=1.0, focus=[1.2, 1.5, 1.5], waist=0.9,
+                time_envelope=tgaussian(start=0., duration=1.6, fwhm=0.6, center=0.8))
+Species(name="electron", position_initialization="regular", regular_number=[1, 1, 1], momentum_initialization="cold",
+        particles_per_cell=1, mass=1.0, charge=-1.0, number_density=0.02, pusher="{pusher}",
+        boundary_conditions=[["remove"], ["remove"], ["periodic"]])
+"""
+
+
+def _laser_run(pusher, patch_factory, steps):
+    from smilei_b200 import namelist
+    from smilei_b200.simulation import Simulation
+    params = namelist.load_namelist(LASER_NAMELIST.format(pusher=pusher), is_source=True)
+    sim = Simulation(params, patch_factory=patch_factory)
+    n = sim.n
+    rng = np.random.default_rng(3)
+    N = 4000
+    L = [n[d] * params.cell_length[d] for d in range(3)]
+    P = {c: np.ascontiguousarray(rng.random(N) * L[i] * (1 - 1e-12)) for i, c in enumerate("xyz")}
+    for c in ("px", "py", "pz"):
+        P[c] = np.ascontiguousarray(0.4 * rng.standard_normal(N))      # fast enough that some reach the open sides
+    P["w"] = np.full(N, 0.02 * params.cell_volume * n[0] * n[1] * n[2] / N)
+    P["q"] = np.full(N, -1, dtype=np.int16)
+    sim.set_particles(0, **P)
+    hist = sim.run(steps, scalars_every=1)
+    fields = {k: sim.patch.field_get(k) for k in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm")}
+    part = sim.patch.species_get(0)
+    lost = sim.patch.species_lost_energy(0)
+    count = sim.n_particles()
+    sim.close()
+    return hist, fields, part, lost, count
+
+
+@pytest.mark.parametrize("pusher", ["boris", "vay"])
+def test_laser_through_silver_muller_with_remove_matches_oracle(pusher):
+    """A Gaussian laser pulse injected through the xmin Silver-Mueller face of an open box (x, y open, z
+    periodic) onto electrons with `remove` boundaries: the CUDA path against the oracle-backed driver."""
+    steps = 40
+    hg, fg, pg, lg, cg = _laser_run(pusher, None, steps)
+    ho, fo, po, lo, co = _laser_run(pusher, OraclePatch, steps)
+    assert cg == co and cg[0] < 4000                          # particles did leave through the open sides
+    assert lo > 0 and abs(lg - lo) <= 1e-9 * lo
+    peak = max(np.max(np.abs(fo[k])) for k in ("Ey", "Ez", "By", "Bz"))
+    assert peak > 0.2                                          # the pulse is in the box
+    for name in fg:
+        assert np.max(np.abs(fg[name] - fo[name])) <= 1e-10 * steps * peak, name
+    for k, (a, b) in enumerate(zip(hg, ho)):
+        assert np.allclose(a[1], b[1], rtol=1e-10 * steps, atol=0), (k, a[1], b[1])
+        assert abs(a[2] - b[2]) <= 1e-10 * steps * max(abs(b[2]), 1e-300), (k, a[2], b[2])
+    ia = np.lexsort((pg["pz"], pg["py"], pg["px"]))
+    ib = np.lexsort((po["pz"], po["py"], po["px"]))
+    for k in ("x", "y", "z", "px", "py", "pz"):
+        assert np.allclose(pg[k][ia], po[k][ib], rtol=0, atol=1e-10), k
