@@ -191,6 +191,19 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def measured_traffic(args):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, when this run is the captured
+    configuration (it is not re-measured here: a number taken under a profiler is never a bench value)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)["k_dynamics_o2"]
+        if t["config"]["ncell"] == args.ncell and t["config"]["order"] == args.order:
+            return t["mean_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,9 +332,10 @@ def main():
         "yee_roofline_frac": (192. * ncell_local / ((mw_ms + ctr_ms) * 1e-3) / 1e9) / peak,
         "yee_ms": {"ampere_faraday_center": mw_ms, "center_shell": ctr_ms},
         "roofline": {"bound": "hbm", "kernel": "k_dynamics (gather+push+BC+deposit, one species)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dyn_bytes, "ms_per_launch": dyn_ms,
-                     "note": "FP64-pipe / shared-memory bound, not HBM bound: see DESIGN.md §6 and profiles/"},
+                     "note": "FP64-issue / latency bound, not HBM bound (DESIGN.md §4.2, profiles/r1_final_dynamics_256.txt); "
+                             "traffic = DRAM bytes per launch from the ncu --set full capture recorded in profiles/r1_traffic.json"},
         "energies": {"Ukin": [float(v) for v in uk], "Uelm": ue},
         "gpu_launches": int(launches),
     }

@@ -220,3 +220,83 @@ def test_three_ranks_gloo_distinct_neighbours():
         assert len(a["x"]) == len(b["x"]) == 18 * 12 * 12 * 6
         for k in a:
             assert np.allclose(a[k], b[k], rtol=0, atol=1e-11), k
+
+
+# ---------------------------------------------------------------------------------------------------------
+# open box: Silver-Mueller sides, a laser, `remove` particles — ranks at a box side have no neighbour there
+# ---------------------------------------------------------------------------------------------------------
+OPEN_NAMELIST = """
+Main(geometry="3Dcartesian", interpolation_order=2, timestep=0.04, number_of_timesteps=30,
+     cell_length=[0.1, 0.25, 0.25], number_of_cells=[24, 12, 12], number_of_patches=[1, 1, 1],
+     EM_boundary_conditions=[["silver-muller"], ["silver-muller"], ["periodic"]])
+LaserGaussian3D(box_side="xmin", a0=1.5, omega=1.0, focus=[1.2, 1.5, 1.5], waist=0.9,
+                time_envelope=tgaussian(start=0., duration=1.6, fwhm=0.6, center=0.8))
+Species(name="electron", position_initialization="regular", regular_number=[1, 1, 1], momentum_initialization="cold",
+        particles_per_cell=1, mass=1.0, charge=-1.0, number_density=0.02, pusher="boris",
+        boundary_conditions=[["remove"], ["remove"], ["periodic"]])
+"""
+
+
+def _run_rank_open(rank, world, rank_grid, steps, port, ret):
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p = namelist.load_namelist(OPEN_NAMELIST, is_source=True)
+    sim = Simulation(p, rank_grid=rank_grid, rank=rank, patch_factory=OraclePatch)
+    rng = np.random.default_rng(3)
+    N = 3000
+    L = [p.global_size[d] * p.cell_length[d] for d in range(3)]
+    a = {c: rng.random(N) * L[i] * (1 - 1e-12) for i, c in enumerate("xyz")}
+    for c in ("px", "py", "pz"):
+        a[c] = 0.4 * rng.standard_normal(N)
+    a["w"] = np.full(N, 1e-3)
+    a["q"] = np.full(N, -1, dtype=np.int16)
+    mn, mx = sim.patch.mn, sim.patch.mx
+    inside = np.ones(N, bool)
+    for d, c in enumerate("xyz"):
+        inside &= (a[c] >= mn[d]) & (a[c] < mx[d])
+    sim.set_particles(0, **{k: np.ascontiguousarray(v[inside]) for k, v in a.items()})
+    hist = sim.run(steps, scalars_every=1)
+    parts = [sim.patch.species_get(0)]
+    lost = sim.patch.species_lost_energy(0)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (parts, lost))
+        dist.barrier()
+        dist.destroy_process_group()
+    else:
+        gathered = [(parts, lost)]
+    if rank == 0:
+        ret["hist"] = [(h[0], h[1].tolist(), h[2]) for h in hist]
+        ret["parts"] = [g[0] for g in gathered]
+        ret["lost"] = sum(g[1] for g in gathered)
+
+
+def _launch_open(rank_grid, steps):
+    world = int(np.prod(rank_grid))
+    if world == 1:
+        ret = {}
+        _run_rank_open(0, 1, rank_grid, steps, 0, ret)
+        return ret
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_run_rank_open, args=(world, rank_grid, steps, _free_port(), ret), nprocs=world, join=True)
+    return dict(ret)
+
+
+@pytest.mark.parametrize("rank_grid", [(2, 1, 1), (1, 2, 1)])
+def test_open_box_two_ranks_gloo_match_single_rank(rank_grid):
+    """Laser through the xmin Silver-Mueller side, open in x and y: split across two ranks along an OPEN
+    dimension (each rank has a neighbour on one side only) the run reproduces the single-rank one — fields
+    energy, kinetic energy, the surviving particles and the energy carried away by the removed ones."""
+    one = _launch_open((1, 1, 1), 30)
+    two = _launch_open(rank_grid, 30)
+    assert one["lost"] > 0 and abs(one["lost"] - two["lost"]) <= 1e-9 * one["lost"]
+    for (it_a, uk_a, ue_a), (it_b, uk_b, ue_b) in zip(one["hist"], two["hist"]):
+        assert it_a == it_b
+        assert np.allclose(uk_a, uk_b, rtol=1e-10, atol=0)
+        assert abs(ue_a - ue_b) <= 1e-9 * abs(ue_a)
+    a = _canonical(one["parts"], 0)
+    b = _canonical(two["parts"], 0)
+    assert 0 < len(a["x"]) == len(b["x"]) < 3000
+    for k in a:
+        assert np.allclose(a[k], b[k], rtol=0, atol=1e-10), k
