@@ -27,6 +27,8 @@
 #include "Interpolator3D.h"
 #include "Params.h"
 #include "Particles.h"
+#include "ElectroMagnBC3D.h"
+#include "Laser.h"
 #include "Patch.h"
 #include "Projector3D.h"
 #include "Pusher.h"
@@ -200,6 +202,76 @@ public:
 private:
     Patch *patch_;
 };
+
+// ---------------------------------------------------------------------------------------------------
+//! Silver-Mueller side: replaces ElectroMagnBC3D_SM (src/ElectroMagnBC/ElectroMagnBC3D_SM.cpp) where
+//! ElectroMagnBC_Factory::create (src/ElectroMagnBC/ElectroMagnBC_Factory.h) returns it for "silver-muller".
+//! The laser amplitudes stay the reference's business (Laser / LaserProfile objects of vecLaser, Python profiles
+//! included): they are summed on the host exactly as ElectroMagnBC3D_SM::apply does (:189-199, :265-275) and
+//! handed to the device kernel.  External fields (B_val) are not on this path.
+class ElectroMagnBC3D_SM_B200 : public ElectroMagnBC3D
+{
+public:
+    ElectroMagnBC3D_SM_B200( Params &params, Patch *patch, unsigned int i_boundary )
+        : ElectroMagnBC3D( params, patch, i_boundary )
+    {
+        axis0_ = i_boundary / 2;
+        axis1_ = axis0_ == 0 ? 1 : 0;
+        axis2_ = axis0_ == 2 ? 1 : 2;
+        for( int i=0; i<3; i++ ) k_[i] = params.EM_BCs_k[i_boundary][i];
+    }
+    void apply( ElectroMagn *EMfields, double time_dual, Patch *patch ) override
+    {
+        if( !patch->isBoundary( i_boundary_ ) ) return;
+        const int isb[4] = { patch->isBoundary( axis1_, 0 ), patch->isBoundary( axis1_, 1 ),
+                             patch->isBoundary( axis2_, 0 ), patch->isBoundary( axis2_, 1 ) };
+        const unsigned int n1p = n_p[axis1_], n1d = n_d[axis1_], n2p = n_p[axis2_], n2d = n_d[axis2_];
+        std::vector<double> b1, b2, pos( 2 );
+        if( !vecLaser.empty() ) {
+            b1.assign( n1p*n2d, 0. );
+            b2.assign( n1d*n2p, 0. );
+            for( unsigned int j=isb[0]; j<n1p-isb[1]; j++ ) {
+                pos[0] = patch->getDomainLocalMin( axis1_ ) + ( ( int )j - ( int )EMfields->oversize[axis1_] )*d[axis1_];
+                for( unsigned int k=isb[2]; k<n2d-isb[3]; k++ ) {
+                    pos[1] = patch->getDomainLocalMin( axis2_ ) + ( ( int )k - 0.5 - ( int )EMfields->oversize[axis2_] )*d[axis2_];
+                    for( unsigned int il=0; il<vecLaser.size(); il++ ) b1[j*n2d+k] += vecLaser[il]->getAmplitude0( pos, time_dual, j, k );
+                }
+            }
+            for( unsigned int j=isb[0]; j<n1d-isb[1]; j++ ) {
+                pos[0] = patch->getDomainLocalMin( axis1_ ) + ( ( int )j - 0.5 - ( int )EMfields->oversize[axis1_] )*d[axis1_];
+                for( unsigned int k=isb[2]; k<n2p-isb[3]; k++ ) {
+                    pos[1] = patch->getDomainLocalMin( axis2_ ) + ( ( int )k - ( int )EMfields->oversize[axis2_] )*d[axis2_];
+                    for( unsigned int il=0; il<vecLaser.size(); il++ ) b2[j*n2p+k] += vecLaser[il]->getAmplitude1( pos, time_dual, j, k );
+                }
+            }
+        }
+        SB200_OR_ERROR( sb200_apply_SM( Bridge::of( patch ), ( int )i_boundary_, k_, isb,
+                                        b1.empty() ? NULL : b1.data(), b2.empty() ? NULL : b2.data() ) );
+    }
+    void save_fields( Field *, Patch * ) override {}
+    void disableExternalFields() override {}
+
+private:
+    unsigned int axis0_, axis1_, axis2_;
+    double k_[3];
+};
+
+//! Particle boundary conditions of a species: PartBoundCond (src/ParticleBC/PartBoundCond.cpp:99-245) chooses per
+//! box side among internal / remove / reflective ...; the fused kernel applies `periodic` and `remove` itself, so the
+//! adapter only forwards the species' choice (called from Species::initOperators next to the three factories).
+inline void forward_particle_bc( Patch *patch, Species *species, int ispec )
+{
+    int bc[6];
+    for( int d=0; d<3; d++ ) {
+        for( int s=0; s<2; s++ ) {
+            const std::string &name = species->boundary_conditions_[d][s];
+            if( name == "periodic" ) bc[2*d+s] = SB200_PBC_PERIODIC;
+            else if( name == "remove" ) bc[2*d+s] = SB200_PBC_REMOVE;
+            else { ERROR( "smilei_b200: particle boundary condition `" << name << "` is not on the B200 path (periodic, remove)" ); }
+        }
+    }
+    SB200_OR_ERROR( sb200_species_set_bc( Bridge::of( patch ), ispec, bc ) );
+}
 
 } // namespace smilei_b200
 

@@ -65,6 +65,7 @@ def test_adapter_header_compiles_against_reference_headers():
           'void use( Params &p, Patch *pt, Species *s ) {\n' \
           '  smilei_b200::Interpolator3D2OrderB200 i( p, pt ); smilei_b200::PusherB200 pu( p, s );\n' \
           '  smilei_b200::Projector3DB200 pr( p, pt ); smilei_b200::MA_Solver3D_B200 ma( p ); smilei_b200::MF_Solver3D_B200 mf( p, pt );\n' \
+          '  smilei_b200::ElectroMagnBC3D_SM_B200 sm( p, pt, 0 ); smilei_b200::forward_particle_bc( pt, s, 0 );\n' \
           '  smilei_b200::Bridge::attach( p, pt, 2, 0 ); }\n'
     r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-x", "c++", "-"] + inc + pyinc, input=src,
                        capture_output=True, text=True)
