@@ -148,6 +148,19 @@ int  sb200_maxwell( sb200_patch *p );
  * (Smilei.cpp:649 finalizeSyncAndBCFields). */
 int  sb200_apply_SM( sb200_patch *p, int i_boundary, const double k[3], const int is_boundary[4],
                      const double *db1, const double *db2 );
+/* Moving window along x (SimWindow::shift, src/MovWindow/SimWindow.cpp:98-550), cell-granular: the patch slides
+ * by `ncells` cells.  E, B, B_m move down by ncells planes and the planes entering on the right are zero (a patch
+ * created by the window starts with zero fields, SimWindow.cpp:224); the patch origin advances
+ * (Patch::initStep3 with n_moved, src/Patch/Patch.cpp:159-163); particles left behind (x < new xmin) are
+ * dropped and every species is marked unsorted.  The caller then appends the particles of the entering cells
+ * (sb200_species_append) and sorts.  Only a patch that spans the whole box along x (one rank along x). */
+int  sb200_window_shift( sb200_patch *p, int ncells );
+/* HOST -> device append of n particles at the end of a species (ParticleCreator::create on the cells a moving
+ * window uncovers, SimWindow.cpp:372-392); the species becomes unsorted. */
+int  sb200_species_append( sb200_patch *p, int ispec,
+                           const double *x, const double *y, const double *z,
+                           const double *px, const double *py, const double *pz,
+                           const double *w, const short *q, size_t n );
 int  sb200_center_B( sb200_patch *p );
 
 /* SpeciesV::computeParticleCellKeys histogram + SpeciesV::sortParticles

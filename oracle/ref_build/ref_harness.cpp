@@ -96,6 +96,7 @@ typedef struct {
     double dt;
     int    pcoord[3];
     int    npatch[3];
+    int    n_moved;
 } orc_grid;   /* same POD as oracle/smilei_oracle.h */
 
 }
@@ -152,6 +153,10 @@ Ctx *make_ctx( const orc_grid *g, double mass, int nthreads )
         pt.cell_starting_global_index[i]  = pt.Pcoordinates[i]*P.patch_size_[i];
         pt.cell_starting_global_index[i] -= P.oversize[i];
     }
+    /* Patch::initStep3 with n_moved (moving window), Patch.cpp:159-163 */
+    pt.cell_starting_global_index[0] += g->n_moved;
+    pt.min_local_[0] += g->n_moved*P.cell_length[0];
+    pt.max_local_[0] += g->n_moved*P.cell_length[0];
 
     c->species = blank<SpeciesV>();
     SpeciesV &S = *c->species;

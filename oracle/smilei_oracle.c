@@ -25,6 +25,10 @@ void orc_patch_bounds( const orc_grid *g, double *min_local, double *max_local, 
         max_local[i] = ( g->pcoord[i]+1 )*( g->n[i]*g->cell[i] );
         cell_start_gc[i] = g->pcoord[i]*g->n[i] - g->o[i];
     }
+    /* moving window: Patch::initStep3 with n_moved, Patch/Patch.cpp:159-163 */
+    cell_start_gc[0] += g->n_moved;
+    min_local[0] += g->n_moved*g->cell[0];
+    max_local[0] += g->n_moved*g->cell[0];
 }
 
 /* ElectroMagn::ElectroMagn, ElectroMagn/ElectroMagn.cpp:44-49 */

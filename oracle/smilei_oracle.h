@@ -35,6 +35,7 @@ typedef struct {
     double dt;            /* timestep                                                    */
     int    pcoord[3];     /* patch coordinates in the patch grid (Patch::Pcoordinates)    */
     int    npatch[3];     /* number_of_patches                                           */
+    int    n_moved;       /* cells the moving window has advanced along x (SimWindow::n_moved)  */
 } orc_grid;
 
 /* geometry helpers (Patch/Patch.cpp:136-165) */

@@ -33,7 +33,7 @@ SYMBOLS = (
     "sb200_halo_plane_elems", "sb200_halo_pack", "sb200_halo_unpack", "sb200_halo_sum_self",
     "sb200_halo_exchange_self", "sb200_leaving_count", "sb200_leaving_pack", "sb200_leaving_pack_known", "sb200_arriving_unpack",
     "sb200_debug_flags", "sb200_species_init_thermal", "sb200_launch_count",
-    "sb200_species_set_bc", "sb200_species_lost_energy", "sb200_apply_SM",
+    "sb200_species_set_bc", "sb200_species_lost_energy", "sb200_apply_SM", "sb200_window_shift", "sb200_species_append",
 )
 
 
@@ -155,6 +155,18 @@ class Patch:
         q = np.ascontiguousarray(q, dtype=np.int16)
         _check(lib().sb200_species_set(self._h, ispec, *[_p(a, np.float64) for a in cols], _p(q, np.int16),
                                        C.c_size_t(n)), "sb200_species_set")
+
+    def species_append(self, ispec, x, y, z, px, py, pz, w, q):
+        n = len(x)
+        if n == 0:
+            return
+        cols = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, px, py, pz, w)]
+        q = np.ascontiguousarray(q, dtype=np.int16)
+        _check(lib().sb200_species_append(self._h, ispec, *[_p(a, np.float64) for a in cols], _p(q, np.int16),
+                                          C.c_size_t(n)), "sb200_species_append")
+
+    def window_shift(self, ncells):
+        _check(lib().sb200_window_shift(self._h, int(ncells)), "sb200_window_shift")
 
     def species_init_thermal(self, ispec, ppc, density, charge, temperature, seed=0):
         _check(lib().sb200_species_init_thermal(self._h, ispec, (C.c_int * 3)(*ppc), C.c_double(density), int(charge),

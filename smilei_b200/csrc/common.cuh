@@ -103,6 +103,7 @@ struct sb200_patch {
     int               device = 0;
     cudaStream_t      stream = nullptr;
     int               nspec = 0;
+    int               n_moved = 0;           // cells the moving window has advanced (SimWindow::n_moved)
     size_t            falloc = 0;            // elements per field array
     double           *f[SB200_NFIELDS] = {};
     sb200::SpeciesDev *sp = nullptr;

@@ -302,6 +302,78 @@ int sb200_species_set( sb200_patch *p, int ispec,
     return 0;
 }
 
+int sb200_species_append( sb200_patch *p, int ispec,
+                          const double *x, const double *y, const double *z,
+                          const double *px, const double *py, const double *pz,
+                          const double *w, const short *q, size_t n )
+{
+    SB200_CHECK( p && ispec >= 0 && ispec < p->nspec, "sb200_species_append: bad species index" );
+    if( n == 0 ) return 0;
+    SB200_CHECK( x && y && z && px && py && pz && w && q, "sb200_species_append: null column" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    if( materialize( p, ispec ) ) return 1;
+    SpeciesDev &s = p->sp[ispec];
+    SB200_CHECK( s.n + n <= s.cap, "sb200_species_append: species capacity exceeded" );
+    const double *src[7] = { x, y, z, px, py, pz, w };
+    for( int c=0; c<7; c++ ) SB200_CUDA( cudaMemcpyAsync( s.col[c] + s.n, src[c], n*sizeof( double ), cudaMemcpyHostToDevice, p->stream ) );
+    SB200_CUDA( cudaMemcpyAsync( s.q + s.n, q, n*sizeof( short ), cudaMemcpyHostToDevice, p->stream ) );
+    SB200_CUDA( cudaMemsetAsync( s.key + s.n, 0, n*sizeof( int ), p->stream ) );
+    const size_t n0 = s.n;
+    s.n += n;
+    s.sorted = false;
+    s.count_valid = false;
+    if( update_qwmax( p, ispec, n0, n ) ) return 1;
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );       // the host arrays may be reused by the caller
+    return 0;
+}
+
+__global__ void __launch_bounds__( 256 ) k_window_drop( const double *__restrict__ x, int *__restrict__ key, size_t n, double xmin_new )
+{
+    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < n; i += ( size_t )gridDim.x*blockDim.x )
+        key[i] = ( key[i] < 0 || x[i] < xmin_new ) ? -1 : 0;
+}
+
+int sb200_window_shift( sb200_patch *p, int ncells )
+{
+    SB200_CHECK( p && ncells > 0, "sb200_window_shift: bad arguments" );
+    SB200_CHECK( p->gd.npatch[0] == 1, "sb200_window_shift: the patch must span the box along x (one rank along x)" );
+    SB200_CHECK( ncells < p->gd.n[0], "sb200_window_shift: shift larger than the patch" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    GridDev &g = p->gd;
+    // ---- fields: plane i <- plane i+ncells (x is the slowest dimension: one contiguous block), through the staging buffer
+    const size_t plane = ( size_t )g.sx, keep = ( size_t )( g.ax - ncells )*plane;
+    if( ensure_stage( p, keep ) ) return 1;
+    const int ids[9] = { SB200_EX, SB200_EY, SB200_EZ, SB200_BX, SB200_BY, SB200_BZ, SB200_BXM, SB200_BYM, SB200_BZM };
+    for( int f=0; f<9; f++ ) {
+        double *a = p->f[ids[f]];
+        SB200_CUDA( cudaMemcpyAsync( p->stage, a + ( size_t )ncells*plane, keep*sizeof( double ), cudaMemcpyDeviceToDevice, p->stream ) );
+        SB200_CUDA( cudaMemcpyAsync( a, p->stage, keep*sizeof( double ), cudaMemcpyDeviceToDevice, p->stream ) );
+        SB200_CUDA( cudaMemsetAsync( a + keep, 0, ( size_t )ncells*plane*sizeof( double ), p->stream ) );
+    }
+    // ---- origin of the patch (Patch::initStep3 with n_moved, Patch.cpp:159-163)
+    p->n_moved += ncells;
+    g.begin[0] = g.pcoord[0]*g.n[0] - g.o[0] + p->n_moved;
+    g.xmin[0] = ( g.pcoord[0]   )*( g.n[0]*g.cell[0] );
+    g.xmax[0] = ( g.pcoord[0]+1 )*( g.n[0]*g.cell[0] );
+    g.xmin[0] += p->n_moved*g.cell[0];
+    g.xmax[0] += p->n_moved*g.cell[0];
+    g.min_loc_round[0] = std::round( g.xmin[0]*g.dxi[0] );
+    // ---- particles left behind are dropped; keys are recomputed from the new origin by the next sort
+    for( int is=0; is<p->nspec; is++ ) {
+        if( materialize( p, is ) ) return 1;
+        SpeciesDev &s = p->sp[is];
+        if( s.n > 0 ) {
+            const unsigned blocks = ( unsigned )( ( s.n + 255 )/256 < 148*16 ? ( s.n + 255 )/256 : 148*16 );
+            k_window_drop<<<blocks, 256, 0, p->stream>>>( s.col[0], s.key, s.n, g.xmin[0] );
+            sb200::g_launches++;
+            SB200_CUDA( cudaGetLastError() );
+        }
+        s.sorted = false;
+        s.count_valid = false;
+    }
+    return 0;
+}
+
 int sb200_species_get( sb200_patch *p, int ispec,
                        double *x, double *y, double *z, double *px, double *py, double *pz,
                        double *w, short *q, int *keys, size_t n )

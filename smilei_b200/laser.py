@@ -34,8 +34,11 @@ class Laser:
         if side not in BOX_SIDES:
             raise ValueError("Laser: box_side must be xmin, xmax, ymin, ymax, zmin or zmax")           # Laser.cpp:24-46
         self.i_boundary_ = BOX_SIDES[side]
-        if getattr(block, "space_time_profile", None) is not None or getattr(block, "file", None) is not None:
-            raise ValueError("Laser: only separable profiles (time_envelope x space_envelope) are on the B200 path")
+        if getattr(block, "file", None) is not None:
+            raise ValueError("Laser: profiles read from a file (LaserOffset) are not on the B200 path")
+        # space_time_profile = [By(y,z,t), Bz(y,z,t)]: LaserProfileNonSeparable (Laser.h:130-155), None = zero component
+        self.space_time = getattr(block, "space_time_profile", None)
+        self.pos = [None, None]
         self.omega = float(getattr(block, "omega", 1.))
         self.chirp = getattr(block, "chirp_profile", 1.)
         self.time = getattr(block, "time_envelope", 1.)
@@ -67,11 +70,24 @@ class Laser:
                 p2[k] = v
                 v += d2
             Y, Z = np.meshgrid(p1, p2, indexing="ij")
+            if self.space_time is not None:
+                # the non-separable profile is evaluated at the positions ElectroMagnBC3D_SM::apply computes
+                # (ElectroMagnBC3D_SM.cpp:191-195, 267-271): min + (j - oversize)*d, minus half a cell on the dual axis
+                q1 = min_local[ax1] + (np.arange(dim1) - (0. if primal else 0.5) - oversize[ax1]) * d1
+                q2 = min_local[ax2] + (np.arange(dim2) - (0.5 if primal else 0.) - oversize[ax2]) * d2
+                self.pos[comp] = np.meshgrid(q1, q2, indexing="ij")
+                continue
             self.env[comp] = np.ascontiguousarray(_call(self.space[comp], Y, Z))
             self.phi[comp] = np.ascontiguousarray(_call(self.phase[comp], Y, Z))
 
     def amplitude(self, comp, t):
         """Laser::getAmplitude0 / getAmplitude1 on the whole face at time t."""
+        if self.space_time is not None:
+            f = self.space_time[comp]
+            Y, Z = self.pos[comp]
+            if f is None:
+                return np.zeros(Y.shape)
+            return np.ascontiguousarray(_call(f, Y, Z, np.float64(t)))
         omega = self.omega * float(_call(self.chirp, np.float64(t)))
         phi = self.phi[comp]
         envt = _call(self.time, t - (phi + self.delay[comp]) / omega)

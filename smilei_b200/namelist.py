@@ -16,7 +16,8 @@ _OUT_OF_SCOPE_BLOCKS = (
     "DiagTrackParticles", "DiagPerformances", "DiagRadiationSpectrum", "DiagNewParticles", "CurrentFilter",
     "FieldFilter", "MultipleDecomposition", "Collisions", "RadiationReaction", "MultiphotonBreitWheeler",
     "ParticleInjector", "ExternalField", "PrescribedField", "Antenna", "PartWall", "LaserEnvelope",
-    "LaserPlanar1D", "LaserGaussian2D", "LaserOffset", "LaserGaussianAM",
+    "LaserPlanar1D", "LaserGaussian2D", "LaserOffset", "LaserGaussianAM", "LaserEnvelopePlanar1D",
+    "LaserEnvelopeGaussian2D", "LaserEnvelopeGaussian3D", "LaserEnvelopeGaussianAM",
 )
 
 
@@ -93,7 +94,8 @@ _SCALAR_DEFAULTS = dict(every=None, precision=10, vars=[])
 
 
 def _fresh_namespace():
-    ns = {"math": math}
+    import numpy
+    ns = {"math": math, "np": numpy, "numpy": numpy, "os": os}
     ns["Main"] = _make_block("Main", _MAIN_DEFAULTS, singleton=True)
     ns["Species"] = _make_block("Species", _SPECIES_DEFAULTS)
     ns["Vectorization"] = _make_block("Vectorization", _VECTO_DEFAULTS, singleton=True)
@@ -219,6 +221,7 @@ class Params:
         v = ns["Vectorization"]._instances
         self.vectorization_mode = v[0].mode if v else "off"
         self.has_window = len(ns["MovingWindow"]._instances) > 0
+        self.window = ns["MovingWindow"]._instances[0] if self.has_window else None
         self.species = [SpeciesParams(b, i) for i, b in enumerate(ns["Species"]._instances)]
         sc = ns["DiagScalar"]._instances
         self.scalar_every = sc[0].every if sc else None
@@ -240,8 +243,8 @@ class Params:
             bc = self.EM_BCs[d]
             if bc != ["periodic", "periodic"] and any(b != "silver-muller" for b in bc):
                 raise NamelistError(f"EM_boundary_conditions {bc} along dim {d}: periodic and silver-muller are on the B200 hot path")
-        if self.has_window:
-            raise NamelistError("MovingWindow is a 'next' row of the hot-path scope (SURVEY §8f), not built")
+        if self.has_window and self.EM_BCs[0][0] == "periodic":
+            raise NamelistError("MovingWindow with a periodic x direction is not supported")
         for s in self.species:
             if s.pusher not in ("boris", "vay", "higueracary"):
                 raise NamelistError(f"pusher `{s.pusher}` is outside the B200 hot path (boris, vay, higueracary)")
@@ -259,7 +262,10 @@ class Params:
             d = {"x": 0, "y": 1, "z": 2}[str(L.box_side)[0]]
             if self.EM_BCs[d][0 if str(L.box_side).endswith("min") else 1] != "silver-muller":
                 raise NamelistError(f"Laser on {L.box_side} needs a silver-muller boundary there")
-        for key in ("Collisions", "RadiationReaction", "MultiphotonBreitWheeler", "ParticleInjector", "LaserOffset"):
+        for key in ("Collisions", "RadiationReaction", "MultiphotonBreitWheeler", "ParticleInjector", "LaserOffset",
+                    "LaserEnvelope", "LaserEnvelopePlanar1D", "LaserEnvelopeGaussian2D", "LaserEnvelopeGaussian3D",
+                    "LaserEnvelopeGaussianAM", "LaserPlanar1D", "LaserGaussian2D", "LaserGaussianAM", "ExternalField",
+                    "PrescribedField", "Antenna", "PartWall"):
             if key in self.ignored_blocks:
                 raise NamelistError(f"{key} blocks are outside the B200 hot path")
 

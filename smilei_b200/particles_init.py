@@ -64,11 +64,16 @@ def _maxwell_juttner(T, n, rng):
     return out
 
 
-def create(params, sp, n, pcoord, seed, rank, positions=None):
-    """Arrays (x,y,z,px,py,pz,w,q) of species `sp` inside the patch at `pcoord` with `n` cells."""
+def create(params, sp, n, pcoord, seed, rank, positions=None, origin_cells=None):
+    """Arrays (x,y,z,px,py,pz,w,q) of species `sp` inside the patch at `pcoord` with `n` cells, or — with
+    `origin_cells` — inside the box of `n` cells that starts at that global cell (the cells a moving window
+    uncovers, SimWindow.cpp:372-392)."""
     cell = params.cell_length
     nppc_prof = sp.particles_per_cell
-    origin = [pcoord[d] * n[d] * cell[d] for d in range(3)]
+    if origin_cells is None:
+        origin = [pcoord[d] * n[d] * cell[d] for d in range(3)]
+    else:
+        origin = [origin_cells[d] * cell[d] for d in range(3)]
     ic, jc, kc = np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(n[2]), indexing="ij")
     # profiles are evaluated at the cell centre (ParticleCreator.cpp:170-210: x_cell + 0.5 dx)
     X = origin[0] + (ic + 0.5) * cell[0]

@@ -78,6 +78,26 @@ class _Smpi:
     keep_scratch = False
 
 
+class SimWindow:
+    """src/MovWindow/SimWindow.{h,cpp}: the moving window along x.  The reference slides by one patch
+    (params.patch_size_[0] cells) whenever (time_dual - time_start)*velocity_x exceeds the distance already
+    moved; here the GPU holds one patch spanning the box along x and the same stride — the patch size of the
+    NAMELIST's number_of_patches — is applied as a shift of that patch by that many cells."""
+
+    def __init__(self, params):
+        w = params.window
+        self.active = w is not None
+        self.time_start = float(w.time_start) if self.active else float("inf")
+        self.velocity_x = float(w.velocity_x) if self.active else 1.
+        self.cell_length_x_ = params.cell_length[0]
+        self.n_space_x_ = params.global_size[0] // params.number_of_patches[0]      # params.patch_size_[0]
+        self.x_moved = 0.
+        self.n_moved = 0
+
+    def isMoving(self, time_dual):                                                    # SimWindow.cpp:93-96
+        return self.active and (time_dual - self.time_start) * self.velocity_x > self.x_moved
+
+
 class Simulation:
     """One rank's share of the run.  `rank_grid` = ranks per dimension (the GPU grid); the global box
     of the namelist is split evenly, one patch per rank, periodic."""
@@ -127,6 +147,9 @@ class Simulation:
             if self.is_boundary[L.i_boundary_ // 2][L.i_boundary_ % 2]:
                 L.init_fields(self.n, params.oversize, params.cell_length, min_local)
                 self.lasers.append(L)
+        self.simWindow = SimWindow(params)
+        if self.simWindow.active and self.rank_grid[0] != 1:
+            raise ValueError("MovingWindow: one rank along x (the patch must span the box along x)")
         self.itime = 0
 
     # ------------------------------------------------------------------ initial state
@@ -168,10 +191,11 @@ class Simulation:
         if any(b != "periodic" for b in flat):
             self.patch.species_set_bc(ispec, flat)
 
-    def boundaryConditions(self, time_dual):
+    def boundaryConditions(self, time_dual, sides=range(6)):
         """ElectroMagn::boundaryConditions (ElectroMagn.cpp:371-394): the six sides in order, Silver-Mueller where
-        the box is open; the laser amplitudes of a side are summed on the host (ElectroMagnBC3D_SM.cpp:189-199)."""
-        for ib in range(6):
+        the box is open; the laser amplitudes of a side are summed on the host (ElectroMagnBC3D_SM.cpp:189-199).
+        The x sides are skipped while the window moves (:374): SimWindow::shift applies xmin itself."""
+        for ib in sides:
             axis0, side = ib // 2, ib % 2
             if self.periodic[axis0] or not self.is_boundary[axis0][side]:
                 continue
@@ -204,10 +228,40 @@ class Simulation:
         for sp in self.vecSpecies:
             p.sort(sp.ispec)
         # ---- finalizeSyncAndBCFields (Smilei.cpp:649): boundary conditions on the open sides, then centre B
+        time_dual = (self.itime + 1.5) * self.params.timestep                      # Smilei.cpp:172,488
+        moving = self.simWindow.isMoving(time_dual)
         if not all(self.periodic):
-            self.boundaryConditions((self.itime + 1.5) * self.params.timestep)     # time_dual of this step (Smilei.cpp:172,488)
+            self.boundaryConditions(time_dual, sides=range(2, 6) if moving else range(6))
         self.EMfields.centerMagneticFields()
+        # ---- moveWindow (Smilei.cpp:667)
+        if moving:
+            self.moveWindow(time_dual)
         self.itime += 1
+
+    def moveWindow(self, time_dual):
+        """SimWindow::shift (SimWindow.cpp:98-550) for one patch spanning the box along x."""
+        w = self.simWindow
+        S = w.n_space_x_
+        w.n_moved += S                                                               # :136
+        self.lasers = []                                                             # laserDisabled, :144
+        self.patch.window_shift(S)
+        # particles of the cells uncovered on the right (ParticleCreator over the new patch, :372-392)
+        first_new = self.params.global_size[0] + w.n_moved - S
+        box = (S, self.n[1], self.n[2])
+        origin = (first_new, self.pcoord[1] * self.n[1], self.pcoord[2] * self.n[2])
+        created = {}
+        for sp in self.vecSpecies:
+            src = created.get(sp.sparams.position_initialization)
+            arrays = particles_init.create(self.params, sp.sparams, box, self.pcoord, self.params.random_seed + w.n_moved,
+                                           self.rank, positions=None if src is None else (src["x"], src["y"], src["z"]),
+                                           origin_cells=origin)
+            created[sp.name] = arrays
+            self.patch.species_append(sp.ispec, **arrays)
+            self.patch.sort(sp.ispec)
+        # xmin boundary condition now that the patch has moved (:420-430), lasers off
+        if not self.periodic[0]:
+            self.boundaryConditions(time_dual, sides=[0])
+        w.x_moved += w.cell_length_x_ * S                                            # :549
 
     def run(self, n_steps, scalars_every=None):
         out = []

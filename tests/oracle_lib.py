@@ -20,12 +20,17 @@ REF_FAST_SO = os.path.join(ORACLE_DIR, "_ref", "libsmilei_ref_fast.so")
 class Grid(C.Structure):
     """orc_grid of oracle/smilei_oracle.h."""
     _fields_ = [("n", C.c_int * 3), ("o", C.c_int * 3), ("cell", C.c_double * 3), ("dt", C.c_double),
-                ("pcoord", C.c_int * 3), ("npatch", C.c_int * 3)]
+                ("pcoord", C.c_int * 3), ("npatch", C.c_int * 3), ("n_moved", C.c_int)]
 
 
-def make_grid(n, order, cell, dt, pcoord=(0, 0, 0), npatch=(1, 1, 1)):
+def make_grid(n, order, cell, dt, pcoord=(0, 0, 0), npatch=(1, 1, 1), n_moved=0):
     return Grid((C.c_int * 3)(*n), (C.c_int * 3)(order, order, order), (C.c_double * 3)(*cell), float(dt),
-                (C.c_int * 3)(*pcoord), (C.c_int * 3)(*npatch))
+                (C.c_int * 3)(*pcoord), (C.c_int * 3)(*npatch), int(n_moved))
+
+
+def make_grid_moved(g, n_moved):
+    """The same patch after the moving window advanced n_moved cells in total."""
+    return make_grid(tuple(g.n), g.o[0], tuple(g.cell), g.dt, tuple(g.pcoord), tuple(g.npatch), n_moved)
 
 
 # (dual_x, dual_y, dual_z) per field, ElectroMagn3D.cpp:115-123
@@ -42,6 +47,8 @@ def patch_bounds(g):
     """Patch::initStep3 (Patch.cpp:146-147), same expression order."""
     mn = [(g.pcoord[i]) * (g.n[i] * g.cell[i]) for i in range(3)]
     mx = [(g.pcoord[i] + 1) * (g.n[i] * g.cell[i]) for i in range(3)]
+    mn[0] += g.n_moved * g.cell[0]          # Patch.cpp:159-163
+    mx[0] += g.n_moved * g.cell[0]
     return mn, mx
 
 

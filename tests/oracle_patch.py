@@ -62,6 +62,33 @@ class OraclePatch:
         a2 = None if db2 is None else np.ascontiguousarray(db2, dtype=np.float64)
         self.orc.apply_SM(self.g, i_boundary, k, is_boundary, self.F, a1, a2)
 
+    def species_append(self, ispec, x, y, z, px, py, pz, w, q):
+        P = self.sp[ispec]["P"]
+        new = dict(x=x, y=y, z=z, px=px, py=py, pz=pz, w=w)
+        for k, v in new.items():
+            P[k] = np.concatenate([P[k], np.asarray(v, dtype=np.float64)])
+        P["q"] = np.concatenate([P["q"], np.asarray(q, dtype=np.int16)])
+        P["key"] = np.concatenate([P["key"], np.zeros(len(x), dtype=np.int32)])
+        self.sp[ispec]["sorted"] = False
+
+    def window_shift(self, ncells):
+        """Cell-granular SimWindow::shift of a patch spanning the box along x (see sb200_window_shift)."""
+        for k in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm"):
+            a = self.F[k]
+            a[:-ncells] = a[ncells:].copy()
+            a[-ncells:] = 0.
+        self.n_moved = getattr(self, "n_moved", 0) + ncells
+        self.g = ol.make_grid_moved(self.g, self.n_moved) if hasattr(ol, "make_grid_moved") else self.g
+        self.mn, self.mx = ol.patch_bounds(self.g)
+        for s in self.sp:
+            P = s["P"]
+            if P is None:
+                continue
+            keep = P["x"] >= self.mn[0]
+            for k in P:
+                P[k] = np.ascontiguousarray(P[k][keep])
+            s["sorted"] = False
+
     def species_set(self, ispec, x, y, z, px, py, pz, w, q):
         P = dict(x=x, y=y, z=z, px=px, py=py, pz=pz, w=w)
         P = {k: np.ascontiguousarray(v, dtype=np.float64).copy() for k, v in P.items()}

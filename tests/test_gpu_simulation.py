@@ -184,3 +184,54 @@ def test_laser_through_silver_muller_with_remove_matches_oracle(pusher):
     ib = np.lexsort((po["pz"], po["py"], po["px"]))
     for k in ("x", "y", "z", "px", "py", "pz"):
         assert np.allclose(pg[k][ia], po[k][ib], rtol=0, atol=1e-10), k
+
+
+WINDOW_NAMELIST = """
+Main(geometry="3Dcartesian", interpolation_order=2, timestep=0.09, number_of_timesteps=90,
+     cell_length=[0.1, 0.5, 0.5], number_of_cells=[48, 8, 8], number_of_patches=[12, 1, 1],
+     EM_boundary_conditions=[["silver-muller"]])
+MovingWindow(time_start=2.5, velocity_x=0.9997)
+LaserGaussian3D(box_side="xmin", a0=1.0, omega=2.0, focus=[0., 2.0, 2.0], waist=1.5,
+                time_envelope=tgaussian(start=0., duration=2.4, fwhm=0.8, center=1.2))
+Species(name="electron", position_initialization="regular", momentum_initialization="cold",
+        particles_per_cell=1, mass=1.0, charge=-1.0, charge_density=0.01, pusher="vay",
+        boundary_conditions=[["remove"]])
+"""
+
+
+def _window_run(patch_factory, steps):
+    from smilei_b200 import namelist
+    from smilei_b200.simulation import Simulation
+    params = namelist.load_namelist(WINDOW_NAMELIST, is_source=True)
+    sim = Simulation(params, patch_factory=patch_factory)
+    sim.create_particles()
+    hist = sim.run(steps, scalars_every=1)
+    fields = {k: sim.patch.field_get(k) for k in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm")}
+    part = sim.patch.species_get(0)
+    out = dict(hist=hist, fields=fields, part=part, count=sim.n_particles(), n_moved=sim.simWindow.n_moved,
+               lost=sim.patch.species_lost_energy(0))
+    sim.close()
+    return out
+
+
+def test_moving_window_matches_oracle():
+    """Laser + cold plasma followed by a moving window (stride = the namelist's patch size, 4 cells): fields
+    slide, particles left behind are dropped, the uncovered cells are filled by the particle creator — the CUDA
+    path against the oracle-backed driver, through 15 shifts."""
+    steps = 90
+    G = _window_run(None, steps)
+    O = _window_run(OraclePatch, steps)
+    assert G["n_moved"] == O["n_moved"] and G["n_moved"] >= 14 * 4
+    assert G["count"] == O["count"]
+    peak = max(np.max(np.abs(O["fields"][k])) for k in ("Ey", "Ez", "By", "Bz"))
+    assert peak > 0.1                                             # the pulse is still in the (moved) box
+    for name in G["fields"]:
+        assert np.max(np.abs(G["fields"][name] - O["fields"][name])) <= 1e-10 * steps * peak, name
+    for k, (a, b) in enumerate(zip(G["hist"], O["hist"])):
+        assert np.allclose(a[1], b[1], rtol=1e-9 * steps, atol=1e-30), (k, a[1], b[1])
+        assert abs(a[2] - b[2]) <= 1e-10 * steps * max(abs(b[2]), 1e-300), (k, a[2], b[2])
+    pa, pb = G["part"], O["part"]
+    ia = np.lexsort((pa["z"], pa["y"], pa["x"]))
+    ib = np.lexsort((pb["z"], pb["y"], pb["x"]))
+    for k in ("x", "y", "z", "px", "py", "pz"):
+        assert np.allclose(pa[k][ia], pb[k][ib], rtol=0, atol=1e-9), k

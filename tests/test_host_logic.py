@@ -69,10 +69,25 @@ def test_reference_namelists_load_unmodified(path, order, nspec, n_time, size):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/benchmarks"), reason="reference namelists not present")
-def test_out_of_scope_namelist_is_rejected_loudly():
+def test_laser_wake_namelist_loads_unmodified():
+    """BASELINE.json configs[3]: Vay pusher, lasers through Silver-Mueller sides with oblique absorption vectors,
+    `remove` particles, moving window — all on the path."""
     p = namelist.load_namelist("/root/reference/benchmarks/tst3d_s_o2_laser_wake_yee_vay.py")
+    p.check_hot_path()
+    assert p.global_size == [512, 40, 40] and p.number_of_patches == [64, 4, 4] and p.n_time == 1077
+    assert p.EM_BCs == [["silver-muller", "silver-muller"]] * 3 and p.EM_BCs_k[3] == [1., -0.005, 0.]
+    assert p.species[0].pusher == "vay" and p.species[0].boundary_conditions == [["remove", "remove"]] * 3
+    assert p.has_window and float(p.window.time_start) == 102.4 and p.window.velocity_x == 0.9997
+    assert len(p.laser_blocks) == 1 and p.laser_blocks[0].space_time_profile is not None
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/benchmarks"), reason="reference namelists not present")
+@pytest.mark.parametrize("path", ["benchmarks/tst3d_08_envelope_wake.py", "benchmarks/tst3d_22_em_dispersion_m4.py",
+                                  "benchmarks/tst3d_13_particle_injection_x.py"])
+def test_out_of_scope_namelist_is_rejected_loudly(path):
+    """Envelope model / PML, another Maxwell solver, particle injectors: rejected, never silently ignored."""
     with pytest.raises(namelist.NamelistError):
-        p.check_hot_path()         # moving window / lasers / Silver-Muller are 'next' rows, not silently ignored
+        namelist.load_namelist(os.path.join("/root/reference", path)).check_hot_path()
 
 
 def test_factories_follow_the_reference_surface():

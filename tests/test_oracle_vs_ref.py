@@ -215,3 +215,39 @@ def test_silver_muller(libs, i_boundary, laser):
         assert np.array_equal(A[name], B[name]), name
         changed += int((A[name] != F[name]).sum())
     assert changed > 0
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_moved_window_origin(libs, order):
+    """A patch the moving window has advanced (Patch::initStep3 with n_moved, Patch.cpp:159-163): gather, boundary
+    tags, cell keys and deposit all use the moved origin — exact equality with the reference classes."""
+    orc, ref = libs
+    n, cell, dt = (10, 9, 11), (0.2, 0.3, 0.25), 0.1
+    g = ol.make_grid(n, order, cell, dt, (0, 1, 0), (1, 2, 1), n_moved=24)
+    rng = np.random.default_rng(60 + order)
+    F = ol.random_fields(g, rng)
+    P = ol.random_particles(g, rng, 3000, p_scale=0.5)
+    mn, mx = ol.patch_bounds(g)
+    assert mn[0] == 24 * cell[0] and np.all(P["x"] >= mn[0])
+    a = orc.interp(g, order, F, P["x"], P["y"], P["z"])
+    b = ref.interp(g, order, F, P["x"], P["y"], P["z"])
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    E, B, iold, delta = a
+    Pa = {k: v.copy() for k, v in P.items()}
+    Pb = {k: v.copy() for k, v in P.items()}
+    orc.push(g, 0, 1.0, Pa["x"], Pa["y"], Pa["z"], Pa["px"], Pa["py"], Pa["pz"], Pa["q"], E, B)
+    ref.push(g, 0, 1.0, Pb["x"], Pb["y"], Pb["z"], Pb["px"], Pb["py"], Pb["pz"], Pb["q"], E, B)
+    ta = orc.bc_tag(g, Pa["x"], Pa["y"], Pa["z"])
+    tb = ref.bc_tag(g, Pb["x"], Pb["y"], Pb["z"])
+    assert np.array_equal(ta, tb) and (ta < 0).sum() > 0
+    ka, kb = ta.copy(), tb.copy()
+    orc.cell_keys(g, Pa["x"], Pa["y"], Pa["z"], keys=ka)
+    ref.cell_keys(g, Pb["x"], Pb["y"], Pb["z"], keys=kb)
+    assert np.array_equal(ka, kb)
+    Ja = {k: F[k].copy() for k in ("Jx", "Jy", "Jz")}
+    Jb = {k: F[k].copy() for k in ("Jx", "Jy", "Jz")}
+    orc.project(g, order, Ja, Pa["x"], Pa["y"], Pa["z"], Pa["q"], Pa["w"], iold, delta)
+    ref.project(g, order, Jb, Pb["x"], Pb["y"], Pb["z"], Pb["q"], Pb["w"], iold, delta)
+    for k in Ja:
+        assert np.array_equal(Ja[k], Jb[k]), k
