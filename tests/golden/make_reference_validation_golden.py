@@ -2,9 +2,9 @@
 
     python tests/golden/make_reference_validation_golden.py      (needs /root/reference)
 
-validation/references/tst3d_s_o2_laser_wake_yee_vay.py.txt is the pickle Smilei's validation script compares
-against (validation/analyses/validate_tst3d_s_o2_laser_wake_yee_vay.py): Ey on the central axis, every 4th of
-the 512 probe points, at timesteps 300 and 1000, absolute tolerance 0.01.
+validation/references/tst3d_*_laser_wake_*.py.txt are the pickles Smilei's validation scripts compare against
+(validation/analyses/validate_tst3d_s_o2_laser_wake_yee_vay.py and siblings): Ey on the central axis, every 4th
+of the 512 probe points, at timesteps 300 and 1000, absolute tolerance 0.01.
 """
 import os
 import pickle
@@ -12,13 +12,18 @@ import pickle
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = "/root/reference/validation/references/tst3d_s_o2_laser_wake_yee_vay.py.txt"
+REFS = "/root/reference/validation/references/"
+# the four laser-wake benchmarks share the analysis (validate_tst3d_*_laser_wake_*.py): vay / higueracary with
+# oblique absorption vectors, boris (vectorised build, default vectors), boris at interpolation order 4
+CASES = {"vay": "tst3d_s_o2_laser_wake_yee_vay", "higueracary": "tst3d_s_o2_laser_wake_yee_higuera",
+         "boris": "tst3d_v_o2_laser_wake_yee_boris", "boris_o4": "tst3d_v_o4_laser_wake_boris"}
 
 if __name__ == "__main__":
-    with open(SRC, "rb") as f:
-        d = pickle.load(f, encoding="latin1")
-    out = {"Ey_axis_300": np.asarray(d["Field Ey on central axis timestep 300"], dtype=np.float64),
-           "Ey_axis_1000": np.asarray(d["Field Ey on central axis timestep 1000"], dtype=np.float64),
-           "tolerance": np.float64(0.01)}
-    np.savez_compressed(os.path.join(HERE, "ref_validation_laser_wake_vay.npz"), **out)
-    print({k: (v.shape, float(np.max(np.abs(v)))) for k, v in out.items()})
+    out = {"tolerance": np.float64(0.01)}
+    for tag, name in CASES.items():
+        with open(REFS + name + ".py.txt", "rb") as f:
+            d = pickle.load(f, encoding="latin1")
+        out[tag + "_300"] = np.asarray(d["Field Ey on central axis timestep 300"], dtype=np.float64)
+        out[tag + "_1000"] = np.asarray(d["Field Ey on central axis timestep 1000"], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "ref_validation_laser_wake.npz"), **out)
+    print({k: (np.shape(v), float(np.max(np.abs(v)))) for k, v in out.items()})

@@ -237,49 +237,58 @@ def test_moving_window_matches_oracle():
         assert np.allclose(pa[k][ia], pb[k][ib], rtol=0, atol=1e-9), k
 
 
-# The reference's benchmarks/tst3d_s_o2_laser_wake_yee_vay.py restated (same box, plasma, laser, window; its
-# hand-written space_time_profile is the Gaussian beam LaserGaussian3D builds, as that namelist itself notes).
+# The reference's benchmarks/tst3d_{s_o2_laser_wake_yee_vay, s_o2_laser_wake_yee_higuera, v_o2_laser_wake_yee_boris,
+# v_o4_laser_wake_boris}.py restated (same box, plasma, laser, window; their hand-written space_time_profile is the
+# Gaussian beam LaserGaussian3D builds, as those namelists themselves note).
 LASER_WAKE_NAMELIST = """
 dx, dtrans, dt, nx, ntrans = 0.2, 3., 0.19, 512, 40
-Main(geometry="3Dcartesian", interpolation_order=2, timestep=dt, simulation_time=int(2*nx*dx/dt)*dt,
+Main(geometry="3Dcartesian", interpolation_order={order}, timestep=dt, simulation_time=int(2*nx*dx/dt)*dt,
      cell_length=[dx, dtrans, dtrans], grid_length=[nx*dx, ntrans*dtrans, ntrans*dtrans],
-     number_of_patches=[64, 4, 4], EM_boundary_conditions=[["silver-muller"]],
-     EM_boundary_conditions_k=[[1., 0., 0.], [-1., 0., 0.], [1., 0.005, 0.], [1., -0.005, 0.], [1., 0., 0.005], [1., 0., -0.005]],
-     solve_poisson=False)
+     number_of_patches=[{npatch_x}, 4, 4], EM_boundary_conditions=[["silver-muller"]],
+     EM_boundary_conditions_k={kvec}, solve_poisson=False)
 MovingWindow(time_start=Main.grid_length[0], velocity_x=0.9997)
 Species(name="electron", position_initialization="regular", momentum_initialization="cold", particles_per_cell=1,
-        mass=1.0, charge=-1.0, charge_density=0.000494, pusher="vay", boundary_conditions=[["remove", "remove"]]*3)
+        mass=1.0, charge=-1.0, charge_density=0.000494, pusher="{pusher}", boundary_conditions=[["remove", "remove"]]*3)
 LaserGaussian3D(box_side="xmin", a0=2., focus=[0., Main.grid_length[1]/2., Main.grid_length[2]/2.], waist=10.,
                 time_envelope=tgaussian(center=2**0.5*19.80, fwhm=19.80))
 """
+_OBLIQUE_K = "[[1., 0., 0.], [-1., 0., 0.], [1., 0.005, 0.], [1., -0.005, 0.], [1., 0., 0.005], [1., 0., -0.005]]"
+LASER_WAKE_CASES = {   # tag -> (pusher, order, patches along x = window stride 512/npatch_x, absorption vectors)
+    "vay": ("vay", 2, 64, _OBLIQUE_K), "higueracary": ("higueracary", 2, 64, _OBLIQUE_K),
+    "boris": ("boris", 2, 64, "[]"), "boris_o4": ("boris", 4, 32, "[]"),
+}
 
 
 def _probe_Ey_axis(sim, orc):
-    """DiagProbe of the reference namelist: 512 points from (0, Ly/2, Lz/2) to (Lx, Ly/2, Lz/2), moving with the
+    """DiagProbe of the reference namelists: 512 points from (0, Ly/2, Lz/2) to (Lx, Ly/2, Lz/2), moving with the
     window; the fields are interpolated like particles (DiagnosticProbes.cpp).  Test-side diagnostic."""
     p = sim.params
-    g = ol.make_grid(tuple(sim.n), 2, tuple(p.cell_length), p.timestep, n_moved=sim.simWindow.n_moved)
+    order = p.interpolation_order
+    g = ol.make_grid(tuple(sim.n), order, tuple(p.cell_length), p.timestep, n_moved=sim.simWindow.n_moved)
     L = p.grid_length
     x = np.linspace(0., L[0], 512) + sim.simWindow.n_moved * p.cell_length[0]
     x = np.ascontiguousarray(np.minimum(x, np.nextafter(x[-1], 0.)))
     y = np.full(512, L[1] / 2.)
     z = np.full(512, L[2] / 2.)
     F = {k: sim.patch.field_get(k) for k in ("Ex", "Ey", "Ez", "Bxm", "Bym", "Bzm")}
-    E, B, _, _ = orc.interp(g, 2, F, x, y, z)
+    E, B, _, _ = orc.interp(g, order, F, x, y, z)
     return E[512:1024][::4]
 
 
-def test_reference_validation_laser_wake_vay():
-    """The reference's own regression data for BASELINE.json configs[3] (validation/references/
-    tst3d_s_o2_laser_wake_yee_vay.py.txt, committed as tests/golden/ref_validation_laser_wake_vay.npz): Ey on the
-    central axis at timesteps 300 (laser in a fixed box) and 1000 (after 55 window shifts), within the reference's
-    own tolerance of 0.01."""
+@pytest.mark.parametrize("case", list(LASER_WAKE_CASES))
+def test_reference_validation_laser_wake(case):
+    """The reference's OWN regression data for BASELINE.json configs[3] and its siblings (validation/references/
+    tst3d_*_laser_wake_*.py.txt, committed as tests/golden/ref_validation_laser_wake.npz): Ey on the central axis
+    at timesteps 300 (laser in a fixed box) and 1000 (after the window has slid 440 cells), within the
+    reference's own tolerance of 0.01 — three pushers, both interpolation orders."""
     import os
     from smilei_b200 import namelist
     from smilei_b200.simulation import Simulation
-    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_validation_laser_wake_vay.npz"))
+    pusher, order, npatch_x, kvec = LASER_WAKE_CASES[case]
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_validation_laser_wake.npz"))
     orc = ol.Oracle()
-    params = namelist.load_namelist(LASER_WAKE_NAMELIST, is_source=True)
+    params = namelist.load_namelist(LASER_WAKE_NAMELIST.format(pusher=pusher, order=order, npatch_x=npatch_x, kvec=kvec),
+                                    is_source=True)
     assert params.n_time == 1077 and params.global_size == [512, 40, 40]
     sim = Simulation(params)
     sim.create_particles()
@@ -290,10 +299,10 @@ def test_reference_validation_laser_wake_vay():
         got[target] = _probe_Ey_axis(sim, orc)
     n_moved = sim.simWindow.n_moved
     sim.close()
-    assert n_moved == 8 * 55
+    assert n_moved in (440, 448)            # stride 8 (55 shifts) or 16 (28 shifts)
     tol = float(gold["tolerance"])
     for target in (300, 1000):
-        ref = gold["Ey_axis_%d" % target]
+        ref = gold["%s_%d" % (case, target)]
         err = np.max(np.abs(got[target] - ref))
-        print("timestep", target, "max |Ey - reference| =", err, "max |reference| =", np.max(np.abs(ref)))
-        assert err <= tol, (target, err)
+        print(case, "timestep", target, "max |Ey - reference| =", err, "max |reference| =", np.max(np.abs(ref)))
+        assert err <= tol, (case, target, err)
