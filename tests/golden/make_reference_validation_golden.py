@@ -27,3 +27,13 @@ if __name__ == "__main__":
         out[tag + "_1000"] = np.asarray(d["Field Ey on central axis timestep 1000"], dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "ref_validation_laser_wake.npz"), **out)
     print({k: (np.shape(v), float(np.max(np.abs(v)))) for k, v in out.items()})
+    # tst3d_00_em_propagation: a Gaussian beam at oblique incidence through Silver-Mueller sides, no plasma;
+    # validate_tst3d_00_em_propagation.py checks probes of Ey with tolerance 0.01
+    with open(REFS + "tst3d_00_em_propagation.py.txt", "rb") as f:
+        d = pickle.load(f, encoding="latin1")
+    em = {"probe0_Ey_vs_time": np.asarray(d["0-D probe Ey vs time"], dtype=np.float64),
+          "probe1_Ey": np.asarray(d["1-D probe Ey at last iteration"], dtype=np.float64),
+          "probe2_Ey": np.asarray(d["2-D probe Ey at last iteration"], dtype=np.float64),
+          "tolerance": np.float64(0.01)}
+    np.savez_compressed(os.path.join(HERE, "ref_validation_em_propagation.npz"), **em)
+    print({k: (np.shape(v), float(np.max(np.abs(v)))) for k, v in em.items()})

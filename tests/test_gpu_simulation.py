@@ -306,3 +306,66 @@ def test_reference_validation_laser_wake(case):
         err = np.max(np.abs(got[target] - ref))
         print(case, "timestep", target, "max |Ey - reference| =", err, "max |reference| =", np.max(np.abs(ref)))
         assert err <= tol, (case, target, err)
+
+
+# The reference's benchmarks/tst3d_00_em_propagation.py restated: a Gaussian beam at oblique incidence entering
+# through xmin, Silver-Mueller sides with oblique absorption vectors, no plasma.
+EM_PROPAGATION_NAMELIST = """
+from math import pi, cos, sin
+l0 = 2.0*pi
+Lsim = [7.*l0, 10.*l0, 20.*l0]
+angle1, angle2 = 0.2*pi, 0.07*pi
+Main(geometry="3Dcartesian", interpolation_order=2, cell_length=[l0/16.]*3, grid_length=Lsim,
+     number_of_patches=[4, 4, 4], timestep=l0/30., simulation_time=12.*l0,
+     EM_boundary_conditions=[['silver-muller']],
+     EM_boundary_conditions_k=[[cos(angle1)*cos(angle2), sin(angle2), -sin(angle1)*cos(angle2)],
+                               [-cos(angle1)*cos(angle2), -sin(angle2), sin(angle1)*cos(angle2)],
+                               [0., 1., 0.], [0., -1., 0.], [0., 0., 1.], [0., 0., -1.]])
+LaserGaussian3D(a0=1., omega=1., focus=[0.5*Lsim[0], 0.6*Lsim[1], 0.3*Lsim[2]], waist=2*l0,
+                incidence_angle=[angle1, angle2])
+"""
+
+
+def _probe(sim, orc, pts, comp=1):
+    p = sim.params
+    g = ol.make_grid(tuple(sim.n), p.interpolation_order, tuple(p.cell_length), p.timestep)
+    x, y, z = (np.ascontiguousarray(pts[:, i]) for i in range(3))
+    F = {k: sim.patch.field_get(k) for k in ("Ex", "Ey", "Ez", "Bxm", "Bym", "Bzm")}
+    E, _, _, _ = orc.interp(g, p.interpolation_order, F, x, y, z)
+    n = len(x)
+    return E[comp * n:(comp + 1) * n]
+
+
+def test_reference_validation_em_propagation():
+    """The reference's OWN regression data for benchmarks/tst3d_00_em_propagation.py (oblique Gaussian beam
+    through Silver-Mueller sides in vacuum): Ey at a point every 10 steps over the whole run, on a line and on a
+    plane at timestep 200 (the probe output closest to the `timesteps=240` the analysis asks for), tolerance 0.01."""
+    import os
+    from smilei_b200 import namelist
+    from smilei_b200.simulation import Simulation
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_validation_em_propagation.npz"))
+    orc = ol.Oracle()
+    params = namelist.load_namelist(EM_PROPAGATION_NAMELIST, is_source=True)
+    assert params.global_size == [112, 160, 320] and params.n_time == 360
+    L = params.grid_length
+    sim = Simulation(params)
+    p0 = np.array([[0.1 * L[0], 0.5 * L[1], 0.5 * L[2]]])
+    line = np.stack([np.linspace(0.1 * L[0], 0.9 * L[0], 30), np.full(30, 0.5 * L[1]), np.full(30, 0.5 * L[2])], axis=1)
+    u, v = np.meshgrid(np.linspace(0., 1., 10), np.linspace(0., 1., 10), indexing="ij")
+    plane = np.stack([(0.1 + 0.8 * u).ravel() * L[0], (0.9 * v).ravel() * L[1], np.full(100, 0.5 * L[2])], axis=1)
+    series = [float(_probe(sim, orc, p0)[0])]
+    got_line = got_plane = None
+    for it in range(10, 361, 10):
+        sim.run(10)
+        series.append(float(_probe(sim, orc, p0)[0]))
+        if it == 200:
+            got_line = _probe(sim, orc, line)
+            got_plane = _probe(sim, orc, plane).reshape(10, 10)
+    sim.close()
+    tol = float(gold["tolerance"])
+    e0 = np.max(np.abs(np.array(series) - gold["probe0_Ey_vs_time"]))
+    e1 = np.max(np.abs(got_line - gold["probe1_Ey"]))
+    e2 = np.max(np.abs(got_plane - gold["probe2_Ey"]))
+    print("em_propagation: 0-D probe", e0, " 1-D probe", e1, " 2-D probe", e2,
+          " max |reference| =", np.max(np.abs(gold["probe0_Ey_vs_time"])), np.max(np.abs(gold["probe1_Ey"])))
+    assert e0 <= tol and e1 <= tol and e2 <= tol
