@@ -109,6 +109,7 @@ struct DynArgs {
     double  one_over_mass;
     double  jscale, jinv;     // fixed-point scale of the J box and its inverse
     int     tiles[3];
+    int     any_remove;       // some entry of bc_remove is set
     int     bc_remove[6];     // 1: `remove` particle BC on this side (xmin xmax ymin ymax zmin zmax) AND the patch touches that global edge
     double *lost;             // accumulates w*(gamma-1) of the removed particles
 };
@@ -130,6 +131,18 @@ __device__ __forceinline__ int boundary_tag( const DynArgs &a, const GridDev &g,
                                              double weight, size_t ip, bool &removed )
 {
     int tag = 0, nrem = 0;
+    removed = false;
+    if( !a.any_remove ) {
+        // all sides exchange (periodic box or inner patch): the first side the particle is beyond wins
+#pragma unroll
+        for( int d=0; d<3; d++ ) {
+            if( tag == 0 ) {
+                if( npos[d] < g.xmin[d] ) tag = -2 - 2*d;
+                else if( npos[d] >= g.xmax[d] ) tag = -3 - 2*d;
+            }
+        }
+        return tag;
+    }
 #pragma unroll
     for( int d=0; d<3; d++ ) {
         if( a.bc_remove[2*d] ) { if( npos[d] < g.xmin[d] ) { tag = -1; nrem++; } }
@@ -1528,6 +1541,8 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
         a.bc_remove[2*d]   = s.bc[2*d]   == SB200_PBC_REMOVE && p->gd.pcoord[d] == 0;
         a.bc_remove[2*d+1] = s.bc[2*d+1] == SB200_PBC_REMOVE && p->gd.pcoord[d] == p->gd.npatch[d]-1;
     }
+    a.any_remove = 0;
+    for( int i=0; i<6; i++ ) a.any_remove |= a.bc_remove[i];
     a.lost = s.d_lost;
     a.one_over_mass = 1.0/s.mass;                      // Pusher.cpp:20
     {
