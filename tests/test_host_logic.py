@@ -315,3 +315,74 @@ def test_open_box_two_ranks_gloo_match_single_rank(rank_grid):
     assert 0 < len(a["x"]) == len(b["x"]) < 3000
     for k in a:
         assert np.allclose(a[k], b[k], rtol=0, atol=1e-10), k
+
+
+# ---------------------------------------------------------------------------------------------------------
+# moving window with the box split across ranks along y (one rank along x spans the window direction)
+# ---------------------------------------------------------------------------------------------------------
+WINDOW_NAMELIST = """
+Main(geometry="3Dcartesian", interpolation_order=2, timestep=0.09, number_of_timesteps=70,
+     cell_length=[0.1, 0.5, 0.5], number_of_cells=[48, 8, 8], number_of_patches=[12, 1, 1],
+     EM_boundary_conditions=[["silver-muller"]])
+MovingWindow(time_start=2.5, velocity_x=0.9997)
+LaserGaussian3D(box_side="xmin", a0=1.0, omega=2.0, focus=[0., 2.0, 2.0], waist=1.5,
+                time_envelope=tgaussian(start=0., duration=2.4, fwhm=0.8, center=1.2))
+Species(name="electron", position_initialization="regular", momentum_initialization="cold",
+        particles_per_cell=1, mass=1.0, charge=-1.0, charge_density=0.01, pusher="vay",
+        boundary_conditions=[["remove"]])
+"""
+
+
+def _run_rank_window(rank, world, rank_grid, steps, port, ret):
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p = namelist.load_namelist(WINDOW_NAMELIST, is_source=True)
+    sim = Simulation(p, rank_grid=rank_grid, rank=rank, patch_factory=OraclePatch)
+    sim.create_particles()
+    hist = sim.run(steps, scalars_every=1)
+    parts = [sim.patch.species_get(0)]
+    info = (parts, sim.patch.species_lost_energy(0), sim.simWindow.n_moved)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, info)
+        dist.barrier()
+        dist.destroy_process_group()
+    else:
+        gathered = [info]
+    if rank == 0:
+        ret["hist"] = [(h[0], h[1].tolist(), h[2]) for h in hist]
+        ret["parts"] = [g[0] for g in gathered]
+        ret["lost"] = sum(g[1] for g in gathered)
+        ret["n_moved"] = [g[2] for g in gathered]
+
+
+def _launch_window(rank_grid, steps):
+    world = int(np.prod(rank_grid))
+    if world == 1:
+        ret = {}
+        _run_rank_window(0, 1, rank_grid, steps, 0, ret)
+        return ret
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_run_rank_window, args=(world, rank_grid, steps, _free_port(), ret), nprocs=world, join=True)
+    return dict(ret)
+
+
+def test_moving_window_two_ranks_gloo_match_single_rank():
+    """Laser + cold plasma + moving window with the box split in two along y: every rank slides its patch by the
+    same stride at the same steps, creates the particles of its share of the uncovered cells, and the run
+    reproduces the single-rank one."""
+    one = _launch_window((1, 1, 1), 70)
+    two = _launch_window((1, 2, 1), 70)
+    assert one["n_moved"][0] >= 10 * 4 and two["n_moved"] == [one["n_moved"][0]] * 2
+    for (it_a, uk_a, ue_a), (it_b, uk_b, ue_b) in zip(one["hist"], two["hist"]):
+        assert it_a == it_b
+        assert np.allclose(uk_a, uk_b, rtol=1e-9, atol=1e-30)
+        assert abs(ue_a - ue_b) <= 1e-9 * abs(ue_a)
+    cols_a = {k: np.concatenate([r[0][k] for r in one["parts"]]) for k in ("x", "y", "z", "px", "py", "pz", "w")}
+    cols_b = {k: np.concatenate([r[0][k] for r in two["parts"]]) for k in ("x", "y", "z", "px", "py", "pz", "w")}
+    ia = np.lexsort((cols_a["z"], cols_a["y"], cols_a["x"]))
+    ib = np.lexsort((cols_b["z"], cols_b["y"], cols_b["x"]))
+    assert len(ia) == len(ib) > 0
+    for k in cols_a:
+        assert np.allclose(cols_a[k][ia], cols_b[k][ib], rtol=0, atol=1e-9), k
