@@ -602,7 +602,7 @@ template<> struct CG<2> {
 template<> struct CG<4> {
     using T = Tile<4, 4, 4, 8>;
     static constexpr int NSL = 1;
-    static constexpr int MINB = 1;
+    static constexpr int MINB = 2;
     static constexpr int LOG2CELLS = 7;
 };
 template<int ORDER> struct CGDim {
@@ -698,7 +698,10 @@ __device__ __forceinline__ void cross_pass( jbox_t *sJ, const double *xq, const 
                 Cx[f] = rx; Cy[f] = ry; Cz[f] = rz;
             }
         }
-#pragma unroll
+        // NOT unrolled: the body holds 3*NW inlined fixed-point adds; unrolled (5 copies at order 4) the kernel no
+        // longer fits the instruction cache and two thirds of the stall samples of an electron launch were
+        // instruction fetches
+#pragma unroll 1
         for( int h=0; h<( WX*WX + GRP - 1 )/GRP; h++ ) {
             const int pp = gl + GRP*h;
             if( pp < WX*WX ) {
