@@ -731,6 +731,8 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
     using D = CGDim<ORDER>;
     using T = typename D::T;
     constexpr int NW = D::NW, NCELL = D::NCELL, CPT = D::CPT, NV = D::NV, NS = D::NS, NSL = D::NSL, NPASS = D::NPASS;
+    constexpr bool COMPACT = ORDER == 4;      // loops over components / flux passes kept rolled: code size (see the deposit)
+    static_assert( !COMPACT || NSL == 1, "the compact deposit advances one flux point per pass" );
     extern __shared__ __align__( 128 ) double smem[];
     double *sF = smem;
     jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FBOX );
@@ -879,12 +881,33 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
                 sp[d] = cl[d] + T::H + ( d == 2 ? zs : 0 );
                 sd[d] = sp[d] + ( idn - ipn );
             }
-            const double Ex = gather<T>( sF+0*T::FBOX, cd[0], S0[1], S0[2], sd[0], sp[1], sp[2] );
-            const double Ey = gather<T>( sF+1*T::FBOX, S0[0], cd[1], S0[2], sp[0], sd[1], sp[2] );
-            const double Ez = gather<T>( sF+2*T::FBOX, S0[0], S0[1], cd[2], sp[0], sp[1], sd[2] );
-            const double Bx = gather<T>( sF+3*T::FBOX, S0[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
-            const double By = gather<T>( sF+4*T::FBOX, cd[0], S0[1], cd[2], sd[0], sp[1], sd[2] );
-            const double Bz = gather<T>( sF+5*T::FBOX, cd[0], cd[1], S0[2], sd[0], sd[1], sp[2] );
+            double Ex, Ey, Ez, Bx, By, Bz;
+            if( COMPACT ) {
+                // one loop over the six components instead of six inlined gathers (750 FMA + 750 loads at order 4):
+                // the weights of a component are picked per dimension (dual along its own direction for E, along
+                // the two others for B), ElectroMagn3D.cpp:115-123
+                double EB[6];
+#pragma unroll 1
+                for( int c=0; c<6; c++ ) {
+                    const bool ux = c < 3 ? c == 0 : c != 3, uy = c < 3 ? c == 1 : c != 4, uz = c < 3 ? c == 2 : c != 5;
+                    double wx[NW], wy[NW], wz[NW];
+#pragma unroll
+                    for( int s=0; s<NW; s++ ) {
+                        wx[s] = ux ? cd[0][s] : S0[0][s];
+                        wy[s] = uy ? cd[1][s] : S0[1][s];
+                        wz[s] = uz ? cd[2][s] : S0[2][s];
+                    }
+                    EB[c] = gather<T>( sF + c*T::FBOX, wx, wy, wz, ux ? sd[0] : sp[0], uy ? sd[1] : sp[1], uz ? sd[2] : sp[2] );
+                }
+                Ex = EB[0]; Ey = EB[1]; Ez = EB[2]; Bx = EB[3]; By = EB[4]; Bz = EB[5];
+            } else {
+                Ex = gather<T>( sF+0*T::FBOX, cd[0], S0[1], S0[2], sd[0], sp[1], sp[2] );
+                Ey = gather<T>( sF+1*T::FBOX, S0[0], cd[1], S0[2], sp[0], sd[1], sp[2] );
+                Ez = gather<T>( sF+2*T::FBOX, S0[0], S0[1], cd[2], sp[0], sp[1], sd[2] );
+                Bx = gather<T>( sF+3*T::FBOX, S0[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+                By = gather<T>( sF+4*T::FBOX, cd[0], S0[1], cd[2], sd[0], sp[1], sd[2] );
+                Bz = gather<T>( sF+5*T::FBOX, cd[0], cd[1], S0[2], sd[0], sd[1], sp[2] );
+            }
 
             const double cmd = ( double )charge*a.one_over_mass*g.dts2;
             double dxp, dyp, dzp, invgf;
@@ -943,6 +966,52 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
         const bool owner = own8 && !( same16 && ( lane & 16 ) );
         // ---- non-crossing particles: (NW-1) x NW x NW values per component, NV at a time, summed over the 8
         //      lanes of the cell group in registers (all 32 lanes take part in the shuffles)
+        if( COMPACT ) {
+            // the same arithmetic with the component loop and the flux-pass loop NOT unrolled (the unrolled body
+            // is 12 copies of ~330 instructions at order 4: the kernel did not fit the instruction cache)
+#pragma unroll 1
+            for( int c=0; c<3; c++ ) {
+                const double third = 1./3.;
+                double Sa[NW], Da[NW], A[NW], B[NW], Dc[NW-1];
+#pragma unroll
+                for( int k=0; k<NW; k++ ) {
+                    Sa[k] = c == 0 ? S0[1][k] : S0[0][k];                  // slow transverse dimension: y for Jx, x otherwise
+                    Da[k] = c == 0 ? DS[1][k] : DS[0][k];
+                    const double sb = c == 2 ? S0[1][k] : S0[2][k];       // fast transverse dimension: y for Jz, z otherwise
+                    const double db_ = c == 2 ? DS[1][k] : DS[2][k];
+                    A[k] = sb + 0.5*db_; B[k] = 0.5*sb + third*db_;
+                }
+#pragma unroll
+                for( int f=0; f<NW-1; f++ ) Dc[f] = c == 0 ? DS[0][f] : ( c == 1 ? DS[1][f] : DS[2][f] );
+                const double crc = c == 0 ? cr[0] : ( c == 1 ? cr[1] : cr[2] );
+                const int fs = c == 0 ? fstride[0] : ( c == 1 ? fstride[1] : fstride[2] );
+                int jo[NS];
+#pragma unroll
+                for( int r=0; r<NS; r++ ) jo[r] = c == 0 ? joff[0][r] : ( c == 1 ? joff[1][r] : joff[2][r] );
+                double run = 0.;
+#pragma unroll 1
+                for( int ps=0; ps<NPASS; ps++ ) {
+                    run -= crc*Dc[0];                                      // flux coefficient of this pass (NSL == 1)
+#pragma unroll
+                    for( int f=0; f<NW-2; f++ ) Dc[f] = Dc[f+1];
+                    double v[NV];
+#pragma unroll
+                    for( int j=0; j<NW; j++ )
+#pragma unroll
+                        for( int k=0; k<NW; k++ )
+                            v[j*NW + k] = fast ? run*( Sa[j]*A[k] + Da[j]*B[k] ) : 0.;
+                    xr_step<NV>( v, 4, up4 ); xr_step<D::N1>( v, 2, up2 ); xr_step<D::N2>( v, 1, up1 );
+#pragma unroll
+                    for( int r=0; r<NS; r++ ) {
+                        const double o8 = __shfl_xor_sync( 0xffffffffu, v[r], 8 );
+                        if( same8 ) v[r] += o8;
+                        const double o16 = __shfl_xor_sync( 0xffffffffu, v[r], 16 );
+                        if( same16 ) v[r] += o16;
+                        if( owner && jo[r] >= 0 && v[r] != 0. ) jadd( jb + jo[r] + ps*fs, v[r], a.jscale );
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for( int c=0; c<3; c++ ) {
             const int da = c == 0 ? 1 : 0, db = c == 2 ? 1 : 2;      // transverse dimensions (slow, fast)
@@ -980,6 +1049,7 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
                     if( owner && joff[c][r] >= 0 && v[r] != 0. ) jadd( jb + joff[c][r] + ps*fstride[c], v[r], a.jscale );
                 }
             }
+        }
         }
         // ---- particles that changed cell (Projector3D2Order.cpp:124-340 with ip_m_ipo != 0) go to the warp's
         //      queue; whenever 4 are pending the warp deposits them, one per lane group (cross_pass)
