@@ -203,7 +203,7 @@ __device__ __forceinline__ void push( double cmd, double dt, double &px, double 
         local_invgf *= dt;
         dxp = pxsm*local_invgf; dyp = pysm*local_invgf; dzp = pzsm*local_invgf;
     } else if( PUSHER == SB200_PUSHER_VAY ) {
-        double invgf = 1./sqrt( 1.0 + px*px + py*py + pz*pz );
+        double invgf = rsqrt( 1.0 + px*px + py*py + pz*pz );      // rsqrt / reciprocal as in the Boris branch
         double upx = px + 2.*cmd*Ex, upy = py + 2.*cmd*Ey, upz = pz + 2.*cmd*Ez;
         double Tx = cmd*Bx, Ty = cmd*By, Tz = cmd*Bz;
         upx += invgf*( py*Tz - pz*Ty );
@@ -214,14 +214,14 @@ __device__ __forceinline__ void push( double cmd, double dt, double &px, double 
         double s = alpha - T2;
         double us2 = upx*Tx + upy*Ty + upz*Tz;
         us2 = us2*us2;
-        alpha = 1.0/sqrt( 0.5*( s + sqrt( s*s + 4.0*( T2 + us2 ) ) ) );
+        alpha = rsqrt( 0.5*( s + sqrt( s*s + 4.0*( T2 + us2 ) ) ) );
         Tx *= alpha; Ty *= alpha; Tz *= alpha;
-        s = 1.0/( 1.0 + Tx*Tx + Ty*Ty + Tz*Tz );
+        s = __drcp_rn( 1.0 + Tx*Tx + Ty*Ty + Tz*Tz );
         alpha = upx*Tx + upy*Ty + upz*Tz;
         const double pxsm = s*( upx + alpha*Tx + Tz*upy - Ty*upz );
         const double pysm = s*( upy + alpha*Ty + Tx*upz - Tz*upx );
         const double pzsm = s*( upz + alpha*Tz + Ty*upx - Tx*upy );
-        invgf = 1.0/sqrt( 1.0 + pxsm*pxsm + pysm*pysm + pzsm*pzsm );
+        invgf = rsqrt( 1.0 + pxsm*pxsm + pysm*pysm + pzsm*pzsm );
         invgf_out = invgf;
         px = pxsm; py = pysm; pz = pzsm;
         dxp = dt*pxsm*invgf; dyp = dt*pysm*invgf; dzp = dt*pzsm*invgf;
@@ -232,15 +232,15 @@ __device__ __forceinline__ void push( double cmd, double dt, double &px, double 
         double Tx = cmd*Bx, Ty = cmd*By, Tz = cmd*Bz;
         const double beta2 = Tx*Tx + Ty*Ty + Tz*Tz;
         const double Tum = Tx*umx + Ty*umy + Tz*umz;
-        const double local_invgf = 1./sqrt( 0.5*( gfm2 - beta2 + sqrt( ( gfm2-beta2 )*( gfm2-beta2 ) + 4.0*( beta2 + Tum*Tum ) ) ) );
+        const double local_invgf = rsqrt( 0.5*( gfm2 - beta2 + sqrt( ( gfm2-beta2 )*( gfm2-beta2 ) + 4.0*( beta2 + Tum*Tum ) ) ) );
         Tx *= local_invgf; Ty *= local_invgf; Tz *= local_invgf;
         const double Tx2 = Tx*Tx, Ty2 = Ty*Ty, Tz2 = Tz*Tz, TxTy = Tx*Ty, TyTz = Ty*Tz, TzTx = Tz*Tx;
-        const double inv_det_T = 1.0/( 1.0 + Tx2 + Ty2 + Tz2 );
+        const double inv_det_T = __drcp_rn( 1.0 + Tx2 + Ty2 + Tz2 );
         const double upx = ( ( 1.0+Tx2-Ty2-Tz2 )*umx + 2.0*( TxTy+Tz )*umy + 2.0*( TzTx-Ty )*umz )*inv_det_T;
         const double upy = ( 2.0*( TxTy-Tz )*umx + ( 1.0-Tx2+Ty2-Tz2 )*umy + 2.0*( TyTz+Tx )*umz )*inv_det_T;
         const double upz = ( 2.0*( TzTx+Ty )*umx + 2.0*( TyTz-Tx )*umy + ( 1.0-Tx2-Ty2+Tz2 )*umz )*inv_det_T;
         pxsm += upx; pysm += upy; pzsm += upz;
-        const double invgf = 1./sqrt( 1.0 + pxsm*pxsm + pysm*pysm + pzsm*pzsm );
+        const double invgf = rsqrt( 1.0 + pxsm*pxsm + pysm*pysm + pzsm*pzsm );
         invgf_out = invgf;
         px = pxsm; py = pysm; pz = pzsm;
         dxp = dt*pxsm*invgf; dyp = dt*pysm*invgf; dzp = dt*pzsm*invgf;
