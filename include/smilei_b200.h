@@ -152,8 +152,12 @@ int  sb200_apply_SM( sb200_patch *p, int i_boundary, const double k[3], const in
  * by `ncells` cells.  E, B, B_m move down by ncells planes and the planes entering on the right are zero (a patch
  * created by the window starts with zero fields, SimWindow.cpp:224); the patch origin advances
  * (Patch::initStep3 with n_moved, src/Patch/Patch.cpp:159-163); particles left behind (x < new xmin) are
- * dropped and every species is marked unsorted.  The caller then appends the particles of the entering cells
- * (sb200_species_append) and sorts.  Only a patch that spans the whole box along x (one rank along x). */
+ * dropped on the patch at the left end of the box and tagged for the -x neighbour elsewhere (then
+ * sb200_leaving_count / sb200_leaving_pack(dim 0, side 0) hand them over); every species is marked unsorted.
+ * With several patches along x the caller packs the planes the -x neighbour needs BEFORE the shift
+ * (sb200_halo_pack, planes [2*oversize+1+dual, +ncells) of E, B, B_m) and unpacks what the +x neighbour sent into
+ * the last ncells real planes AFTER it.  The caller then appends the particles of the cells uncovered at the
+ * right end of the box (sb200_species_append) and sorts. */
 int  sb200_window_shift( sb200_patch *p, int ncells );
 /* HOST -> device append of n particles at the end of a species (ParticleCreator::create on the cells a moving
  * window uncovers, SimWindow.cpp:372-392); the species becomes unsorted. */

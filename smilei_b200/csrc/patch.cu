@@ -327,16 +327,28 @@ int sb200_species_append( sb200_patch *p, int ispec,
     return 0;
 }
 
-__global__ void __launch_bounds__( 256 ) k_window_drop( const double *__restrict__ x, int *__restrict__ key, size_t n, double xmin_new )
+// particles the window leaves behind: dropped on the patch at the left end of the box, tagged for the -x neighbour
+// (and listed, as the dynamics kernel lists its leavers) elsewhere
+__global__ void __launch_bounds__( 256 ) k_window_tag( const double *__restrict__ x, int *__restrict__ key, size_t n, double xmin_new,
+        int tag_left, int *__restrict__ leave_count, int *__restrict__ leave_idx, int leave_cap )
 {
-    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < n; i += ( size_t )gridDim.x*blockDim.x )
-        key[i] = ( key[i] < 0 || x[i] < xmin_new ) ? -1 : 0;
+    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < n; i += ( size_t )gridDim.x*blockDim.x ) {
+        int k = 0;
+        if( key[i] < 0 ) k = -1;
+        else if( x[i] < xmin_new ) {
+            k = tag_left;
+            if( tag_left == -2 ) {
+                const int c = atomicAdd( leave_count, 1 );
+                if( c < leave_cap ) leave_idx[c] = ( int )i;
+            }
+        }
+        key[i] = k;
+    }
 }
 
 int sb200_window_shift( sb200_patch *p, int ncells )
 {
     SB200_CHECK( p && ncells > 0, "sb200_window_shift: bad arguments" );
-    SB200_CHECK( p->gd.npatch[0] == 1, "sb200_window_shift: the patch must span the box along x (one rank along x)" );
     SB200_CHECK( ncells < p->gd.n[0], "sb200_window_shift: shift larger than the patch" );
     SB200_CUDA( cudaSetDevice( p->device ) );
     GridDev &g = p->gd;
@@ -362,9 +374,12 @@ int sb200_window_shift( sb200_patch *p, int ncells )
     for( int is=0; is<p->nspec; is++ ) {
         if( materialize( p, is ) ) return 1;
         SpeciesDev &s = p->sp[is];
+        SB200_CUDA( cudaMemsetAsync( p->leave_counts + 8*is, 0, 8*sizeof( int ), p->stream ) );
         if( s.n > 0 ) {
             const unsigned blocks = ( unsigned )( ( s.n + 255 )/256 < 148*16 ? ( s.n + 255 )/256 : 148*16 );
-            k_window_drop<<<blocks, 256, 0, p->stream>>>( s.col[0], s.key, s.n, g.xmin[0] );
+            const int tag_left = g.pcoord[0] > 0 ? -2 : -1;      // a -x neighbour takes them over, or they leave the box
+            k_window_tag<<<blocks, 256, 0, p->stream>>>( s.col[0], s.key, s.n, g.xmin[0], tag_left, p->leave_counts + 8*is,
+                    s.leave_idx, ( int )s.leave_cap );
             sb200::g_launches++;
             SB200_CUDA( cudaGetLastError() );
         }

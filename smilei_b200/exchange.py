@@ -255,6 +255,85 @@ class Exchanger:
                     p.arriving_unpack(s, from_hi[RECORD * pad_from_hi * s:].data_ptr(), n_from_hi[s])
             self._sync_patch_stream()
 
+    # ------------------------------------------------------------------ moving window across ranks along x
+    WINDOW_FIELDS = ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm")
+    _DUAL_X = {"Ex": 1, "Ey": 0, "Ez": 0, "Bx": 0, "By": 1, "Bz": 1, "Bxm": 0, "Bym": 1, "Bzm": 1}
+
+    def _send_left_recv_right(self, send, recv):
+        """One-directional hand-over along x: my block goes to the -x neighbour, the +x neighbour's comes to me."""
+        lo, hi = self.nbr[0]
+        p2p = []
+        if lo is not None and send is not None:
+            p2p.append(dist.P2POp(dist.isend, send, lo, self.group))
+            self.bytes_sent += send.numel() * send.element_size()
+        if hi is not None and recv is not None:
+            p2p.append(dist.P2POp(dist.irecv, recv, hi, self.group))
+        if p2p:
+            for w in dist.batch_isend_irecv(p2p):
+                w.wait()
+
+    def window_fields_begin(self, stride):
+        """Before the shift: the planes the -x neighbour will uncover at its right end are my (old) planes
+        [2*oversize+1+dual, +stride) of E, B, B_m; returns what the +x neighbour sent (or None at the right end)."""
+        if self.npatch[0] == 1:
+            return None
+        p = self.patch
+        lo, hi = self.nbr[0]
+        sizes = [stride * p.halo_plane_elems(f, 0) for f in self.WINDOW_FIELDS]
+        tot = sum(sizes)
+        send = recv = None
+        if lo is not None:
+            send = self._buf(("wl", 0), tot)[:tot]
+            off = 0
+            for f, s in zip(self.WINDOW_FIELDS, sizes):
+                p.halo_pack(f, 0, 2 * self.o[0] + 1 + self._DUAL_X[f], stride, send[off:off + s].data_ptr())
+                off += s
+            self._sync_patch_stream()
+        if hi is not None:
+            recv = self._buf(("wr", 0), tot)[:tot]
+        self._send_left_recv_right(send, recv)
+        return recv
+
+    def window_fields_end(self, stride, recv):
+        """After the shift: the +x neighbour's planes become my last `stride` real planes."""
+        if recv is None:
+            return
+        p = self.patch
+        off = 0
+        for f in self.WINDOW_FIELDS:
+            s = stride * p.halo_plane_elems(f, 0)
+            nreal = self.n[0] + 2 * self.o[0] + 1 + self._DUAL_X[f]
+            p.halo_unpack(f, 0, nreal - stride, stride, recv[off:off + s].data_ptr(), UNPACK_COPY)
+            off += s
+        self._sync_patch_stream()
+
+    def exchange_window_particles(self, n_species):
+        """Particles the shift left behind on a patch with a -x neighbour (tag -2) move to that neighbour."""
+        if self.npatch[0] == 1:
+            return
+        p = self.patch
+        lo, hi = self.nbr[0]
+        counts = [p.leaving_count(s)[0] for s in range(n_species)]
+        cnt = torch.tensor([float(v) for v in counts], dtype=torch.float64, device=self.device)
+        rcnt = torch.zeros(n_species, dtype=torch.float64, device=self.device)
+        self._send_left_recv_right(cnt if lo is not None else None, rcnt if hi is not None else None)
+        n_from = [int(v) for v in rcnt.cpu().tolist()] if hi is not None else [0] * n_species
+        pad_to, pad_from = max(max(counts), 1), max(max(n_from), 1)
+        send = recv = None
+        if lo is not None:
+            send = self._buf(("pwl", 0), RECORD * pad_to * n_species)[:RECORD * pad_to * n_species]
+            for s in range(n_species):
+                got = p.leaving_pack(s, 0, 0, 0., send[RECORD * pad_to * s:].data_ptr(), pad_to)
+                assert got == counts[s]
+            self._sync_patch_stream()
+        if hi is not None:
+            recv = self._buf(("pwr", 0), RECORD * pad_from * n_species)[:RECORD * pad_from * n_species]
+        self._send_left_recv_right(send, recv)
+        if hi is not None:
+            for s in range(n_species):
+                p.arriving_unpack(s, recv[RECORD * pad_from * s:].data_ptr(), n_from[s])
+            self._sync_patch_stream()
+
     def _ensure_pcap(self, need):
         if need > self._pcap:
             self._pcap = int(need * 1.5) + 16

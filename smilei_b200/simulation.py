@@ -148,8 +148,6 @@ class Simulation:
                 L.init_fields(self.n, params.oversize, params.cell_length, min_local)
                 self.lasers.append(L)
         self.simWindow = SimWindow(params)
-        if self.simWindow.active and self.rank_grid[0] != 1:
-            raise ValueError("MovingWindow: one rank along x (the patch must span the box along x)")
         self.itime = 0
 
     # ------------------------------------------------------------------ initial state
@@ -244,19 +242,25 @@ class Simulation:
         S = w.n_space_x_
         w.n_moved += S                                                               # :136
         self.lasers = []                                                             # laserDisabled, :144
+        # with several ranks along x every patch hands its leftmost interior planes and the particles it leaves
+        # behind to its -x neighbour (the reference sends whole patches to the left, :166-222)
+        incoming = self.exchanger.window_fields_begin(S)
         self.patch.window_shift(S)
-        # particles of the cells uncovered on the right (ParticleCreator over the new patch, :372-392)
-        first_new = self.params.global_size[0] + w.n_moved - S
-        box = (S, self.n[1], self.n[2])
-        origin = (first_new, self.pcoord[1] * self.n[1], self.pcoord[2] * self.n[2])
+        self.exchanger.window_fields_end(S, incoming)
+        self.exchanger.exchange_window_particles(len(self.vecSpecies))
+        # particles of the cells uncovered at the right end of the box (ParticleCreator over the new patch, :372-392)
         created = {}
         for sp in self.vecSpecies:
-            src = created.get(sp.sparams.position_initialization)
-            arrays = particles_init.create(self.params, sp.sparams, box, self.pcoord, self.params.random_seed + w.n_moved,
-                                           self.rank, positions=None if src is None else (src["x"], src["y"], src["z"]),
-                                           origin_cells=origin)
-            created[sp.name] = arrays
-            self.patch.species_append(sp.ispec, **arrays)
+            if self.pcoord[0] == self.rank_grid[0] - 1:
+                first_new = self.params.global_size[0] + w.n_moved - S
+                box = (S, self.n[1], self.n[2])
+                origin = (first_new, self.pcoord[1] * self.n[1], self.pcoord[2] * self.n[2])
+                src = created.get(sp.sparams.position_initialization)
+                arrays = particles_init.create(self.params, sp.sparams, box, self.pcoord, self.params.random_seed + w.n_moved,
+                                               self.rank, positions=None if src is None else (src["x"], src["y"], src["z"]),
+                                               origin_cells=origin)
+                created[sp.name] = arrays
+                self.patch.species_append(sp.ispec, **arrays)
             self.patch.sort(sp.ispec)
         # xmin boundary condition now that the patch has moved (:420-430), lasers off
         if not self.periodic[0]:

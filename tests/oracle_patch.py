@@ -84,9 +84,13 @@ class OraclePatch:
             P = s["P"]
             if P is None:
                 continue
-            keep = P["x"] >= self.mn[0]
-            for k in P:
-                P[k] = np.ascontiguousarray(P[k][keep])
+            behind = P["x"] < self.mn[0]
+            if self.g.pcoord[0] > 0:
+                P["key"] = np.where(behind, -2, np.where(P["key"] < 0, -1, 0)).astype(np.int32)    # the -x neighbour takes them
+            else:
+                for k in P:
+                    P[k] = np.ascontiguousarray(P[k][~behind])
+                P["key"] = np.where(P["key"] < 0, -1, 0).astype(np.int32)
             s["sorted"] = False
 
     def species_set(self, ispec, x, y, z, px, py, pz, w, q):

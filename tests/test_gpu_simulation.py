@@ -188,7 +188,7 @@ def test_laser_through_silver_muller_with_remove_matches_oracle(pusher):
 
 WINDOW_NAMELIST = """
 Main(geometry="3Dcartesian", interpolation_order=2, timestep=0.09, number_of_timesteps=90,
-     cell_length=[0.1, 0.5, 0.5], number_of_cells=[48, 8, 8], number_of_patches=[12, 1, 1],
+     cell_length=[0.1, 0.5, 0.5], number_of_cells=[48, NY, 8], number_of_patches=[12, 1, 1],
      EM_boundary_conditions=[["silver-muller"]])
 MovingWindow(time_start=2.5, velocity_x=0.9997)
 LaserGaussian3D(box_side="xmin", a0=1.0, omega=2.0, focus=[0., 2.0, 2.0], waist=1.5,
@@ -199,10 +199,10 @@ Species(name="electron", position_initialization="regular", momentum_initializat
 """
 
 
-def _window_run(patch_factory, steps):
+def _window_run(patch_factory, steps, ny=8):
     from smilei_b200 import namelist
     from smilei_b200.simulation import Simulation
-    params = namelist.load_namelist(WINDOW_NAMELIST, is_source=True)
+    params = namelist.load_namelist(WINDOW_NAMELIST.replace("NY", str(ny)), is_source=True)
     sim = Simulation(params, patch_factory=patch_factory)
     sim.create_particles()
     hist = sim.run(steps, scalars_every=1)
@@ -369,3 +369,55 @@ def test_reference_validation_em_propagation():
     print("em_propagation: 0-D probe", e0, " 1-D probe", e1, " 2-D probe", e2,
           " max |reference| =", np.max(np.abs(gold["probe0_Ey_vs_time"])), np.max(np.abs(gold["probe1_Ey"])))
     assert e0 <= tol and e1 <= tol and e2 <= tol
+
+
+def _nccl_window_rank(rank, world, rank_grid, steps, port, ret, ny=12):
+    import torch
+    import torch.distributed as dist
+    from smilei_b200 import namelist
+    from smilei_b200.simulation import Simulation
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    params = namelist.load_namelist(WINDOW_NAMELIST.replace("NY", str(ny)), is_source=True)
+    sim = Simulation(params, rank_grid=rank_grid, rank=rank)
+    sim.create_particles()
+    hist = sim.run(steps, scalars_every=1)
+    info = (sim.patch.species_get(0), sim.simWindow.n_moved)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, info)
+    if rank == 0:
+        ret["hist"] = [(h[0], h[1].tolist(), h[2]) for h in hist]
+        ret["parts"] = [g[0] for g in gathered]
+        ret["n_moved"] = [g[1] for g in gathered]
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rank_grid", [(2, 1, 1), (1, 2, 1)])
+def test_two_gpus_nccl_moving_window_matches_oracle_single_rank(rank_grid):
+    """Open box, laser, `remove` particles and the moving window on two GPUs (split along the window direction or
+    across it) against the oracle-backed single-rank run."""
+    import torch
+    import torch.multiprocessing as mp
+    from test_host_logic import _free_port
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    steps = 70
+    O = _window_run(OraclePatch, steps, ny=12)         # 12 cells along y: 6 per rank = 2*oversize+2, the smallest patch
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_nccl_window_rank, args=(2, rank_grid, steps, _free_port(), ret), nprocs=2, join=True)
+    two = dict(ret)
+    assert two["n_moved"] == [O["n_moved"]] * 2 and O["n_moved"] >= 10 * 4
+    for k, (a, b) in enumerate(zip(O["hist"][:steps], two["hist"])):
+        assert a[0] == b[0]
+        assert np.allclose(a[1], b[1], rtol=1e-9 * steps, atol=1e-30), (k, a[1], b[1])
+        assert abs(a[2] - b[2]) <= 1e-9 * steps * max(abs(a[2]), 1e-300), (k, a[2], b[2])
+    po = O["part"]
+    cols = {k: np.concatenate([r[k] for r in two["parts"]]) for k in ("x", "y", "z", "px", "py", "pz")}
+    ia = np.lexsort((cols["z"], cols["y"], cols["x"]))
+    ib = np.lexsort((po["z"], po["y"], po["x"]))
+    assert len(ia) == len(ib) > 0
+    for k in cols:
+        assert np.allclose(cols[k][ia], po[k][ib], rtol=0, atol=1e-9), k

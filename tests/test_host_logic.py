@@ -368,12 +368,14 @@ def _launch_window(rank_grid, steps):
     return dict(ret)
 
 
-def test_moving_window_two_ranks_gloo_match_single_rank():
-    """Laser + cold plasma + moving window with the box split in two along y: every rank slides its patch by the
-    same stride at the same steps, creates the particles of its share of the uncovered cells, and the run
-    reproduces the single-rank one."""
+@pytest.mark.parametrize("rank_grid", [(1, 2, 1), (2, 1, 1)])
+def test_moving_window_two_ranks_gloo_match_single_rank(rank_grid):
+    """Laser + cold plasma + moving window with the box split in two, along y (every rank slides its patch by the
+    same stride and creates the particles of its share of the uncovered cells) or along x (the +x rank hands its
+    leftmost interior planes and the particles it leaves behind to the -x rank, only the +x rank creates
+    particles): the run reproduces the single-rank one."""
     one = _launch_window((1, 1, 1), 70)
-    two = _launch_window((1, 2, 1), 70)
+    two = _launch_window(rank_grid, 70)
     assert one["n_moved"][0] >= 10 * 4 and two["n_moved"] == [one["n_moved"][0]] * 2
     for (it_a, uk_a, ue_a), (it_b, uk_b, ue_b) in zip(one["hist"], two["hist"]):
         assert it_a == it_b
