@@ -73,6 +73,8 @@ struct SpeciesDev {
     // perm[j] = index of the particle that belongs in slot j.  The next dynamics kernel reads its particles
     // through perm and writes them, pushed, at their sorted slots of the spare column set (one pass over the
     // particle data per step instead of two); any other consumer calls materialize() first.
+    size_t n_sorted = 0;                   // particles [0, n_sorted) are the cell runs `first` describes (0: no valid runs); later ones were appended
+    bool   window_tagged = false;          // leavers were tagged by a window shift: they sit anywhere in the first cells along x
     int    bc[6] = { 0, 0, 0, 0, 0, 0 };   // SB200_PBC_* per global box side
     double *d_lost = nullptr;              // sum of w*(gamma-1) of removed particles
     int    *perm = nullptr;

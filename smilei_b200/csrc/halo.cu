@@ -167,36 +167,93 @@ __global__ void __launch_bounds__( 256 ) k_arrive( GridDev g, MutCols out, size_
     }
 }
 
-// Leavers of one (dim, side) from the index list the dynamics kernel / arrivals filled in atomic order:
-// each entry finds its rank (number of listed indices below its own) by brute force - the list is a
-// boundary layer's worth of particles - and writes its record there, so the packed order is the index
-// order whatever order the atomics were served in.
-__global__ void __launch_bounds__( 256 ) k_rank_pack( ConstCols in, const int *__restrict__ list, int m, int dim, double wrap,
-        double lo, double hi, double *__restrict__ buf )
+// ---------------------------------------------------------------- leavers of one box side, in index order
+// A particle tagged for side (dim, side) sat, before the push, in one of the two outermost node layers of that
+// side (it moves less than a cell per step), or it is an arrival appended behind the sorted runs.  The layers'
+// cells are enumerated in increasing cell index, then the appended tail in chunks: counting the tagged particles
+// per entry, scanning, and writing the records at the scanned offsets is a stable compaction of the boundary
+// layer only — a few hundred thousand keys instead of all of them, and no quadratic ranking of a leaver list.
+struct LayerGeom { int dim, l0, l1, nc0, nc1, nc2; unsigned ncells_layer; unsigned ntail_chunks; size_t n_sorted, n; };
+
+__device__ __forceinline__ int layer_cell( const LayerGeom &G, unsigned e )
 {
-    __shared__ int tile[256];
-    const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    const int mine = t < m ? list[t] : 0x7fffffff;
-    int rank = 0;
-    for( int base = 0; base < m; base += 256 ) {
-        __syncthreads();
-        tile[threadIdx.x] = base + threadIdx.x < m ? list[base + threadIdx.x] : 0x7fffffff;
-        __syncthreads();
-        const int lim = min( 256, m - base );
-        for( int j=0; j<lim; j++ ) rank += tile[j] < mine;
+    if( G.dim == 0 ) { const unsigned A = ( unsigned )G.nc1*G.nc2; const unsigned l = e / A, r = e - l*A; return ( int )( ( l ? G.l1 : G.l0 )*A + r ); }
+    if( G.dim == 1 ) { const unsigned iz = e % G.nc2, t = e / G.nc2, l = t & 1u, ix = t >> 1; return ( int )( ( ix*G.nc1 + ( l ? G.l1 : G.l0 ) )*G.nc2 + iz ); }
+    const unsigned l = e & 1u, t = e >> 1;
+    return ( int )( t*G.nc2 + ( l ? G.l1 : G.l0 ) );
+}
+
+__global__ void __launch_bounds__( 256 ) k_layer_count( LayerGeom G, const int *__restrict__ first, const int *__restrict__ key, int tag, int *__restrict__ cnt )
+{
+    const unsigned total = G.ncells_layer + G.ntail_chunks;
+    for( unsigned e = blockIdx.x*blockDim.x + threadIdx.x; e < total; e += gridDim.x*blockDim.x ) {
+        size_t b, en;
+        if( e < G.ncells_layer ) { const int c = layer_cell( G, e ); b = ( size_t )first[c]; en = ( size_t )first[c+1]; }
+        else { b = G.n_sorted + ( size_t )( e - G.ncells_layer )*256; en = b + 256 < G.n ? b + 256 : G.n; }
+        int c = 0;
+        for( size_t i=b; i<en; i++ ) c += key[i] == tag;
+        cnt[e] = c;
     }
-    if( t >= m ) return;
-    double *r = buf + ( size_t )rank*SB200_PARTICLE_RECORD_DOUBLES;
+}
+
+__global__ void __launch_bounds__( 256 ) k_layer_write( LayerGeom G, ConstCols in, const int *__restrict__ first, const int *__restrict__ key, int tag,
+        int dim, double wrap, double lo, double hi, const int *__restrict__ off, double *__restrict__ buf, size_t max_records )
+{
+    const unsigned total = G.ncells_layer + G.ntail_chunks;
+    for( unsigned e = blockIdx.x*blockDim.x + threadIdx.x; e < total; e += gridDim.x*blockDim.x ) {
+        size_t b, en;
+        if( e < G.ncells_layer ) { const int c = layer_cell( G, e ); b = ( size_t )first[c]; en = ( size_t )first[c+1]; }
+        else { b = G.n_sorted + ( size_t )( e - G.ncells_layer )*256; en = b + 256 < G.n ? b + 256 : G.n; }
+        size_t o = ( size_t )off[e];
+        for( size_t i=b; i<en; i++ ) {
+            if( key[i] != tag ) continue;
+            if( o < max_records ) {
+                double *r = buf + o*SB200_PARTICLE_RECORD_DOUBLES;
 #pragma unroll
-    for( int cc=0; cc<7; cc++ ) r[cc] = in.c[cc][mine];
-    if( wrap > 0. ) { if( r[dim] < lo ) r[dim] += wrap; }
-    else if( wrap < 0. ) { if( r[dim] >= hi ) r[dim] += wrap; }
-    r[7] = ( double )in.q[mine];
+                for( int cc=0; cc<7; cc++ ) r[cc] = in.c[cc][i];
+                if( wrap > 0. ) { if( r[dim] < lo ) r[dim] += wrap; }          // Patch::prepareParticles, Patch.cpp:633-650
+                else if( wrap < 0. ) { if( r[dim] >= hi ) r[dim] += wrap; }
+                r[7] = ( double )in.q[i];
+            }
+            o++;
+        }
+    }
 }
 
 } // namespace sb200
 
 using namespace sb200;
+
+// stable pack of the leavers of one side from the boundary layer (see k_layer_count); total_out may be null
+static int pack_boundary_layer( sb200_patch *p, SpeciesDev &s, int tag, int dim, int side, double wrap, double hi,
+                                double *dev_buf, size_t max_records, int *d_total_out )
+{
+    const GridDev &g = p->gd;
+    LayerGeom G;
+    G.dim = dim; G.nc0 = g.ncell[0]; G.nc1 = g.ncell[1]; G.nc2 = g.ncell[2];
+    const int nc = g.ncell[dim];
+    G.l0 = side == 0 ? 0 : nc-2; G.l1 = side == 0 ? 1 : nc-1;
+    G.ncells_layer = 2u*( unsigned )( ( size_t )G.nc0*G.nc1*G.nc2 / nc );
+    G.n_sorted = s.n_sorted; G.n = s.n;
+    G.ntail_chunks = ( unsigned )( ( s.n - s.n_sorted + 255 )/256 );
+    const size_t ne = ( size_t )G.ncells_layer + G.ntail_chunks;
+    if( ensure_perm( p, ne + 1 ) ) return 1;
+    int *cnt = p->perm;                       // scratch (the sort orders live in the species' own perm arrays)
+    const unsigned blocks = ( unsigned )( ( ne + 255 )/256 < 148*8 ? ( ne + 255 )/256 : 148*8 );
+    k_layer_count<<<blocks, 256, 0, p->stream>>>( G, s.first, s.key, tag, cnt );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    SB200_CUDA( cudaMemsetAsync( cnt + ne, 0, sizeof( int ), p->stream ) );
+    if( exclusive_scan_int( p, cnt, ne + 1 ) ) return 1;
+    if( d_total_out ) SB200_CUDA( cudaMemcpyAsync( d_total_out, cnt + ne, sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+    ConstCols in;
+    for( int c=0; c<7; c++ ) in.c[c] = s.col[c];
+    in.q = s.q;
+    k_layer_write<<<blocks, 256, 0, p->stream>>>( G, in, s.first, s.key, tag, dim, wrap, 0., hi, cnt, dev_buf, max_records );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    return 0;
+}
 
 extern "C" {
 
@@ -292,22 +349,18 @@ int sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wra
     ConstCols in;
     for( int c=0; c<7; c++ ) in.c[c] = s.col[c];
     in.q = s.q;
-    {
-        // fast path: the tagged particles were listed when they were tagged
+    if( s.n_sorted > 0 && !s.window_tagged ) {
+        // the leavers sit in the boundary layer of that side (or in the appended tail): compact those cells only
         int cnt = 0;
         SB200_CUDA( cudaMemcpyAsync( &cnt, p->leave_counts + 8*ispec + ( -tag-2 ), sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
         SB200_CUDA( cudaStreamSynchronize( p->stream ) );
-        if( ( size_t )cnt <= s.leave_cap && cnt <= 200000 ) {
-            SB200_CHECK( ( size_t )cnt <= max_records, "sb200_leaving_pack: buffer too small for the leaving particles" );
-            if( cnt > 0 ) {
-                SB200_CHECK( dev_buf, "sb200_leaving_pack: null buffer" );
-                k_rank_pack<<<( cnt + 255 )/256, 256, 0, p->stream>>>( in, s.leave_idx + ( size_t )( -tag-2 )*s.leave_cap, cnt, dim, wrap, 0., hi, dev_buf );
-                sb200::g_launches++;
-                SB200_CUDA( cudaGetLastError() );
-            }
-            *n_packed = ( size_t )cnt;
-            return 0;
+        SB200_CHECK( ( size_t )cnt <= max_records, "sb200_leaving_pack: buffer too small for the leaving particles" );
+        if( cnt > 0 ) {
+            SB200_CHECK( dev_buf, "sb200_leaving_pack: null buffer" );
+            if( pack_boundary_layer( p, s, tag, dim, side, wrap, hi, dev_buf, max_records, nullptr ) ) return 1;
         }
+        *n_packed = ( size_t )cnt;
+        return 0;
     }
     // general path (list overflow or very many leavers): stable compaction over all keys
     const size_t nb = ( s.n + CP_B - 1 )/CP_B;
@@ -336,22 +389,16 @@ int sb200_leaving_pack_known( sb200_patch *p, int ispec, int dim, int side, doub
 {
     SB200_CHECK( p && ispec >= 0 && ispec < p->nspec && dim >= 0 && dim < 3 && ( side==0 || side==1 ), "sb200_leaving_pack_known: bad arguments" );
     SpeciesDev &s = p->sp[ispec];
-    SB200_CHECK( n_known <= s.leave_cap && n_known <= 200000, "sb200_leaving_pack_known: too many leavers for the tag list (use sb200_leaving_pack)" );
     SB200_CHECK( n_known <= max_records, "sb200_leaving_pack_known: buffer too small for the leaving particles" );
     if( n_known == 0 ) return 0;
     SB200_CHECK( dev_buf, "sb200_leaving_pack_known: null buffer" );
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( materialize( p, ispec ) ) return 1;
+    SB200_CHECK( s.n_sorted > 0 && !s.window_tagged, "sb200_leaving_pack_known: the species has no valid cell runs (use sb200_leaving_pack)" );
     const int tag = -2 - 2*dim - side;
     const GridDev &g = p->gd;
     const double hi = g.cell[dim]*( double )( g.n[dim]*g.npatch[dim] );
-    ConstCols in;
-    for( int c=0; c<7; c++ ) in.c[c] = s.col[c];
-    in.q = s.q;
-    k_rank_pack<<<( unsigned )( ( n_known + 255 )/256 ), 256, 0, p->stream>>>( in, s.leave_idx + ( size_t )( -tag-2 )*s.leave_cap, ( int )n_known, dim, wrap, 0., hi, dev_buf );
-    sb200::g_launches++;
-    SB200_CUDA( cudaGetLastError() );
-    return 0;
+    return pack_boundary_layer( p, s, tag, dim, side, wrap, hi, dev_buf, max_records, nullptr );
 }
 
 int sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, size_t n )

@@ -91,6 +91,7 @@ extern "C" int sb200_species_init_thermal( sb200_patch *p, int ispec, const int 
             sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     s.n = n;
+    s.n_sorted = 0;
     s.sorted = false;
     s.count_valid = false;
     s.perm_pending = false;

@@ -294,6 +294,7 @@ int sb200_species_set( sb200_patch *p, int ispec,
     SB200_CUDA( cudaMemsetAsync( s.key, 0, n*sizeof( int ), p->stream ) );
     SB200_CUDA( cudaMemsetAsync( s.d_qwmax, 0, sizeof( unsigned long long ), p->stream ) );
     s.n = n;
+    s.n_sorted = 0;
     s.count_valid = false;
     s.perm_pending = false;
     if( update_qwmax( p, ispec, 0, n ) ) return 1;
@@ -385,6 +386,7 @@ int sb200_window_shift( sb200_patch *p, int ncells )
         }
         s.sorted = false;
         s.count_valid = false;
+        s.window_tagged = true;
     }
     return 0;
 }

@@ -363,6 +363,8 @@ int launch_sort( sb200_patch *p, int ispec )
     SB200_CHECK( flags[0] == 0, "sb200_sort: particles outside the patch without a leaving tag (positions must lie in [min,max) of the patch)" );
     // the columns stay where they are: the next dynamics kernel reads them through perm (materialize() for anyone else)
     s.n = ( size_t )kept;
+    s.n_sorted = ( size_t )kept;
+    s.window_tagged = false;
     s.perm_pending = kept > 0;
     s.sorted = true;
     s.count_valid = false;
