@@ -153,25 +153,34 @@ __global__ void __launch_bounds__( 256 ) k_cell_sort( const int *__restrict__ fi
         const int cb = first[min( c, ncells )], ce = first[min( c+1, ncells )];
         const int base = __shfl_sync( 0xffffffffu, cb, 0 ), end = __shfl_sync( 0xffffffffu, ce, 31 );
         const bool staged = end - base <= SW;
-        unsigned bad = 0;
+        bool mybad = false;
         __syncwarp();
+        if( staged ) {
+            // all the loads of the stretch are issued back to back (nothing below depends on them until the barrier)
+            for( int q = lane; q < end - base; q += 32 ) sm[q + ( q >> 4 )] = perm[base + q];
+            __syncwarp();
+        }
         for( int j0 = base; j0 < end; j0 += 32 ) {
             const int j = j0 + lane;
-            const int v = j < end ? perm[j] : 0x7fffffff;
-            if( staged && j < end ) { const int q = j - base; sm[q + ( q >> 4 )] = v; }
+            int v = 0x7fffffff;
+            if( j < end ) { const int q = j - base; v = staged ? sm[q + ( q >> 4 )] : perm[j]; }
             int vn = __shfl_down_sync( 0xffffffffu, v, 1 );
-            if( lane == 31 ) vn = j+1 < end ? perm[j+1] : 0x7fffffff;
-            // cell of position j among the warp's 32 cells: the number of run ends <= j
-            int k = 0;
-#pragma unroll
-            for( int st=16; st>0; st>>=1 ) {
-                const int probe = __shfl_sync( 0xffffffffu, ce, k + st - 1 );
-                if( probe <= j ) k += st;
+            if( lane == 31 && j+1 < end ) { const int q = j + 1 - base; vn = staged ? sm[q + ( q >> 4 )] : perm[j+1]; }
+            else if( lane == 31 ) vn = 0x7fffffff;
+            // positions of the chunk that are the LAST entry of a cell (the next entry starts another cell): lane c
+            // knows where its own cell ends
+            const int last = ce - 1 - j0;
+            const unsigned ends = __reduce_or_sync( 0xffffffffu, ( ce > cb && last >= 0 && last < 32 ) ? ( 1u << last ) : 0u );
+            const bool inv = j+1 < end && v > vn && !( ( ends >> lane ) & 1u );
+            const unsigned invmask = __ballot_sync( 0xffffffffu, inv );
+            // does an inversion fall inside my own cell's run?
+            const int lo = max( cb - j0, 0 ), hi = min( ce - j0, 32 );
+            if( invmask && hi > lo ) {
+                const unsigned range = ( hi >= 32 ? 0xffffffffu : ( ( 1u << hi ) - 1u ) ) & ~( ( 1u << lo ) - 1u );
+                mybad = mybad || ( invmask & range ) != 0u;
             }
-            const int kend = __shfl_sync( 0xffffffffu, ce, k & 31 );
-            const bool inv = j+1 < end && k < 32 && j+1 < kend && v > vn;
-            bad |= __reduce_or_sync( 0xffffffffu, inv ? ( 1u << k ) : 0u );
         }
+        const unsigned bad = __ballot_sync( 0xffffffffu, mybad );
         if( bad == 0 ) continue;
         __syncwarp();
         if( ( bad >> lane ) & 1u ) {
