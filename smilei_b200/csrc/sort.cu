@@ -364,7 +364,17 @@ int launch_sort( sb200_patch *p, int ispec )
         k_scatter_idx<<<blocks, 256, 0, p->stream>>>( s.key, s.first, p->cursor, s.perm, n );
         sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
-        k_cell_sort<<<148*8, 256, 0, p->stream>>>( s.first, s.perm, ncells );
+        // persistent grid: as many CTAs as are resident at once (the loop strides over the cells; a partial second
+        // wave would run at a fraction of the occupancy)
+        static int cs_blocks = 0;
+        if( !cs_blocks ) {
+            int per_sm = 1, dev = 0, sms = 148;
+            cudaGetDevice( &dev );
+            cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_cell_sort, 256, 0 );
+            cs_blocks = sms*( per_sm > 0 ? per_sm : 1 );
+        }
+        k_cell_sort<<<cs_blocks, 256, 0, p->stream>>>( s.first, s.perm, ncells );
         sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
     }
