@@ -114,7 +114,10 @@ struct DynArgs {
     double *lost;             // accumulates w*(gamma-1) of the removed particles
 };
 
-// a particle tagged for exchange: count it and remember its index (sb200_leaving_pack orders the list)
+// a particle tagged for exchange: count it per box side and remember its index.  sb200_leaving_pack no longer reads
+// the index list (it compacts the boundary layer of the side, halo.cu); the list write stays because without it
+// ptxas allocates k_dynamics_o2's 128 registers differently and the kernel runs 6 % slower (A/B inside one box:
+// 74.8 vs 79.1 ms per step at 256^3) — to be removed together with the next rework of that kernel's register pressure
 __device__ __forceinline__ void note_leaver( const DynArgs &a, int tag, size_t ip )
 {
     const int t = -tag-2;
