@@ -220,6 +220,29 @@ int  sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, si
 int  sb200_species_init_thermal( sb200_patch *p, int ispec, const int ppc[3], double density, int charge,
                                  double temperature, unsigned long long seed );
 
+/* ---- initial particles on the reference's random streams (HOST, init time only) --- */
+/* Hilbert index of the patch at (x,y,z) in a box of 2^m0 x 2^m1 x 2^m2 patches: replaces
+ * generalhilbertindex (src/DomainDecomposition/Hilbert_functions.cpp:246-296), which
+ * HilbertDomainDecomposition3D::getDomainId calls (HilbertDomainDecomposition.cpp:83-87).  A patch's
+ * stream is xorshift32 seeded with random_seed + this index (src/Patch/Patch.cpp:129, Random.h:91-140). */
+int  sb200_hilbert_index3d( unsigned m0, unsigned m1, unsigned m2, int x, int y, int z, unsigned *hindex );
+/* Particles of ONE species in the box[3] cells starting at box_min (one reference patch), cell by cell
+ * in the order and with the arithmetic of ParticleCreator::create (src/Particles/ParticleCreator.cpp:
+ * 300-338): createPosition (:611-745; position_init 0 regular, 1 random, 2 centered, 3 = positions
+ * already in x,y,z, copied from another species), createMomentum (:818-851; momentum_init 0 cold,
+ * 1 maxwell-juettner with ParticleCreator::maxwellJuttner :1002-1071 and its two tables), createWeight
+ * (:933-939), createCharge (:964-974).  Per cell (row-major, z fastest): nppc, n_real = |density| x
+ * cell volume (0 = empty cell), charge, temperature (units of m_e c^2; divided by `mass` here).
+ * *rng_state is the patch's xorshift32 state, read and written back, so that the next species
+ * continues the stream as the reference does.  All pointers are HOST pointers. */
+int  sb200_create_particles_ref( unsigned int *rng_state, int position_init, int momentum_init,
+                                 const int box[3], const double box_min[3], const double cell_length[3],
+                                 const int *nppc, const double *n_real, const double *charge, const double *temperature,
+                                 double mass, const int regular_number[3],
+                                 const double *lnInvF, const double *lnInvH,
+                                 double *x, double *y, double *z, double *px, double *py, double *pz,
+                                 double *w, short *q, size_t capacity, size_t *n_created );
+
 /* ---- debugging -------------------------------------------------------------------------- */
 /* HOST int[8] counters, cleared by sb200_sort: [0] particles outside the patch without a tag at
  * sort time, [1] particles found outside the cell their sort key says during sb200_dynamics. */

@@ -56,6 +56,8 @@ ElectroMagnBC/ElectroMagnBC.cpp
 ElectroMagnBC/ElectroMagnBC3D.cpp
 ElectroMagnBC/ElectroMagnBC3D_SM.cpp
 Field/Field2D.cpp
+Particles/ParticleCreator.cpp
+DomainDecomposition/Hilbert_functions.cpp
 "
 pids=()
 for s in $SRCS; do
@@ -66,6 +68,8 @@ for s in $SRCS; do
     fi
 done
 g++ $CXXFLAGS -c "$HERE/ref_harness.cpp" -o "$OBJ/ref_harness.o" &
+pids+=($!)
+g++ $CXXFLAGS -c "$HERE/ref_creator_harness.cpp" -o "$OBJ/ref_creator_harness.o" &
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p" || { echo "build_ref: compile failed" >&2; exit 1; }; done
 

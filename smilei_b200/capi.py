@@ -34,6 +34,7 @@ SYMBOLS = (
     "sb200_halo_exchange_self", "sb200_leaving_count", "sb200_leaving_pack", "sb200_leaving_pack_known", "sb200_arriving_unpack",
     "sb200_debug_flags", "sb200_species_init_thermal", "sb200_launch_count",
     "sb200_species_set_bc", "sb200_species_lost_energy", "sb200_apply_SM", "sb200_window_shift", "sb200_species_append",
+    "sb200_hilbert_index3d", "sb200_create_particles_ref",
 )
 
 
@@ -86,6 +87,59 @@ def launch_count():
     n = C.c_ulonglong(0)
     _check(lib().sb200_launch_count(C.byref(n)), "sb200_launch_count")
     return n.value
+
+
+# ---- initial particles on the reference's random streams (host side, init time only)
+POSITION_INIT = {"regular": 0, "random": 1, "centered": 2, None: 3}
+MOMENTUM_INIT = {"cold": 0, "maxwell-juettner": 1, "mj": 1}
+_mj_tables = None
+
+
+def mj_tables():
+    """The two tables of ParticleCreator::maxwellJuttner (smilei_b200/data/mj_tables.npz)."""
+    global _mj_tables
+    if _mj_tables is None:
+        d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "mj_tables.npz"))
+        _mj_tables = (np.ascontiguousarray(d["lnInvF"]), np.ascontiguousarray(d["lnInvH"]))
+    return _mj_tables
+
+
+def hilbert_index3d(m, coords):
+    """generalhilbertindex( m0, m1, m2, x, y, z ) of the reference (Hilbert_functions.cpp:246)."""
+    h = C.c_uint(0)
+    _check(lib().sb200_hilbert_index3d(C.c_uint(m[0]), C.c_uint(m[1]), C.c_uint(m[2]), int(coords[0]), int(coords[1]),
+                                       int(coords[2]), C.byref(h)), "sb200_hilbert_index3d")
+    return h.value
+
+
+def create_particles_ref(rng_state, position_init, momentum_init, box, box_min, cell_length, nppc, n_real, charge,
+                         temperature, mass, regular_number=None, positions=None):
+    """sb200_create_particles_ref: (arrays, new rng_state) for one species in one reference patch."""
+    nppc = np.ascontiguousarray(nppc, dtype=np.int32).ravel()
+    n_real = np.ascontiguousarray(n_real, dtype=np.float64).ravel()
+    charge = np.ascontiguousarray(charge, dtype=np.float64).ravel()
+    temperature = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
+    cap = int(nppc[(n_real > 0) & (nppc > 0)].sum())
+    out = {k: np.zeros(cap) for k in ("x", "y", "z", "px", "py", "pz", "w")}
+    out["q"] = np.zeros(cap, dtype=np.int16)
+    pinit = POSITION_INIT[position_init]
+    if pinit == 3:
+        for k, v in zip("xyz", positions):
+            if len(v) != cap:
+                raise SmileiB200Error("Copying particles: the two species should have the same number of particles")
+            out[k][:] = v
+    state = C.c_uint(int(rng_state) & 0xffffffff)
+    n = C.c_size_t(0)
+    F, H = mj_tables()
+    reg = (C.c_int * 3)(*([int(v) for v in regular_number] if regular_number else [0, 0, 0]))
+    _check(lib().sb200_create_particles_ref(
+        C.byref(state), pinit, MOMENTUM_INIT[momentum_init], (C.c_int * 3)(*[int(v) for v in box]),
+        (C.c_double * 3)(*box_min), (C.c_double * 3)(*cell_length), _p(nppc, np.int32), _p(n_real, np.float64),
+        _p(charge, np.float64), _p(temperature, np.float64), C.c_double(mass), reg, _p(F, np.float64), _p(H, np.float64),
+        *[_p(out[k], np.float64) for k in ("x", "y", "z", "px", "py", "pz", "w")], _p(out["q"], np.int16),
+        C.c_size_t(cap), C.byref(n)), "sb200_create_particles_ref")
+    assert n.value == cap
+    return out, state.value
 
 
 class Patch:

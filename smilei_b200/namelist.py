@@ -206,6 +206,7 @@ class Params:
             raise NamelistError("simulation_time or number_of_timesteps must be defined")
         self.simulation_time = self.n_time * self.timestep
         self.number_of_patches = [int(v) for v in (m.number_of_patches or [1, 1, 1])]
+        self.patch_arrangement = str(m.patch_arrangement)
         bcs = m.EM_boundary_conditions
         self.EM_BCs = [list(bcs[min(i, len(bcs) - 1)]) for i in range(3)]
         for bc in self.EM_BCs:

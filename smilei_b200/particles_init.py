@@ -7,9 +7,12 @@ thermal-plasma namelists use:
     species (same positions);
   * weight = density*cell_volume/nppc (:259, :933-939), charge (:964-974);
   * momentum_initialization "cold", "maxwell-juettner"/"mj" (:840-851,1002-1071).
-The random stream is numpy's, not the reference's per-patch xorshift32 (src/Tools/Random.h), so
-states are statistically, not bitwise, those of the reference; bitwise parity tests import
-explicit arrays instead (the reference supports that too, ParticleCreator.cpp:344-529).
+Two random streams:
+  * `create`: numpy's generator — states are statistically those of the reference (synthetic workloads);
+  * `create_reference_streams`: the reference's own per-patch xorshift32 streams
+    (src/Tools/Random.h, seed random_seed + Hilbert index of the patch, src/Patch/Patch.cpp:129) walked in
+    the reference's order by the C ABI (sb200_create_particles_ref), so that a namelist run starts from
+    the reference's particles bit for bit whatever the rank layout.
 """
 import zlib
 
@@ -62,6 +65,91 @@ def _maxwell_juttner(T, n, rng):
         out[filled:filled + k] = eta[ok][:k]
         filled += k
     return out
+
+
+def _log2_exact(v, what):
+    m = int(v).bit_length() - 1
+    if v <= 0 or (1 << m) != v:
+        raise ValueError(f"{what} = {v} must be a power of 2 (Params.cpp:716-720)")
+    return m
+
+
+def _cell_profiles(params, sp, box, origin):
+    """nppc, n_real (= |density| x cell volume), charge and temperature of the `box` cells starting at `origin`
+    (ParticleCreator.cpp:150-263; profiles are evaluated at the cell centre)."""
+    cell = params.cell_length
+    ic, jc, kc = np.meshgrid(np.arange(box[0]), np.arange(box[1]), np.arange(box[2]), indexing="ij")
+    X = origin[0] + (ic + 0.5) * cell[0]
+    Y = origin[1] + (jc + 0.5) * cell[1]
+    Z = origin[2] + (kc + 0.5) * cell[2]
+    nppc = np.floor(_profile(sp.particles_per_cell, X, Y, Z)).astype(np.int32)
+    charge = _profile(sp.charge, X, Y, Z)
+    if sp.charge_density is not None:
+        dens = _profile(sp.charge_density, X, Y, Z)
+        dens = np.where(np.abs(dens) < 1e-200, 0., dens)                                         # :236-238
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dens = np.where(dens != 0, np.abs(dens / charge), 0.)                                # :250-256
+    else:
+        dens = _profile(sp.number_density, X, Y, Z)
+        dens = np.abs(np.where(np.abs(dens) < 1e-200, 0., dens))
+    n_real = dens * params.cell_volume                                                           # :259
+    n_real = np.where(nppc > 0, n_real, 0.)
+    T = sp.temperature[0] if sp.temperature and sp.temperature[0] is not None else 1e-10       # :164 default
+    temperature = _profile(T, X, Y, Z)
+    return nppc, n_real, charge, temperature
+
+
+def create_reference_streams(params, species, n, pcoord):
+    """Initial particles of every species of the namelist inside the rank box (`n` cells at rank coordinates
+    `pcoord`), drawn from the reference's per-patch streams: {species name: arrays}.
+
+    The box is walked by reference patches (Main.number_of_patches of the namelist, Hilbert-numbered,
+    HilbertDomainDecomposition.cpp:83-87); each patch owns one xorshift32 stream seeded with random_seed +
+    hindex (Patch.cpp:129) that the species consume one after the other (SpeciesFactory.h:1153-1157), each
+    cell by cell (ParticleCreator.cpp:300-338)."""
+    from . import capi
+    if getattr(params, "patch_arrangement", "hilbertian") != "hilbertian":
+        raise ValueError("reference streams need patch_arrangement = 'hilbertian'")
+    npatch = params.number_of_patches
+    m = [_log2_exact(npatch[d], f"number_of_patches[{d}]") for d in range(3)]
+    psize = [params.global_size[d] // npatch[d] for d in range(3)]
+    for d in range(3):
+        if psize[d] * npatch[d] != params.global_size[d] or n[d] % psize[d]:
+            raise ValueError("the rank box must be made of whole reference patches")
+    first = [pcoord[d] * n[d] // psize[d] for d in range(3)]
+    count = [n[d] // psize[d] for d in range(3)]
+    patches = []
+    for a in range(count[0]):
+        for b in range(count[1]):
+            for c in range(count[2]):
+                P = (first[0] + a, first[1] + b, first[2] + c)
+                h = capi.hilbert_index3d(m, P)
+                patches.append((h, P))
+    patches.sort()                                                    # the reference's patch order on a rank
+    state = {h: (params.random_seed + h) & 0xffffffff or 0xffffffff for h, _ in patches}       # Random.h:91-99
+    columns = ("x", "y", "z", "px", "py", "pz", "w", "q")
+    created = {}
+    for sp in species:
+        if any(abs(v) > 0 for v in sp.mean_velocity):
+            raise ValueError("mean_velocity != 0 is not supported by this initialiser")
+        posinit = sp.position_initialization
+        src = created.get(posinit)
+        if src is None and posinit not in ("regular", "random", "centered"):
+            raise ValueError(f"position_initialization `{posinit}` is neither a method nor an earlier species")
+        parts = []
+        for ip, (h, P) in enumerate(patches):
+            box_min = [P[d] * (psize[d] * params.cell_length[d]) for d in range(3)]              # Patch.cpp:149
+            nppc, n_real, charge, temperature = _cell_profiles(params, sp, psize, box_min)
+            arrays, state[h] = capi.create_particles_ref(
+                state[h], None if src is not None else posinit, sp.momentum_initialization, psize, box_min,
+                params.cell_length, nppc, n_real, charge, temperature, sp.mass, sp.regular_number,
+                positions=None if src is None else [src["_parts"][ip][k] for k in "xyz"])
+            parts.append(arrays)
+        created[sp.name] = {k: np.concatenate([p[k] for p in parts]) for k in columns}
+        created[sp.name]["_parts"] = parts
+    for v in created.values():
+        del v["_parts"]
+    return created
 
 
 def create(params, sp, n, pcoord, seed, rank, positions=None, origin_cells=None):

@@ -151,8 +151,16 @@ class Simulation:
         self.itime = 0
 
     # ------------------------------------------------------------------ initial state
-    def create_particles(self, seed=None):
-        """ParticleCreator for the species of the namelist (host-side, init time only)."""
+    def create_particles(self, seed=None, reference_streams=False):
+        """ParticleCreator for the species of the namelist (host-side, init time only).  With
+        `reference_streams` the particles are those the reference creates for this namelist and random_seed
+        (per-patch xorshift32 streams, particles_init.create_reference_streams)."""
+        if reference_streams:
+            created = particles_init.create_reference_streams(self.params, [sp.sparams for sp in self.vecSpecies],
+                                                              self.n, self.pcoord)
+            for sp in self.vecSpecies:
+                self.set_particles(sp.ispec, **created[sp.name])
+            return
         seed = self.params.random_seed if seed is None else seed
         created = {}
         for sp in self.vecSpecies:

@@ -37,3 +37,17 @@ if __name__ == "__main__":
           "tolerance": np.float64(0.01)}
     np.savez_compressed(os.path.join(HERE, "ref_validation_em_propagation.npz"), **em)
     print({k: (np.shape(v), float(np.max(np.abs(v)))) for k, v in em.items()})
+    # tst3d_v_o2_thermal_plasma_short (== tst3d_gpu_o2_thermal_plasma_short, the same data): energy curves every 10
+    # steps over 2001 steps, validate_tst3d_v_o2_thermal_plasma_short.py: Ukin/avg, Uelm/avg, Utot/avg with
+    # tolerances 1e-3, 0.02, 1e-3
+    with open(REFS + "tst3d_v_o2_thermal_plasma_short.py.txt", "rb") as f:
+        d = pickle.load(f, encoding="latin1")
+    with open(REFS + "tst3d_gpu_o2_thermal_plasma_short.py.txt", "rb") as f:
+        dg = pickle.load(f, encoding="latin1")
+    th = {"ukin": np.asarray(d["Ukinetic energy evolution: "], dtype=np.float64),
+          "uelm": np.asarray(d["Uelectromag evolution: "], dtype=np.float64),
+          "utot": np.asarray(d["Total energy evolution: "], dtype=np.float64),
+          "tolerance": np.asarray([1e-3, 0.02, 1e-3])}
+    assert all(np.array_equal(np.asarray(dg[k]), np.asarray(d[k])) for k in d)
+    np.savez_compressed(os.path.join(HERE, "ref_validation_thermal_plasma_short.npz"), **th)
+    print({k: (np.shape(v), float(np.max(np.abs(v)))) for k, v in th.items()})

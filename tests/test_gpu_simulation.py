@@ -421,3 +421,41 @@ def test_two_gpus_nccl_moving_window_matches_oracle_single_rank(rank_grid):
     assert len(ia) == len(ib) > 0
     for k in cols:
         assert np.allclose(cols[k][ia], po[k][ib], rtol=0, atol=1e-9), k
+
+
+def test_reference_validation_thermal_plasma_short():
+    """The golden vector SURVEY §8c names for the thermal-plasma path: the reference's OWN energy curves of
+    benchmarks/gpu/tst3d_v_o2_thermal_plasma_short.py (validation/references/tst3d_v_o2_thermal_plasma_short.py.txt,
+    identical to tst3d_gpu_o2_thermal_plasma_short.py.txt; committed as tests/golden/
+    ref_validation_thermal_plasma_short.npz) — 32^3 cells in 4x4x4 patches, 8 ppc at random positions, protons at
+    10 keV and electrons at 100 keV, 2001 steps, scalars every 10 steps.  The GPU run starts from the reference's
+    particles (per-patch xorshift32 streams of seed 0, Simulation.create_particles(reference_streams=True)) and is
+    held to the tolerances of validate_tst3d_v_o2_thermal_plasma_short.py: Ukin/avg 1e-3, Uelm/avg 0.02,
+    Utot/avg 1e-3."""
+    import os
+    from smilei_b200.simulation import Simulation
+    from test_reference_streams import thermal_short
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                "ref_validation_thermal_plasma_short.npz"))
+    params = thermal_short()
+    assert params.n_time == 2001 and params.global_size == [32, 32, 32]
+    sim = Simulation(params)
+    sim.create_particles(reference_streams=True)
+    assert sim.n_particles() == [32 ** 3 * 8] * 2
+    uk, ue = sim.scalars()
+    ukin, uelm = [float(uk.sum())], [ue]
+    for _, k, e in sim.run(2000, scalars_every=10):
+        ukin.append(float(k.sum()))
+        uelm.append(e)
+    sim.close()
+    ukin, uelm = np.asarray(ukin), np.asarray(uelm)
+    utot = ukin + uelm
+    assert len(ukin) == 201
+    err = {}
+    for name, mine, tol in (("ukin", ukin, 1e-3), ("uelm", uelm, 0.02), ("utot", utot, 1e-3)):
+        err[name] = float(np.max(np.abs(mine / mine.mean() - gold[name])))
+        print(f"thermal_plasma_short {name}/avg: max |GPU - reference| = {err[name]:.3e} (tolerance {tol})")
+    # the first samples, before rounding differences had time to grow, pin the initial state itself
+    print("first samples: ukin", np.abs(ukin / ukin.mean() - gold["ukin"])[:4], "uelm",
+          np.abs(uelm / uelm.mean() - gold["uelm"])[:4])
+    assert err["ukin"] <= 1e-3 and err["uelm"] <= 0.02 and err["utot"] <= 1e-3, err
