@@ -51,3 +51,11 @@ if __name__ == "__main__":
     assert all(np.array_equal(np.asarray(dg[k]), np.asarray(d[k])) for k in d)
     np.savez_compressed(os.path.join(HERE, "ref_validation_thermal_plasma_short.npz"), **th)
     print({k: (np.shape(v), float(np.max(np.abs(v)))) for k, v in th.items()})
+    # tst3d_v_o2_thermal_plasma_medium (== tst3d_gpu_o2_thermal_plasma_medium): 51 samples, tolerance 1e-3 on all three
+    with open(REFS + "tst3d_v_o2_thermal_plasma_medium.py.txt", "rb") as f:
+        d = pickle.load(f, encoding="latin1")
+    tm = {"ukin": np.asarray(d["Ukinetic energy evolution: "], dtype=np.float64),
+          "uelm": np.asarray(d["Uelectromag evolution: "], dtype=np.float64),
+          "utot": np.asarray(d["Total energy evolution: "], dtype=np.float64),
+          "tolerance": np.asarray([1e-3, 1e-3, 1e-3])}
+    np.savez_compressed(os.path.join(HERE, "ref_validation_thermal_plasma_medium.npz"), **tm)

@@ -136,6 +136,26 @@ def test_regular_number_and_hot_cold_branches():
             assert np.array_equal(a[c], b[c]), (T, c)
 
 
+@need_ref
+def test_regular_64_per_cell_follows_the_reference_truncation():
+    """pow(64., 1./3.) is 3.9999999999999996 in IEEE double and the reference stores it in an int
+    (ParticleCreator.cpp:651-652): 64 'regular' particles sit on a 3x3x3 lattice of spacing ~0.975/4 of the cell.
+    The benchmark tst3d_v_o2_thermal_plasma_medium starts from exactly that; so does the product."""
+    from ref_creator import RefCreator
+    ref = RefCreator()
+    box, cell, box_min = (2, 1, 2), (0.22, 0.22, 0.22), (0.0, 0.44, 1.1)
+    nppc = np.full(box, 64, dtype=np.int32)
+    n_real = np.full(box, 0.01)
+    charge = np.full(box, 1.)
+    temperature = np.full(box, 0.0196)
+    a, sa = capi.create_particles_ref(7, "regular", "mj", box, box_min, cell, nppc, n_real, charge, temperature, 1836.)
+    b, sb = ref.patch(7, "regular", "maxwell-juettner", box, box_min, cell, nppc, n_real, charge, temperature, 1836.)
+    assert sa == sb
+    for c in COLS:
+        assert np.array_equal(a[c], b[c]), c
+    assert len(np.unique(a["x"][:64])) == 3 and len(np.unique(a["z"][:64])) == 3
+
+
 def test_streams_do_not_depend_on_the_rank_layout():
     """The particles of the box are the same multiset whether one rank or eight ranks create them."""
     params = thermal_short(ncell=16, npatch=(2, 2, 2))
