@@ -37,11 +37,13 @@ def _regular_counts(nppc, regular_number):
         c = [int(v) for v in regular_number]
         if len(c) != 3 or c[0] * c[1] * c[2] != nppc:
             raise ValueError("regular_number is not coherent with particles_per_cell")          # :627-640
-        return c
-    coeff = round(nppc ** (1. / 3.))
-    if coeff ** 3 != nppc:
+        return c, [1. / v for v in c]
+    # :645-653 as written: the count per dimension is the double pow( nppc, 1/3 ) stored in an int (64 -> 3, because
+    # pow( 64., 1./3. ) = 3.9999999999999996) while the spacing uses the double
+    coeff = float(nppc) ** (1. / 3.)
+    if round(coeff) ** 3 != nppc:
         raise ValueError(f"Impossible to put {nppc} particles regularly spaced in one cell")   # :647-649
-    return [coeff] * 3
+    return [int(coeff)] * 3, [1. / coeff] * 3
 
 
 def _maxwell_juttner(T, n, rng):
@@ -195,11 +197,11 @@ def create(params, sp, n, pcoord, seed, rank, positions=None, origin_cells=None)
     elif posinit == "regular":
         uniq = np.unique(npc)
         for u in uniq:
-            c = _regular_counts(int(u), sp.regular_number)
+            c, inv = _regular_counts(int(u), sp.regular_number)
             sel = np.repeat(npc == u, npc)
             i = local[sel].copy()
             for d in range(3):
-                pos[d, sel] = origin[d] + ci[d, sel] * cell[d] + cell[d] * 0.975 * (1. / c[d]) * (0.5 + i % c[d])
+                pos[d, sel] = origin[d] + ci[d, sel] * cell[d] + cell[d] * 0.975 * inv[d] * (0.5 + i % c[d])
                 i //= c[d]
     elif posinit == "random":
         for d in range(3):

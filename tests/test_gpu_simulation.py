@@ -527,3 +527,65 @@ def test_reference_validation_thermal_plasma_medium():
     # each differs from the stored curve (profiles/r1_thermal_short_seed_scatter.json), and 1e-3 on Uelm is below that
     # scatter.  The bound asserted here is the realisation scatter, stated for what it is.
     assert err["uelm"] <= 1e-2, err
+
+
+def _thermal_short_curves(sim, steps):
+    uk, ue = sim.scalars()
+    K, E = [float(uk.sum())], [ue]
+    for _, k, e in sim.run(steps, scalars_every=10):
+        K.append(float(k.sum()))
+        E.append(e)
+    return np.asarray(K), np.asarray(E)
+
+
+def _nccl_rank_streams(rank, world, rank_grid, steps, port, ret):
+    import torch
+    import torch.distributed as dist
+    from smilei_b200.simulation import Simulation
+    from test_reference_streams import thermal_short
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    sim = Simulation(thermal_short(), rank_grid=rank_grid, rank=rank)
+    sim.create_particles(reference_streams=True)              # each rank walks ITS reference patches
+    counts = sim.n_particles()
+    K, E = _thermal_short_curves(sim, steps)
+    if rank == 0:
+        ret["K"], ret["E"], ret["counts"] = K.tolist(), E.tolist(), counts
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rank_grid", [(2, 1, 1)])
+def test_two_gpus_reference_streams_thermal_short(rank_grid):
+    """tst3d_v_o2_thermal_plasma_short with the box split over two GPUs: each rank creates the particles of the
+    reference patches it holds (Hilbert index -> stream), so the run starts from the SAME particles as on one GPU.
+    The energy curves of the two runs agree to rounding growth while the trajectories are still correlated (first
+    100 steps), and the whole 2-GPU run stays inside the reference's tolerances against its stored curves."""
+    import torch
+    import torch.multiprocessing as mp
+    from smilei_b200.simulation import Simulation
+    from test_host_logic import _free_port
+    from test_reference_streams import thermal_short
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                "ref_validation_thermal_plasma_short.npz"))
+    sim = Simulation(thermal_short())
+    sim.create_particles(reference_streams=True)
+    K1, E1 = _thermal_short_curves(sim, 100)
+    sim.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_nccl_rank_streams, args=(2, rank_grid, 2000, _free_port(), ret), nprocs=2, join=True)
+    K2, E2 = np.asarray(ret["K"]), np.asarray(ret["E"])
+    assert ret["counts"] == [32 ** 3 * 8] * 2 and len(K2) == 201
+    dK = np.abs(K2[:11] / K1 - 1.)
+    dE = np.abs(E2[1:11] / E1[1:] - 1.)
+    print("2 GPUs vs 1 GPU, first 100 steps: Ukin", dK.max(), "Uelm", dE.max())
+    assert dK.max() <= 1e-10 and dE.max() <= 1e-7, (dK, dE)
+    U2 = K2 + E2
+    err = {name: float(np.max(np.abs(mine / mine.mean() - gold[name])))
+           for name, mine in (("ukin", K2), ("uelm", E2), ("utot", U2))}
+    print("2 GPUs vs stored reference:", err)
+    assert err["ukin"] <= 1e-3 and err["uelm"] <= 0.02 and err["utot"] <= 1e-3, err
