@@ -461,6 +461,18 @@ def test_reference_validation_thermal_plasma_short():
     print("first samples: ukin", np.abs(ukin / ukin.mean() - gold["ukin"])[:4], "uelm",
           np.abs(uelm / uelm.mean() - gold["uelm"])[:4])
     assert err["ukin"] <= 1e-3 and err["uelm"] <= 0.02 and err["utot"] <= 1e-3, err
+    # the same 2001 steps by the CPU oracle from the same particles (tests/golden/make_oracle_thermal_short.py)
+    orc = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_thermal_short_curves.npz"))
+    dk = np.abs(ukin / orc["ukin"] - 1.)
+    de = np.abs(uelm[1:] / orc["uelm"][1:] - 1.)
+    print(f"GPU vs oracle over 2001 steps: Ukin rel {dk.max():.3e} (first 100 steps {dk[:11].max():.3e}), "
+          f"Uelm rel {de.max():.3e} (first 100 steps {de[:10].max():.3e})")
+    assert dk[:11].max() <= 1e-11 and de[:10].max() <= 1e-9, (dk[:11], de[:10])      # per-step bars x 100 steps
+    assert dk.max() <= ORACLE_CURVE_TOL[0] and de.max() <= ORACLE_CURVE_TOL[1], (dk.max(), de.max())
+
+
+# whole-run bound of the GPU energy curves against the oracle's (rounding differences grow along 2001 steps)
+ORACLE_CURVE_TOL = (1e-10, 1e-8)      # measured on a B200: 8.4e-13, 1.0e-10
 
 
 THERMAL_MEDIUM = """
