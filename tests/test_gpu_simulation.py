@@ -601,3 +601,33 @@ def test_two_gpus_reference_streams_thermal_short(rank_grid):
            for name, mine in (("ukin", K2), ("uelm", E2), ("utot", U2))}
     print("2 GPUs vs stored reference:", err)
     assert err["ukin"] <= 1e-3 and err["uelm"] <= 0.02 and err["utot"] <= 1e-3, err
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_reference_benchmark_tst3d_thermal_plasma_matches_oracle(order):
+    """BASELINE.json configs[0] (benchmarks/tst3d_01_thermal_plasma.py, order 2) and configs[2] at the reference's own
+    size (benchmarks/tst3d_v_o4_thermal_plasma.py, order 4): the whole 163-step run on the GPU from the reference's
+    particles (plasma slab: the patches' streams skip the empty cells as ParticleCreator does), every step's Ukin per
+    species and Uelm against the CPU oracle's run of the same namelist (tests/golden/make_oracle_tst3d_thermal.py).
+    Bars: the north_star's per-step tolerances times the number of steps taken."""
+    from smilei_b200.simulation import Simulation
+    from test_reference_streams import tst3d_thermal
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"oracle_tst3d_thermal_o{order}.npz"))
+    params = tst3d_thermal(order)
+    assert params.n_time == 163 and params.interpolation_order == order
+    sim = Simulation(params)
+    sim.create_particles(reference_streams=True)
+    assert sim.n_particles() == [int(v) for v in gold["n_particles"]]
+    uk, ue = sim.scalars()
+    K, E = [uk.copy()], [ue]
+    for _, k, e in sim.run(params.n_time, scalars_every=1):
+        K.append(k.copy())
+        E.append(e)
+    sim.close()
+    K, E = np.asarray(K), np.asarray(E)
+    steps = np.arange(len(E))
+    dK = np.abs(K / gold["ukin"] - 1.).max(axis=1)
+    dE = np.abs(E[1:] / gold["uelm"][1:] - 1.)
+    print(f"order {order}: Ukin rel max {dK.max():.3e}, Uelm rel max {dE.max():.3e} over {params.n_time} steps")
+    assert np.all(dK <= 1e-12 * np.maximum(steps, 1)), dK.max()
+    assert np.all(dE <= 1e-10 * steps[1:]), dE.max()

@@ -41,6 +41,40 @@ def thermal_short(ncell=32, npatch=(4, 4, 4), posinit="random", nsteps=2001):
                          is_source=True)
 
 
+TST3D_THERMAL = """
+import math as m
+T = 10./511.
+n0 = 1.
+dx = 0.5*m.sqrt(T)
+dt = 0.95*dx/m.sqrt(3.)
+Lx = %(ncell)d.*dx
+Ly = Lx
+Lz = Lx
+def n0_(x,y,z):
+    if (0.1*Lx<x<0.9*Lx) and (0.1*Ly<y<0.9*Ly) and (0.1*Lz<z<0.9*Lz):
+        return n0
+    else:
+        return 0.
+Main(geometry="3Dcartesian", interpolation_order=%(order)d, timestep=dt, simulation_time=2.*m.pi,
+     cell_length=[dx,dx,dx], grid_length=[Lx,Ly,Lz], number_of_patches=[4,4,4],
+     EM_boundary_conditions=[["periodic"]], print_every=1)
+Species(name="proton", position_initialization="regular", momentum_initialization="mj", particles_per_cell=8,
+        c_part_max=1.0, mass=1836.0, charge=1.0, charge_density=n0_, mean_velocity=[0.,0.,0.], temperature=[T],
+        pusher="boris", boundary_conditions=[["periodic","periodic"]]*3)
+Species(name="electron", position_initialization="regular", momentum_initialization="mj", particles_per_cell=8,
+        c_part_max=1.0, mass=1.0, charge=-1.0, charge_density=n0_, mean_velocity=[0.,0.,0.], temperature=[T],
+        pusher="boris", boundary_conditions=[["periodic","periodic"]]*3)
+DiagScalar(every=1)
+"""
+
+
+def tst3d_thermal(order):
+    """benchmarks/tst3d_01_thermal_plasma.py (order 2, 32^3 cells: BASELINE.json configs[0]) and
+    benchmarks/tst3d_v_o4_thermal_plasma.py (order 4, 40^3 cells: configs[2] at the reference's own size): a plasma
+    slab in the central 80 % of a periodic box, 8 ppc regular, 10 keV, 163 steps; diagnostics blocks left out."""
+    return load_namelist(TST3D_THERMAL % dict(order=order, ncell={2: 32, 4: 40}[order]), is_source=True)
+
+
 # ------------------------------------------------------------------------------------------ Hilbert numbering
 SHAPES = [(2, 2, 2), (0, 0, 0), (1, 1, 1), (3, 3, 3), (3, 1, 2), (1, 3, 0), (0, 2, 3), (2, 0, 0), (4, 2, 2), (2, 3, 3)]
 
