@@ -388,3 +388,48 @@ def test_moving_window_two_ranks_gloo_match_single_rank(rank_grid):
     assert len(ia) == len(ib) > 0
     for k in cols_a:
         assert np.allclose(cols_a[k][ia], cols_b[k][ib], rtol=0, atol=1e-9), k
+
+
+# ------------------------------------------------------------------------------------------------------------
+# initial particles on the reference's per-patch streams, across ranks
+def _run_rank_streams(rank, world, rank_grid, steps, port, ret):
+    from test_reference_streams import thermal_short
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p = thermal_short(ncell=16, npatch=(2, 2, 2), nsteps=steps)
+    sim = Simulation(p, rank_grid=rank_grid, rank=rank, patch_factory=OraclePatch)
+    sim.create_particles(reference_streams=True)          # each rank draws the reference patches it holds
+    hist = [(0,) + sim.scalars()] + sim.run(steps, scalars_every=1)
+    parts = [sim.patch.species_get(s.ispec) for s in sim.vecSpecies]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, parts)
+        dist.barrier()
+        dist.destroy_process_group()
+    else:
+        gathered = [parts]
+    if rank == 0:
+        ret["hist"] = [(h[0], h[1].tolist(), h[2]) for h in hist]
+        ret["parts"] = gathered
+
+
+@pytest.mark.parametrize("rank_grid", [(1, 2, 1)])
+def test_reference_streams_two_ranks_gloo_match_single_rank(rank_grid):
+    """The namelist's particles do not depend on the rank layout: a 2-rank run that creates its particles from the
+    reference's streams follows the 1-rank run (energies from step 0 on, every particle after 4 steps)."""
+    ret1 = {}
+    _run_rank_streams(0, 1, (1, 1, 1), 4, 0, ret1)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_run_rank_streams, args=(2, rank_grid, 4, _free_port(), ret), nprocs=2, join=True)
+    two = dict(ret)
+    for (it_a, uk_a, ue_a), (it_b, uk_b, ue_b) in zip(ret1["hist"], two["hist"]):
+        assert it_a == it_b
+        assert np.allclose(uk_a, uk_b, rtol=1e-11, atol=0)
+        assert abs(ue_a - ue_b) <= 1e-9 * abs(ue_a)
+    for ispec in range(2):
+        a = _canonical(ret1["parts"], ispec)
+        b = _canonical(two["parts"], ispec)
+        assert len(a["x"]) == len(b["x"]) == 16 ** 3 * 8
+        for k in a:
+            assert np.allclose(a[k], b[k], rtol=0, atol=1e-11), k
