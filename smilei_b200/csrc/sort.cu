@@ -151,8 +151,17 @@ __global__ void __launch_bounds__( 256 ) k_cell_sort( const int *__restrict__ fi
     for( int w = ( blockIdx.x*blockDim.x + threadIdx.x ) >> 5; w*32 < ncells; w += nwarps ) {
         const int c = w*32 + lane;
         const int cb = first[min( c, ncells )], ce = first[min( c+1, ncells )];
-        const int base = __shfl_sync( 0xffffffffu, cb, 0 ), end = __shfl_sync( 0xffffffffu, ce, 31 );
+        // the warp's 32 cells are taken in `nsub` sub-stretches of 32/nsub cells, so that a sub-stretch fits the
+        // shared-memory staging at any number of particles per cell (one pass up to SW entries, e.g. 16 per cell;
+        // four passes of ~512 entries at 64 per cell)
+        const int total = __shfl_sync( 0xffffffffu, ce, 31 ) - __shfl_sync( 0xffffffffu, cb, 0 );
+        int nsub = 1;
+        if( total > SW ) while( nsub < 32 && nsub*( SW/2 ) < total ) nsub <<= 1;
+        const int G = 32/nsub;
+      for( int sub = 0; sub < nsub; sub++ ) {
+        const int base = __shfl_sync( 0xffffffffu, cb, sub*G ), end = __shfl_sync( 0xffffffffu, ce, sub*G + G - 1 );
         const bool staged = end - base <= SW;
+        const bool member = lane >= sub*G && lane < sub*G + G;      // my cell belongs to this sub-stretch
         bool mybad = false;
         __syncwarp();
         if( staged ) {
@@ -175,7 +184,7 @@ __global__ void __launch_bounds__( 256 ) k_cell_sort( const int *__restrict__ fi
             const unsigned invmask = __ballot_sync( 0xffffffffu, inv );
             // does an inversion fall inside my own cell's run?
             const int lo = max( cb - j0, 0 ), hi = min( ce - j0, 32 );
-            if( invmask && hi > lo ) {
+            if( invmask && hi > lo && member ) {
                 const unsigned range = ( hi >= 32 ? 0xffffffffu : ( ( 1u << hi ) - 1u ) ) & ~( ( 1u << lo ) - 1u );
                 mybad = mybad || ( invmask & range ) != 0u;
             }
@@ -214,6 +223,8 @@ __global__ void __launch_bounds__( 256 ) k_cell_sort( const int *__restrict__ fi
         __syncwarp();
         if( staged )
             for( int q = lane; q < end - base; q += 32 ) perm[base + q] = sm[q + ( q >> 4 )];
+        __syncwarp();
+      }
     }
 }
 

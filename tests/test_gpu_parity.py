@@ -128,6 +128,34 @@ def test_sort_bit_exact(sb, orc, geom):
     p.close()
 
 
+@pytest.mark.parametrize("N,cluster", [(200000, 0), (60000, 3000)])
+def test_sort_bit_exact_dense_cells(sb, orc, N, cluster):
+    """Many particles per cell: a warp's 32 cells no longer fit one staged stretch of k_cell_sort and are taken in
+    sub-stretches (274 per cell: one cell per pass); `cluster` particles in ONE cell exceed the staging altogether
+    (insertion sort in global memory)."""
+    n, cell, dt = (8, 8, 8), (0.07, 0.07, 0.07), 0.038
+    g = ol.make_grid(n, 2, cell, dt)
+    p = make_patch(sb, n, 2, cell, dt, 1)
+    rng = np.random.default_rng(77 + cluster)
+    P = ol.random_particles(g, rng, N)
+    if cluster:
+        for i, c in enumerate("xyz"):
+            P[c][:cluster] = (3.0 + 0.2 * (rng.random(cluster) - 0.5)) * cell[i]
+    p.species_config(0, 1.0, "boris", N + 100)
+    p.species_set(0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+    p.sort(0)
+    ncells = 9 ** 3
+    keys = orc.cell_keys(g, P["x"], P["y"], P["z"])
+    first, perm = orc.counting_sort_perm(keys, ncells)
+    assert (np.diff(first).max() > 1024) == bool(cluster)
+    out = p.species_get(0)
+    assert np.array_equal(p.first_index(0), first)
+    assert np.array_equal(out["key"], keys[perm])
+    for k in ("x", "y", "z", "px", "py", "pz", "w", "q"):
+        assert np.array_equal(out[k], P[k][perm]), k
+    p.close()
+
+
 def test_sort_empty_and_single(sb):
     p = make_patch(sb, (8, 8, 8), 2, (0.1, 0.1, 0.1), 0.05, 1)
     p.species_config(0, 1.0, "boris", 16)
