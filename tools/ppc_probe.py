@@ -19,7 +19,10 @@ if __name__ == "__main__":
     from smilei_b200 import namelist
     from smilei_b200.simulation import Simulation
     T, dx, dt = bench.plasma_constants()
-    for ppc, ncell in (((2, 2, 2), 256), ((4, 2, 2), 200), ((4, 4, 2), 160), ((4, 4, 4), 128)):
+    cases = (((2, 2, 2), 256), ((4, 2, 2), 200), ((4, 4, 2), 160), ((4, 4, 4), 128))
+    if len(sys.argv) > 2:                  # one case: ppc as a,b,c and cells per dimension (e.g. under ncu)
+        cases = ((tuple(int(v) for v in sys.argv[1].split(",")), int(sys.argv[2])),)
+    for ppc, ncell in cases:
         params = namelist.load_namelist(bench.namelist_source([ncell] * 3, 2, "boris"), is_source=True)
         sim = Simulation(params, capacity_factor=1.08)
         sim.init_thermal(ppc, density=1.0, temperature=T, seed=0)
