@@ -123,8 +123,16 @@ __global__ void __launch_bounds__( 256 ) k_scatter_idx( const int *__restrict__ 
         int *__restrict__ cursor, int *__restrict__ perm, size_t n )
 {
     const int lane = threadIdx.x & 31;
-    const size_t nround = ( n + 31 )/32*32;
-    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < nround; i += ( size_t )gridDim.x*blockDim.x ) {
+    // a warp walks ONE contiguous chunk of the particle list, 32 at a time: its successive atomics on a cursor are
+    // served in program order (the shuffle below consumes each result before the next is issued), so the only cells
+    // that come out with swapped blocks are the few that straddle two chunks - not every cell that straddles two
+    // groups of 32 particles, as with a grid-stride loop
+    const size_t nblk = ( n + 31 )/32, nwarp = ( size_t )gridDim.x*( blockDim.x >> 5 );
+    const size_t per = ( nblk + nwarp - 1 )/nwarp;
+    const size_t b0 = ( blockIdx.x*( size_t )( blockDim.x >> 5 ) + ( threadIdx.x >> 5 ) )*per;
+    const size_t b1 = b0 + per < nblk ? b0 + per : nblk;
+    for( size_t b = b0; b < b1; b++ ) {
+        const size_t i = b*32 + lane;
         const int k = i < n ? key[i] : -1;
         const unsigned peers = __match_any_sync( 0xffffffffu, k );
         const int leader = __ffs( peers ) - 1;
