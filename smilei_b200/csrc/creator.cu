@@ -9,7 +9,6 @@
 #include "common.cuh"
 #include <cmath>
 #include <cstdint>
-#include <cstdio>
 #include <vector>
 
 namespace {
@@ -18,7 +17,7 @@ namespace {
 // Random (src/Tools/Random.h:91-140): xorshift32, zero seed replaced by 2^32-1
 struct Stream {
     uint32_t s;
-    explicit Stream( uint32_t seed ) : s( seed ? seed : 4294967295u ) {}
+    explicit Stream( uint32_t state ) : s( state ? state : 4294967295u ) {}   // also how a saved state is resumed (never 0)
     uint32_t next() { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
     double uniform()     { return next() * ( 1. / 4294967296. ); }              // ]0,1]
     double uniform2()    { return next() * ( 2. / 4294967296. ) - 1.; }         // ]-1,1]
@@ -173,8 +172,7 @@ int sb200_create_particles_ref( unsigned int *rng_state, int position_init, int 
         sb200::set_error( "sb200_create_particles_ref: maxwell-juettner needs temperature, the two tables and mass > 0" );
         return 1;
     }
-    Stream R( 1 );
-    R.s = *rng_state;                                       // the patch's stream goes on where the previous species left it
+    Stream R( *rng_state );                                 // the patch's stream goes on where the previous species left it
     double *pos[3] = { x, y, z };
     std::vector<double> energy;
     size_t ip = 0;
