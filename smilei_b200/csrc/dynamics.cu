@@ -9,13 +9,15 @@
 //   SpeciesV::computeParticleCellKeys                     Species/SpeciesV.cpp:796-812
 //   Projector3D2Order::currents / Projector3D4Order       Projector/Projector3D2Order.cpp:55-343, Projector3D4Order.cpp:49-233
 //
-// Design: one CTA per tile of TX x TY x TZ primal-node cells.  Because the
-// particles are sorted by cell key (z fastest), the tile's particles are TX*TY contiguous
-// runs.  The CTA stages the E and B_m stencil box of the tile in shared memory once, keeps a
-// private J accumulation box in shared memory, walks its particles one per thread, and
-// flushes the J box to HBM once with red.global.add.f64.  Particle traffic is the
-// algorithmic 110 B: read 7 doubles + 1 short, write 6 doubles + 1 int; Epart/Bpart/iold/
-// deltaold/invgf never exist in HBM unless SB200_DYN_KEEP_SCRATCH asks for them.
+// Design: one CTA per tile of 4 x 4 x 8 primal-node cells.  Because the particles are
+// sorted by cell key (z fastest), the tile's particles are 16 contiguous runs.  The CTA receives the E and
+// B_m stencil boxes of the tile by TMA (cp.async.bulk.tensor), keeps a private fixed-point J box in shared
+// memory and hands it to the TMA unit once (cp.reduce.async.bulk.tensor .add).  Order 2: k_dynamics_o2
+// (producer warps walk the particle stream, consumer warps form the per-cell current sums); order 4:
+// k_dynamics_cg (8-lane cell groups, shuffle transpose-reduction).  k_dynamics (one thread per particle, full
+// Esirkepov window) is compiled only with -DSB200_AB_KERNELS, for A/B checks.  Particle traffic is the
+// algorithmic 110 B: read 7 doubles + 1 short, write 6 doubles + 1 int; Epart/Bpart/iold/deltaold/invgf
+// never exist in HBM unless SB200_DYN_KEEP_SCRATCH asks for them.
 #include "common.cuh"
 #include <cuda.h>
 #include <cstdlib>
@@ -114,15 +116,11 @@ struct DynArgs {
     double *lost;             // accumulates w*(gamma-1) of the removed particles
 };
 
-// a particle tagged for exchange: count it per box side and remember its index.  sb200_leaving_pack no longer reads
-// the index list (it compacts the boundary layer of the side, halo.cu); the list write stays because without it
-// ptxas allocates k_dynamics_o2's 128 registers differently and the kernel runs 6 % slower (A/B inside one box:
-// 74.8 vs 79.1 ms per step at 256^3) — to be removed together with the next rework of that kernel's register pressure
+// a particle tagged for exchange is counted per box side (sb200_leaving_pack compacts the boundary layer of the
+// side itself, halo.cu: no index list is kept)
 __device__ __forceinline__ void note_leaver( const DynArgs &a, int tag, size_t ip )
 {
-    const int t = -tag-2;
-    const int c = atomicAdd( &a.leave_counts[t], 1 );
-    if( c < a.leave_cap ) a.leave_idx[( size_t )t*a.leave_cap + c] = ( int )ip;
+    atomicAdd( &a.leave_counts[-tag-2], 1 );
 }
 
 // PartBoundCond::apply on one particle (ParticleBC/PartBoundCond.h:38-76): the six boundary functions run in the
@@ -130,12 +128,13 @@ __device__ __forceinline__ void note_leaver( const DynArgs &a, int tag, size_t i
 // exchange only while its key is still >= 0; remove_particle_inf/sup (:204-294) act whatever the key is: key = -1,
 // charge = 0 (so the projector that follows deposits nothing) and w*(gamma-1) is added to the lost energy — once per
 // boundary the particle is beyond, as in the reference.
+template<bool REMOVE>
 __device__ __forceinline__ int boundary_tag( const DynArgs &a, const GridDev &g, const double *npos, double px, double py, double pz,
                                              double weight, size_t ip, bool &removed )
 {
     int tag = 0, nrem = 0;
     removed = false;
-    if( !a.any_remove ) {
+    if( !REMOVE ) {
         // all sides exchange (periodic box or inner patch): the first side the particle is beyond wins
 #pragma unroll
         for( int d=0; d<3; d++ ) {
@@ -160,6 +159,12 @@ __device__ __forceinline__ int boundary_tag( const DynArgs &a, const GridDev &g,
         a.q[ip] = 0;
     }
     return tag;
+}
+__device__ __forceinline__ int boundary_tag( const DynArgs &a, const GridDev &g, const double *npos, double px, double py, double pz,
+                                             double weight, size_t ip, bool &removed )
+{
+    return a.any_remove ? boundary_tag<true>( a, g, npos, px, py, pz, weight, ip, removed )
+                        : boundary_tag<false>( a, g, npos, px, py, pz, weight, ip, removed );
 }
 
 // separable gather of one component from its staged box: sum_i cx[i] sum_j cy[j] sum_k cz[k] F
@@ -340,6 +345,7 @@ __device__ __forceinline__ void esirkepov_general( jbox_t *jb, const double ( &S
     }
 }
 
+#ifdef SB200_AB_KERNELS
 template<int ORDER, int PUSHER, bool SCRATCH>
 __global__ void __launch_bounds__( DYN_THREADS ) k_dynamics( const GridDev g, const DynArgs a )
 {
@@ -536,6 +542,8 @@ static int launch_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int push
     }
 }
 
+#endif // SB200_AB_KERNELS
+
 // ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: raw PTX for sm_100a -----------------------------------
 struct FieldMaps { CUtensorMap m[6]; CUtensorMap j[3]; };   // Ex Ey Ez Bxm Bym Bzm boxes (FZ,FY,FX); Jx Jy Jz boxes (JZ,JY,JX)
 
@@ -654,7 +662,7 @@ __device__ __forceinline__ double pick( const double *w, int t )
 // starting at lo = (shift<0 ? 0 : 1): S0 on window points 1..NW, S1 on 1+shift..NW+shift.  Lanes 0..2 of
 // the group evaluate S0/DS of one dimension each into the group's scratch; then every lane takes its share
 // of the WX x WX transverse positions and the NW non-zero flux points (lo+1..lo+NW) of each component.
-template<int ORDER>
+template<int ORDER, int XQ = sb200::XQ>
 __device__ __forceinline__ void cross_pass( jbox_t *sJ, const double *xq, const int *xqm, double *xscr, int qh, int qn,
                                             int gl, int grp, double jscale )
 {
@@ -1105,49 +1113,109 @@ __global__ void __launch_bounds__( DYN_THREADS, CG<ORDER>::MINB ) k_dynamics_cg(
 
 
 // =================================================================================================
-// Order-2 production kernel: cell groups of FOUR lanes and a two-phase deposit.
+// Order-2 production kernel: a particle STREAM walked by producer warps, the per-cell
+// current sums formed by a consumer warp.
 //
-// The shuffle transpose-reduction of k_dynamics_cg costs more issue slots than the arithmetic it sums
-// (FSEL + SHFL were 20 % of all instructions).  Here the particles of a cell are still walked by one lane
-// group, but the per-cell sums are formed differently:
-//   phase 1  lane = one particle: gather, push, tag, key, new shape; the lane leaves what the deposit needs
-//            — per dimension M = (S0+S1)/2 and DS = S1-S0 on the 3 nodes, and the two flux coefficients per
-//            component — in a 24-double record of the warp's staging area in shared memory;
-//   phase 2  lane = one current COMPONENT of the cell (lanes 0..2 of the group): it walks the group's staged
-//            records and accumulates its 2 x 3 x 3 values in registers,
-//                J_c[f][j][k] += Cf_c[f] * ( M_a[j] M_b[k] + DS_a[j] DS_b[k] / 12 )
-//            (the Esirkepov weight S0S0 + (DS S0 + S0 DS)/2 + DS DS/3 rewritten around the mid-point shape).
-//            The registers persist over all rounds of the cell; 18 fixed-point adds per (cell, component)
-//            reach the J box when the cell is finished.  No shuffles, no selects, no redundant flops.
-// A lane group owns whole cells (cell = group + 64 m), so there is no search for the cell of a work item.
-// Particles that change cell stage zero flux coefficients and take the warp's crosser queue (cross_pass).
+// One CTA (320 threads) owns a tile of 4 x 4 x 8 primal-node cells.  The tile's 16 z-rows of 8 cells are split
+// between two GROUPS (x-slabs {0,1} and {2,3}); a group is 4 producer warps + 1 consumer warp.  Because the
+// particles are sorted by cell key with z fastest, the particles of a row are one contiguous run; the group's
+// stream is its 8 runs one after the other, and producer lane L of round r takes stream item 128 r + L: every
+// lane holds a particle whatever the cell occupancies are (no lock-step on the fullest cell of a warp), and a
+// warp's loads and stores are contiguous.
+//   producer  lane = one particle: gather, push, tag, key, new shape.  What the deposit needs — per dimension
+//             M = (S0+S1)/2 and DS/sqrt(12) on the 3 home nodes, the two flux coefficients per component
+//             (already in fixed-point units) — goes to a 26-double record in shared memory;
+//   consumer  lane = one current COMPONENT of one cell of the row being streamed (8 cells x 3 components): it
+//             walks the records of its cell in the window and accumulates its 2 x 3 x 3 values in registers,
+//                 J_c[f][j][k] += Cf_c[f] * ( M_a[j] M_b[k] + DS_a[j] DS_b[k] / 12 )
+//             (the Esirkepov weight S0S0 + (DS S0 + S0 DS)/2 + DS DS/3 around the mid-point shape); when its
+//             cell is exhausted the 18 sums go to the tile's J box (fixed-point adds) and the lane moves to
+//             the same z of the next row.
+// Producers and consumer hand the record buffer back and forth with two named barriers per group (FULL /
+// EMPTY); the buffer is single: the consumer reads round r while the producers gather and push round r+1,
+// and they only wait for EMPTY right before they write the records of round r+1.
+// A particle that moved to the next node in ONE dimension still deposits its home part through its record;
+// the 21 values that fall outside the home window are added by an 8-lane octet of its own warp, driven by a
+// table (value = C * (P*B0 + Q*B1), five record slots and a J-box offset per entry).  Particles that moved
+// in 2 or 3 dimensions stage zero flux coefficients and take the warp's queue (cross_pass).
 // =================================================================================================
 namespace o2 {
 using T = CG<2>::T;
-constexpr int G4 = 4;                                    // lanes per cell group
-constexpr int NGRP = DYN_THREADS/G4;                     // 64 groups per CTA
+constexpr int NW = 3;
+constexpr int NPROD = 256;                               // producer threads: 2 groups x 4 warps
+constexpr int NTHR = NPROD + 64;                         // + one consumer warp per group
+constexpr int GROUP = 128;                               // stream items per window = producer lanes of a group
+constexpr int GTHR = GROUP + 32;                         // threads meeting at a group's named barriers
 constexpr int NCELL = T::TX*T::TY*T::TZ;                 // 128 cells per tile
-constexpr int CELLS_PER_GROUP = NCELL/NGRP;
-static_assert( NCELL % NGRP == 0 && NCELL <= 256, "whole cells per lane group; cell ranks fit a byte" );
-constexpr int REC = 26;                                  // doubles per staged record: 24 used, padded so that the 4 records of a group fall in distinct banks
-constexpr int GSTAGE = G4*REC;                           // doubles per group
-constexpr int WSTAGE = 8*GSTAGE;                         // doubles per warp
-constexpr size_t BYTES = ( size_t )( 6*T::FBOX + 3*T::JBOX + WSTAGE*( DYN_THREADS/32 ) + XQD*( DYN_THREADS/32 ) )*sizeof( double );
+constexpr int GCELLS = NCELL/2;                          // cells per group (x-slabs {0,1} / {2,3})
+constexpr int ROWS = GCELLS/T::TZ;                       // 8 rows per group
+static_assert( T::TX == 4 && T::TY == 4 && T::TZ == 8, "the row / group arithmetic below is written for 4 x 4 x 8 tiles" );
+constexpr int REC = 26;                                  // doubles per record: 18 M/DS + 6 Cf + outer weight + outer flux coefficient
+// slot L of a group's record buffer; one 16-byte skew every 16 slots: with exactly 16 particles per cell the 8
+// lane quads of the consumer read slots 16 apart, which would otherwise all sit in the same banks
+__device__ __forceinline__ int rec_off( int L ) { return L*REC + 2*( L >> 4 ); }
+constexpr int RECBUF = GROUP*REC + 2*( GROUP/16 );       // doubles per group
+constexpr int XQ2 = 8;                                   // crosser queue entries per producer warp
+constexpr int XQD2 = 9*XQ2 + XQ2/2;
+constexpr int XSCR2 = 4*CGDim<2>::XSCR;                  // cross_pass scratch per producer warp (4 octets)
+constexpr int XTAB = 6*24;                               // outer-part table: (dimension, direction) x 24 items, one int2 each
+constexpr double K12 = 0.28867513459481288225;           // 1/sqrt(12)
+constexpr size_t BYTES = ( size_t )( 6*T::FBOX + 3*T::JBOX + 2*RECBUF + 8*XQD2 + 8*XSCR2 + XTAB )*sizeof( double );
 constexpr unsigned TMA_BYTES = 6u*T::FVOL*sizeof( double );
-static_assert( 4*CGDim<2>::XSCR <= WSTAGE, "the crosser scratch of a warp aliases its staging area" );
+
+__device__ __forceinline__ void bar_sync( int id, int nthreads ) { asm volatile( "bar.sync %0, %1;" :: "r"( id ), "r"( nthreads ) : "memory" ); }
+__device__ __forceinline__ void bar_arrive( int id, int nthreads ) { asm volatile( "bar.arrive %0, %1;" :: "r"( id ), "r"( nthreads ) : "memory" ); }
+
+// Interpolator3D2Order.h:107-123 in 5 operations: c2 - c0 = d exactly
+__device__ __forceinline__ void shape2( double d, double *c )
+{
+    const double t = fma( d, d, 0.25 );
+    c[0] = 0.5*( t - d );
+    c[1] = fma( -d, d, 0.75 );
+    c[2] = c[0] + d;
 }
 
-template<int PUSHER, bool SCRATCH>
-__global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev g, const DynArgs a, const __grid_constant__ FieldMaps tm )
+// entry `it` (0..23) of the outer-part table for a particle that moved to the next node along dimension d,
+// upwards (up = 1) or downwards.  Items 0..8: the flux component d at the flux point outside the home window,
+// on the 3 x 3 home nodes of the two other dimensions; items 9..20: 2 flux points x 3 nodes of each of the two
+// other components on the node plane outside the home window.  value = rec[iC] * ( cP rec[iP] rec[iB] + cQ rec[iQ] rec[iB+3] ).
+__device__ __forceinline__ int2 xtab_entry( int m, int it )
+{
+    const int d = m % 3, up = m / 3;
+    const int a1 = d == 0 ? 1 : 0, a2 = d == 2 ? 1 : 2;
+    const int st[3] = { T::JY*T::JZ, T::JZ, 1 };
+    int comp = 0, iC = 0, iP = 0, iQ = 0, iB = 0, isb = 0, off = 0, valid = 1;
+    if( it < 9 ) {
+        const int j = it/3, kk = it - 3*j;
+        comp = d; iC = 25; iP = 6*a1 + j; iQ = iP + 3; iB = 6*a2 + kk;
+        off = ( up ? 4 : 1 )*st[d] + ( 1+j )*st[a1] + ( 1+kk )*st[a2];
+    } else if( it < 21 ) {
+        const int t = it - 9, second = t >= 6 ? 1 : 0, u = t - 6*second, f = u/3, kk = u - 3*f;
+        const int bdim = second ? a1 : a2;
+        comp = second ? a2 : a1;
+        iC = 18 + 2*comp + f; iP = 24; iQ = 24; iB = 6*bdim + kk; isb = 1;
+        off = ( 2+f )*st[comp] + ( up ? 4 : 0 )*st[d] + ( 1+kk )*st[bdim];
+    } else valid = 0;
+    return make_int2( iC | ( iP << 5 ) | ( iQ << 10 ) | ( iB << 15 ) | ( isb << 20 ) | ( valid << 21 ), comp*T::JBOX + off );
+}
+}
+
+template<int PUSHER, bool SCRATCH, bool REMOVE>
+__global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g, const DynArgs a, const __grid_constant__ FieldMaps tm )
 {
     using namespace o2;
-    constexpr int NW = 3;
     extern __shared__ __align__( 128 ) double smem[];
     double *sF = smem;
     jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FBOX );
+    double *recbase = smem + 6*T::FBOX + 3*T::JBOX;
+    double *xqbase = recbase + 2*RECBUF;
+    double *xscrbase = xqbase + 8*XQD2;
+    int2 *xtab = reinterpret_cast<int2 *>( xscrbase + 8*XSCR2 );
     __shared__ __align__( 8 ) unsigned long long tma_bar;
     __shared__ int cell_first[NCELL];
     __shared__ int cell_cnt[NCELL];
+    __shared__ int cell_off[2][GCELLS+1];                // start of each cell in its group's stream
+    __shared__ unsigned short xsrc[8][32];               // per producer warp: the lanes holding a single-dimension mover
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -1181,8 +1249,10 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
         cell_first[tid] = beg;
         cell_cnt[tid] = cnt;
         mine = cnt;
+    } else if( tid - NCELL < XTAB ) {
+        xtab[tid - NCELL] = xtab_entry( ( tid - NCELL )/24, ( tid - NCELL )%24 );
     }
-    for( int t = tid; t < 3*T::JBOX; t += DYN_THREADS ) sJ[t] = 0ull;
+    for( int t = tid; t < 3*T::JBOX; t += NTHR ) sJ[t] = 0ull;
     const int any = __syncthreads_or( mine );
     tma_wait( &tma_bar, 0 );          // the boxes must have landed before this CTA's shared memory is used or released
     if( !any ) return;
@@ -1202,73 +1272,75 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
             for( size_t i = lo & ~( size_t )15; i <= hi; i += 16 ) asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.in[c] + i ) );
         asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.qin + lo ) );
     }
-    const int gl = lane & ( G4-1 );                       // lane in the group = particle slot (phase 1) = component (phase 2)
-    const int gw = lane >> 2;                             // group in the warp
-    double *wstage = smem + 6*T::FBOX + 3*T::JBOX + WSTAGE*warp;
-    double *rec = wstage + gw*GSTAGE + gl*REC;            // this lane's record (phase 1)
-    double *xscr = wstage + CGDim<2>::XSCR*( lane >> 3 ); // crosser scratch of the 8-lane group: aliases the staging area
-    double *xq = smem + 6*T::FBOX + 3*T::JBOX + WSTAGE*( DYN_THREADS/32 ) + XQD*warp;
-    int *xqm = reinterpret_cast<int *>( xq + 9*XQ );
-    int qh = 0, qn = 0;
+    // stream offsets of the cells: exclusive prefix sum of the 64 counts of each group (warp w < 2 scans group w)
+    if( warp < 2 ) {
+        const int a0 = cell_cnt[GCELLS*warp + 2*lane], a1 = cell_cnt[GCELLS*warp + 2*lane + 1];
+        int inc = a0 + a1;
+#pragma unroll
+        for( int d=1; d<32; d<<=1 ) { const int u = __shfl_up_sync( 0xffffffffu, inc, d ); if( lane >= d ) inc += u; }
+        cell_off[warp][2*lane] = inc - a0 - a1;
+        cell_off[warp][2*lane+1] = inc - a1;
+        if( lane == 31 ) cell_off[warp][GCELLS] = inc;
+    }
+    __syncthreads();
 
-    // phase-2 geometry of this lane: component c = gl (lane 3 idles), transverse dimensions (da, db)
-    const int cc = gl < 3 ? gl : 0;
-    const int da = cc == 0 ? 1 : 0, db = cc == 2 ? 1 : 2;
-    const double *p2a = wstage + gw*GSTAGE + 6*da, *p2b = wstage + gw*GSTAGE + 6*db, *p2c = wstage + gw*GSTAGE + 18 + 2*cc;
-    // J-box strides of the flux index and of the two transverse indices, and the offset of (f,j,k) = (0,0,0)
-    const int sf_ = cc == 0 ? T::JY*T::JZ : ( cc == 1 ? T::JZ : 1 );
-    const int sa_ = cc == 0 ? T::JZ : T::JY*T::JZ;
-    const int sb_ = cc == 2 ? T::JZ : 1;
-    const int jo_ = cc*T::JBOX + 2*sf_ + sa_ + sb_;
-
-#pragma unroll 1
-    for( int m = 0; m < CELLS_PER_GROUP; m++ ) {
-        const int cellt = m*NGRP + ( tid >> 2 );
-        const int cl[3] = { cellt / ( T::TZ*T::TY ), ( cellt / T::TZ ) % T::TY, cellt % T::TZ };
-        const int cnt = cell_cnt[cellt];
-        const size_t first = ( size_t )cell_first[cellt];
-        int nr = ( cnt + G4 - 1 )/G4;
-        nr = __reduce_max_sync( 0xffffffffu, nr );        // rounds of the warp's fullest cell
-        double acc[2][NW][NW];
-#pragma unroll
-        for( int f=0; f<2; f++ )
-#pragma unroll
-            for( int j=0; j<NW; j++ )
-#pragma unroll
-                for( int k=0; k<NW; k++ ) acc[f][j][k] = 0.;
+    if( warp < 8 ) {
+        // ============================================================ producers
+        const int grp = warp >> 2;
+        const int L = tid & ( GROUP-1 );
+        const int *coff = cell_off[grp];
+        const int total = coff[GCELLS];
+        const int nwin = ( total + GROUP - 1 )/GROUP;
+        double *recbuf = recbase + grp*RECBUF;
+        double *rec = recbuf + rec_off( L );
+        double *xq = xqbase + XQD2*warp;
+        int *xqm = reinterpret_cast<int *>( xq + 9*XQ2 );
+        double *xscr = xscrbase + XSCR2*warp + CGDim<2>::XSCR*( lane >> 3 );
+        const int full_id = 1 + 2*grp, empty_id = 2 + 2*grp;
+        const int base[3] = { g.begin[0] + g.o[0] + c0[0], g.begin[1] + g.o[1] + c0[1], g.begin[2] + g.o[2] + c0[2] };
+        int qh = 0, qn = 0, row = 0, bad = 0;
 
 #pragma unroll 1
-        for( int r = 0; r < nr; r++ ) {
-            const int slot = r*G4 + gl;
-            const bool active = slot < cnt;
-            const size_t ip = first + ( size_t )( active ? slot : 0 );
-            double cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
-            int shifts = 0, xmeta = 0;
-            double xe = 0., xc = 0.;
-            bool fast = false, one = false;
-            // ---------------- phase 1: one particle per lane
+        for( int r = 0; r < nwin; r++ ) {
+            const int s = r*GROUP + L;
+            const bool active = s < total;
+            double S0[3][NW], dl1[3] = { 0., 0., 0. }, cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
+            int shifts = 0x15, cellt = 0, nx = 0;
+            // ---------------- part A: gather, push, tag, key
             if( active ) {
+                while( s >= coff[T::TZ*( row+1 )] ) row++;
+                const size_t ip = ( size_t )cell_first[GCELLS*grp + T::TZ*row] + ( size_t )( s - coff[T::TZ*row] );
                 const size_t is = a.perm ? ( size_t )a.perm[ip] : ip;
                 double pos[3] = { a.in[0][is], a.in[1][is], a.in[2][is] };
                 double px = a.in[3][is], py = a.in[4][is], pz = a.in[5][is];
-                const double weight = a.in[6][is];
                 const short charge = a.qin[is];
-                if( a.perm ) { a.col[6][ip] = weight; a.q[ip] = charge; }
 
-                double S0[3][NW], cd[3][NW];
-                int sp[3], sd[3];
+                double cd[3][NW];
+                int sp[3], sd[3], cl[3];
 #pragma unroll
                 for( int d=0; d<3; d++ ) {
                     const double pn = __dmul_rn( pos[d], g.dxi[d] );       // no contraction into the subtraction below: deltaold is bit-exact
                     const int ipn = ( int )round( pn );
                     xdelta[d] = pn - ( double )ipn;
-                    Shape<2>::w( xdelta[d], S0[d] );
+                    shape2( xdelta[d], S0[d] );
                     const int idn = ( int )round( pn + 0.5 );
-                    const double dd = pn - ( double )idn + 0.5;
-                    Shape<2>::w( dd, cd[d] );
-                    if( ipn - g.begin[d] - g.o[d] - c0[d] != cl[d] ) atomicAdd( &a.iflags[1], 1 );
+                    shape2( pn - ( double )idn + 0.5, cd[d] );
+                    cl[d] = ipn - base[d];
+                    sd[d] = idn - ipn;
+                }
+                // the particle must sit in the row the stream says (its sort key): x and y of the row, z inside the tile
+                {
+                    const int lx = 2*grp + ( row >> 2 ), ly = row & 3;
+                    if( cl[0] != lx || cl[1] != ly || ( unsigned )cl[2] >= ( unsigned )T::TZ ) {
+                        bad++;
+                        cl[0] = lx; cl[1] = ly; cl[2] = cl[2] < 0 ? 0 : ( cl[2] >= T::TZ ? T::TZ-1 : cl[2] );
+                    }
+                }
+                cellt = ( cl[0]*T::TY + cl[1] )*T::TZ + cl[2];
+#pragma unroll
+                for( int d=0; d<3; d++ ) {
                     sp[d] = cl[d] + T::H + ( d == 2 ? zs : 0 );
-                    sd[d] = sp[d] + ( idn - ipn );
+                    sd[d] += sp[d];
                 }
                 const double Ex = gather<T>( sF+0*T::FBOX, cd[0], S0[1], S0[2], sd[0], sp[1], sp[2] );
                 const double Ey = gather<T>( sF+1*T::FBOX, S0[0], cd[1], S0[2], sp[0], sd[1], sp[2] );
@@ -1283,6 +1355,8 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
                 const double npos[3] = { pos[0] + dxp, pos[1] + dyp, pos[2] + dzp };
                 a.col[0][ip] = npos[0]; a.col[1][ip] = npos[1]; a.col[2][ip] = npos[2];
                 a.col[3][ip] = px; a.col[4][ip] = py; a.col[5][ip] = pz;
+                const double weight = a.in[6][is];
+                if( a.perm ) { a.col[6][ip] = weight; a.q[ip] = charge; }
                 if( SCRATCH ) {
                     a.sc_E[0*a.n+ip] = Ex; a.sc_E[1*a.n+ip] = Ey; a.sc_E[2*a.n+ip] = Ez;
                     a.sc_B[0*a.n+ip] = Bx; a.sc_B[1*a.n+ip] = By; a.sc_B[2*a.n+ip] = Bz;
@@ -1295,146 +1369,107 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
                 }
 
                 bool removed;
-                const int tag = boundary_tag( a, g, npos, px, py, pz, weight, ip, removed );
-                const double charge_weight = removed ? 0. : g.inv_cell_volume*( double )charge*weight;
+                const int tag = boundary_tag<REMOVE>( a, g, npos, px, py, pz, weight, ip, removed );
+                const double charge_weight = removed ? 0. : g.inv_cell_volume*( double )charge*weight*a.jscale;
                 cr[0] = charge_weight*g.d_ov_dt[0]; cr[1] = charge_weight*g.d_ov_dt[1]; cr[2] = charge_weight*g.d_ov_dt[2];
 
-                // new shape, next key; the record of the deposit: per dimension M[3], DS[3] on the HOME nodes
-                // (the 3 nodes of S0) and the flux coefficients at the 2 home flux points.  A particle that moved to
-                // the next node along a dimension has S1 shifted by one node: two of its three weights still fall on
-                // home nodes, the third (s1e) on the node just outside; the flux running sum (Projector3D2Order.cpp:
-                // 215-228) starts one node earlier when the shift is negative.
-                int nkey[3], nx = 0;
-                double cf[3][2];
+                int nkey[3];
+                shifts = 0;
 #pragma unroll
                 for( int d=0; d<3; d++ ) {
                     const double pn = __dmul_rn( npos[d], g.dxi[d] );
                     const int ipn = ( int )round( pn );
-                    double w1[NW];
-                    Shape<2>::w( pn - ( double )ipn, w1 );
-                    const int shift = ipn - g.begin[d] - ( cl[d] + c0[d] + g.o[d] );
+                    dl1[d] = pn - ( double )ipn;
+                    const int shift = ipn - base[d] - cl[d];
                     shifts |= ( shift+1 ) << ( 2*d );
+                    nx += shift != 0;
                     nkey[d] = ( int )( ( double )ipn - g.min_loc_round[d] );
                     xnpos[d] = pn;
+                }
+                int key = tag;
+                if( tag == 0 ) { key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2]; atomicAdd( &a.count[key], 1 ); }
+                else if( tag < -1 ) atomicAdd( &a.leave_counts[-tag-2], 1 );
+                a.key[ip] = key;
+            }
+            // ---------------- the consumer must have finished with the records of the previous round
+            bar_sync( empty_id, GTHR );
+            // ---------------- part B: new shape, the record of the deposit.  Per dimension M[3], DS[3]/sqrt(12) on
+            //                  the HOME nodes (the 3 nodes of S0) and the flux coefficients at the 2 home flux
+            //                  points.  A particle that moved to the next node along a dimension has S1 shifted by
+            //                  one node: two of its three weights still fall on home nodes, the third (s1e) on the
+            //                  node just outside; the flux running sum (Projector3D2Order.cpp:215-228) starts one
+            //                  node earlier when the shift is negative.
+            int xmeta = 0;
+            if( active ) {
+                const bool home = nx <= 1;           // the consumer deposits the home part; movers in 2+ dimensions go to the queue whole
+                double xe = 0., xc = 0.;
+#pragma unroll
+                for( int d=0; d<3; d++ ) {
+                    double w1[NW];
+                    shape2( dl1[d], w1 );
+                    const int shift = ( ( shifts >> ( 2*d ) ) & 3 ) - 1;
                     double s1a = w1[0], s1b = w1[1], s1c = w1[2], s1e = 0.;
                     if( shift > 0 ) { s1e = w1[2]; s1c = w1[1]; s1b = w1[0]; s1a = 0.; }
                     else if( shift < 0 ) { s1e = w1[0]; s1a = w1[1]; s1b = w1[2]; s1c = 0.; }
                     const double ds0 = s1a - S0[d][0], ds1 = s1b - S0[d][1], ds2 = s1c - S0[d][2];
                     double2 *r2 = reinterpret_cast<double2 *>( rec + 6*d );
-                    r2[0] = make_double2( S0[d][0] + 0.5*ds0, S0[d][1] + 0.5*ds1 );
-                    r2[1] = make_double2( S0[d][2] + 0.5*ds2, ds0 );
-                    r2[2] = make_double2( ds1, ds2 );
-                    cf[d][0] = -cr[d]*( ( shift < 0 ? s1e : 0. ) + ds0 );
-                    cf[d][1] = cf[d][0] - cr[d]*ds1;
+                    r2[0] = make_double2( fma( 0.5, ds0, S0[d][0] ), fma( 0.5, ds1, S0[d][1] ) );
+                    r2[1] = make_double2( fma( 0.5, ds2, S0[d][2] ), ds0*K12 );
+                    r2[2] = make_double2( ds1*K12, ds2*K12 );
+                    const double crd = home ? cr[d] : 0.;
+                    const double cf0 = -crd*( ( shift < 0 ? s1e : 0. ) + ds0 );
+                    const double cf1 = fma( -crd, ds1, cf0 );
+                    *reinterpret_cast<double2 *>( rec + 18 + 2*d ) = make_double2( cf0, cf1 );
                     if( shift != 0 ) {
-                        nx++;
-                        xmeta = d | ( shift > 0 ? 4 : 0 );
+                        xmeta = d + ( shift > 0 ? 3 : 0 );
                         xe = s1e;
-                        xc = shift > 0 ? cf[d][1] - cr[d]*ds2 : -cr[d]*s1e;     // flux coefficient at the point outside the home window
+                        xc = shift > 0 ? fma( -crd, ds2, cf1 ) : -crd*s1e;     // flux coefficient at the point outside the home window
                     }
                 }
-                int key = tag;
-                if( tag == 0 ) { key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2]; atomicAdd( &a.count[key], 1 ); }
-                else if( tag < -1 ) note_leaver( a, tag, ip );
-                a.key[ip] = key;
-                fast = nx == 0;
-                one = nx == 1;
-                const bool home = nx <= 1;           // phase 2 deposits the home part; particles that changed node in 2+ dimensions go to the queue whole
-                double2 *r2 = reinterpret_cast<double2 *>( rec + 18 );
-                r2[0] = home ? make_double2( cf[0][0], cf[0][1] ) : make_double2( 0., 0. );
-                r2[1] = home ? make_double2( cf[1][0], cf[1][1] ) : make_double2( 0., 0. );
-                r2[2] = home ? make_double2( cf[2][0], cf[2][1] ) : make_double2( 0., 0. );
-            } else {
-                double2 *r2 = reinterpret_cast<double2 *>( rec );
-#pragma unroll
-                for( int i=0; i<12; i++ ) r2[i] = make_double2( 0., 0. );
+                *reinterpret_cast<double2 *>( rec + 24 ) = make_double2( xe, xc );
             }
             __syncwarp();
-            // ---------------- phase 2: one current component of the cell per lane
-            if( gl < 3 ) {
-#pragma unroll
-                for( int pp=0; pp<G4; pp++ ) {
-                    const double2 *qa = reinterpret_cast<const double2 *>( p2a + pp*REC );
-                    const double2 *qb = reinterpret_cast<const double2 *>( p2b + pp*REC );
-                    const double2 a0 = qa[0], a1 = qa[1], a2 = qa[2];
-                    const double2 b0 = qb[0], b1 = qb[1], b2 = qb[2];
-                    const double2 cf = *reinterpret_cast<const double2 *>( p2c + pp*REC );
-                    const double Ma[NW] = { a0.x, a0.y, a1.x }, Da[NW] = { a1.y, a2.x, a2.y };
-                    const double Mb[NW] = { b0.x, b0.y, b1.x };
-                    const double twelfth = 1./12.;
-                    const double Db[NW] = { b1.y*twelfth, b2.x*twelfth, b2.y*twelfth };
-#pragma unroll
-                    for( int j=0; j<NW; j++ )
-#pragma unroll
-                        for( int k=0; k<NW; k++ ) {
-                            const double W = Ma[j]*Mb[k] + Da[j]*Db[k];
-                            acc[0][j][k] += cf.x*W;
-                            acc[1][j][k] += cf.y*W;
-                        }
-                }
-            }
-            __syncwarp();
-            // ---------------- particles that moved to the next node in ONE dimension: what falls outside the home
-            //                  window is 21 values — 9 of the flux component at the outer flux point, 2 x 3 of each
-            //                  other component on the outer node plane.  An 8-lane octet takes one such particle.
-            for( unsigned rem = __ballot_sync( 0xffffffffu, active && one ); rem; ) {
-                const unsigned srcu = __fns( rem, 0, ( lane >> 3 ) + 1 );
-                const bool work = srcu != 0xffffffffu;
-                const int src = work ? ( int )srcu : 0;
-                const int meta = __shfl_sync( 0xffffffffu, xmeta, src );
-                const double se = __shfl_sync( 0xffffffffu, xe, src );
-                const double cx = __shfl_sync( 0xffffffffu, xc, src );
-                const int cellx = __shfl_sync( 0xffffffffu, cellt, src );
-                if( work ) {
-                    const int d = meta & 3, up = meta >> 2;
-                    const int a1 = d == 0 ? 1 : 0, a2 = d == 2 ? 1 : 2;
-                    const int strd = d == 0 ? T::JY*T::JZ : ( d == 1 ? T::JZ : 1 );
-                    const int str1 = a1 == 0 ? T::JY*T::JZ : T::JZ;                 // a1 is x or y
-                    const int str2 = a2 == 1 ? T::JZ : 1;                           // a2 is y or z
-                    const double *rc = wstage + ( src >> 2 )*GSTAGE + ( src & 3 )*REC;
-                    jbox_t *jbx = sJ + zj + ( ( cellx / ( T::TZ*T::TY ) )*T::JY + ( cellx / T::TZ ) % T::TY )*T::JZ + cellx % T::TZ;
-                    const double twelfth = 1./12.;
+            bar_arrive( full_id, GTHR );
+            // ---------------- particles that moved to the next node in ONE dimension: the 21 values outside the
+            //                  home window, one particle per 8-lane octet, 3 passes of 8 table items
+            const bool one = active && nx == 1;
+            const unsigned rem = __ballot_sync( 0xffffffffu, one );
+            if( rem ) {
+                if( one ) xsrc[warp][__popc( rem & ( ( 1u << lane ) - 1u ) )] = ( unsigned short )( lane | ( xmeta << 5 ) | ( cellt << 8 ) );
+                __syncwarp();
+                const int n1 = __popc( rem );
+#pragma unroll 1
+                for( int k = lane >> 3; k < n1; k += 4 ) {
+                    const int e = xsrc[warp][k];
+                    const double *rc = recbuf + rec_off( ( L & ~31 ) + ( e & 31 ) );
+                    const int2 *tb = xtab + 24*( ( e >> 5 ) & 7 ) + ( lane & 7 );
+                    const int cx = e >> 8;
+                    jbox_t *jbx = sJ + zj + ( ( cx >> 5 )*T::JY + ( ( cx >> 3 ) & 3 ) )*T::JZ + ( cx & 7 );
 #pragma unroll
                     for( int h=0; h<3; h++ ) {
-                        const int it = ( lane & 7 ) + 8*h;
-                        if( it < 21 ) {
-                            int comp, bdim, kk, off;
-                            double C, P, Q;
-                            if( it < 9 ) {                           // flux component d at the outer flux point, home (j,k)
-                                const int j = it/3;
-                                kk = it - 3*j;
-                                comp = d; bdim = a2;
-                                C = cx; P = rc[6*a1 + j]; Q = rc[6*a1 + 3 + j];
-                                off = ( up ? 4 : 1 )*strd + ( 1+j )*str1 + ( 1+kk )*str2;
-                            } else {                                 // component a1 / a2 on the outer node plane of d
-                                const int t = it - 9;
-                                const int second = t >= 6 ? 1 : 0;
-                                const int u = t - 6*second;
-                                const int f = u/3;
-                                kk = u - 3*f;
-                                comp = second ? a2 : a1; bdim = second ? a1 : a2;
-                                C = rc[18 + 2*comp + f]; P = 0.5*se; Q = se;
-                                off = ( 2+f )*( second ? str2 : str1 ) + ( up ? 4 : 0 )*strd + ( 1+kk )*( second ? str1 : str2 );
-                            }
-                            const double W = P*rc[6*bdim + kk] + Q*( rc[6*bdim + 3 + kk]*twelfth );
-                            jadd( jbx + comp*T::JBOX + off, C*W, a.jscale );
+                        const int2 en = tb[8*h];
+                        if( en.x & ( 1 << 21 ) ) {
+                            const bool isb = en.x & ( 1 << 20 );
+                            const double C = rc[en.x & 31];
+                            const double P = rc[( en.x >> 5 ) & 31]*( isb ? 0.5 : 1.0 );
+                            const double Q = rc[( en.x >> 10 ) & 31]*( isb ? K12 : 1.0 );
+                            const double *bp = rc + ( ( en.x >> 15 ) & 31 );
+                            jadd_scaled( jbx + en.y, C*fma( P, bp[0], Q*bp[3] ) );
                         }
                     }
                 }
-#pragma unroll
-                for( int i=0; i<4; i++ ) rem &= rem - 1u;      // the four lowest set bits are done (x & (x-1) of 0 stays 0)
+                __syncwarp();
             }
-            __syncwarp();
             // ---------------- particles that moved in 2 or 3 dimensions: the warp's queue, 4 at a time (cross_pass)
-            unsigned xmask = __ballot_sync( 0xffffffffu, active && !fast && !one );
+            unsigned xmask = __ballot_sync( 0xffffffffu, active && nx > 1 );
             while( xmask ) {
-                const int room = XQ - qn;
+                const int room = XQ2 - qn;
                 const int rank = __popc( xmask & ( ( 1u << lane ) - 1u ) );
                 const bool mineq = ( ( xmask >> lane ) & 1u ) && rank < room;
                 if( mineq ) {
-                    const int e = ( qh + qn + rank ) % XQ;
+                    const int e = ( qh + qn + rank ) % XQ2;
 #pragma unroll
-                    for( int d=0; d<3; d++ ) { xq[( 0+d )*XQ+e] = xdelta[d]; xq[( 3+d )*XQ+e] = xnpos[d]; xq[( 6+d )*XQ+e] = cr[d]; }
+                    for( int d=0; d<3; d++ ) { xq[( 0+d )*XQ2+e] = xdelta[d]; xq[( 3+d )*XQ2+e] = xnpos[d]; xq[( 6+d )*XQ2+e] = cr[d]; }
                     xqm[e] = cellt | ( shifts << 16 );
                 }
                 const unsigned done = __ballot_sync( 0xffffffffu, mineq );
@@ -1442,34 +1477,104 @@ __global__ void __launch_bounds__( DYN_THREADS, 2 ) k_dynamics_o2( const GridDev
                 qn += __popc( done );
                 __syncwarp();
                 while( qn >= 4 || ( xmask && qn > 0 ) ) {
-                    cross_pass<2>( sJ + zj, xq, xqm, xscr, qh, qn, lane & 7, lane >> 3, a.jscale );
+                    cross_pass<2, XQ2>( sJ + zj, xq, xqm, xscr, qh, qn, lane & 7, lane >> 3, 1.0 );
                     const int took = qn < 4 ? qn : 4;
-                    qh = ( qh + took ) % XQ;
+                    qh = ( qh + took ) % XQ2;
                     qn -= took;
                 }
             }
         }
-        // ---------------- the cell is finished: its sums go to the J box
-        if( gl < 3 && cnt > 0 ) {
-            jbox_t *jb = sJ + zj + ( cl[0]*T::JY + cl[1] )*T::JZ + cl[2] + jo_;
-#pragma unroll
-            for( int f=0; f<2; f++ )
-#pragma unroll
-                for( int j=0; j<NW; j++ )
-#pragma unroll
-                    for( int k=0; k<NW; k++ ) jadd( jb + f*sf_ + j*sa_ + k*sb_, acc[f][j][k], a.jscale );
+        while( qn > 0 ) {
+            cross_pass<2, XQ2>( sJ + zj, xq, xqm, xscr, qh, qn, lane & 7, lane >> 3, 1.0 );
+            const int took = qn < 4 ? qn : 4;
+            qh = ( qh + took ) % XQ2;
+            qn -= took;
         }
-    }
-    while( qn > 0 ) {
-        cross_pass<2>( sJ + zj, xq, xqm, xscr, qh, qn, lane & 7, lane >> 3, a.jscale );
-        const int took = qn < 4 ? qn : 4;
-        qh = ( qh + took ) % XQ;
-        qn -= took;
+        if( bad ) atomicAdd( &a.iflags[1], bad );   // particles not in the cell their sort key says
+    } else {
+        // ============================================================ consumer of group warp-8
+        const int grp = warp - 8;
+        const int *coff = cell_off[grp];
+        const int total = coff[GCELLS];
+        const int nwin = ( total + GROUP - 1 )/GROUP;
+        const double *recbuf = recbase + grp*RECBUF;
+        const int full_id = 1 + 2*grp, empty_id = 2 + 2*grp;
+        const int c = lane >> 2;                               // z of this lane's cells
+        const bool wk = ( lane & 3 ) < 3;                      // lane 3 of a quad idles
+        const int cc = wk ? ( lane & 3 ) : 0;                  // current component
+        const int da = cc == 0 ? 1 : 0, db = cc == 2 ? 1 : 2;  // its transverse dimensions
+        const int oa = 6*da, ob = 6*db, oc = 18 + 2*cc;
+        // J-box strides of the flux index and of the two transverse indices, and the offset of (f,j,k) = (0,0,0)
+        const int sf_ = cc == 0 ? T::JY*T::JZ : ( cc == 1 ? T::JZ : 1 );
+        const int sa_ = cc == 0 ? T::JZ : T::JY*T::JZ;
+        const int sb_ = cc == 2 ? T::JZ : 1;
+        const int jo_ = cc*T::JBOX + 2*sf_ + sa_ + sb_;
+        double acc[2][NW][NW];
+#pragma unroll
+        for( int f=0; f<2; f++ )
+#pragma unroll
+            for( int j=0; j<NW; j++ )
+#pragma unroll
+                for( int k=0; k<NW; k++ ) acc[f][j][k] = 0.;
+        int rowc = 0, next = 0;                                // this lane's current row; stream position it has consumed up to
+        if( nwin > 0 ) bar_arrive( empty_id, GTHR );           // the record buffer starts out free
+#pragma unroll 1
+        for( int r = 0; r < nwin; r++ ) {
+            bar_sync( full_id, GTHR );
+            const int wlo = r*GROUP;
+            const int whi = min( wlo + GROUP, total );
+#pragma unroll 1
+            while( true ) {
+                int clo = 0, chi = 0;
+                if( rowc < ROWS ) { clo = coff[T::TZ*rowc + c]; chi = coff[T::TZ*rowc + c + 1]; }
+                int s = max( max( clo, wlo ), next );
+                const int hi = wk ? min( chi, whi ) : 0;
+                next = max( next, hi );
+#pragma unroll 1
+                while( __any_sync( 0xffffffffu, s < hi ) ) {
+                    if( s < hi ) {
+                        const double *rc = recbuf + rec_off( s - wlo );
+                        const double2 *qa = reinterpret_cast<const double2 *>( rc + oa );
+                        const double2 *qb = reinterpret_cast<const double2 *>( rc + ob );
+                        const double2 a0 = qa[0], a1 = qa[1], a2 = qa[2];
+                        const double2 b0 = qb[0], b1 = qb[1], b2 = qb[2];
+                        const double2 cf = *reinterpret_cast<const double2 *>( rc + oc );
+                        const double Ma[NW] = { a0.x, a0.y, a1.x }, Da[NW] = { a1.y, a2.x, a2.y };
+                        const double Mb[NW] = { b0.x, b0.y, b1.x }, Db[NW] = { b1.y, b2.x, b2.y };
+#pragma unroll
+                        for( int j=0; j<NW; j++ )
+#pragma unroll
+                            for( int k=0; k<NW; k++ ) {
+                                const double W = fma( Ma[j], Mb[k], Da[j]*Db[k] );
+                                acc[0][j][k] = fma( cf.x, W, acc[0][j][k] );
+                                acc[1][j][k] = fma( cf.y, W, acc[1][j][k] );
+                            }
+                    }
+                    s++;
+                }
+                const bool fin = rowc < ROWS && chi <= whi;       // this lane's cell is exhausted (or empty)
+                if( !__any_sync( 0xffffffffu, fin ) ) break;
+                if( fin ) {
+                    if( wk && chi > clo ) {
+                        jbox_t *jb = sJ + zj + ( ( 2*grp + ( rowc >> 2 ) )*T::JY + ( rowc & 3 ) )*T::JZ + c + jo_;
+#pragma unroll
+                        for( int f=0; f<2; f++ )
+#pragma unroll
+                            for( int j=0; j<NW; j++ )
+#pragma unroll
+                                for( int k=0; k<NW; k++ ) { jadd_scaled( jb + f*sf_ + j*sa_ + k*sb_, acc[f][j][k] ); acc[f][j][k] = 0.; }
+                    }
+                    rowc++;
+                }
+            }
+            if( r+1 < nwin ) bar_arrive( empty_id, GTHR );
+        }
     }
     __syncthreads();
 
-    // ---------------- flush the J box (as k_dynamics_cg)
-    for( int t = tid; t < 3*T::JBOX; t += DYN_THREADS ) {
+    // ---------------- flush the J box: convert the fixed-point sums to double in place, then ONE elected thread hands
+    //                  the three boxes to the TMA unit, which adds them into Jx, Jy, Jz in HBM
+    for( int t = tid; t < 3*T::JBOX; t += NTHR ) {
         const long long iv = ( long long )sJ[t];
         reinterpret_cast<double *>( sJ )[t] = ( double )iv*a.jinv;
     }
@@ -1535,27 +1640,34 @@ static int launch_cg( sb200_patch *p, const DynArgs &a, int ntiles )
     return 0;
 }
 
-template<int PUSHER, bool SCRATCH>
+template<int PUSHER, bool SCRATCH, bool REMOVE>
 static int launch_o2( sb200_patch *p, const DynArgs &a, int ntiles )
 {
     using T = o2::T;
     FieldMaps tm;
     if( field_maps( p, T::FX, T::FY, T::FZ, T::JX, T::JY, T::JZ, tm ) ) return 1;
-    auto kern = k_dynamics_o2<PUSHER, SCRATCH>;
+    auto kern = k_dynamics_o2<PUSHER, SCRATCH, REMOVE>;
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )o2::BYTES ) );
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
-    kern<<<ntiles, DYN_THREADS, o2::BYTES, p->stream>>>( p->gd, a, tm );
+    kern<<<ntiles, o2::NTHR, o2::BYTES, p->stream>>>( p->gd, a, tm );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
 }
 
+template<int PUSHER>
+static int launch_o2_flags( sb200_patch *p, const DynArgs &a, int ntiles, bool scratch )
+{
+    if( a.any_remove ) return scratch ? launch_o2<PUSHER, true, true>( p, a, ntiles ) : launch_o2<PUSHER, false, true>( p, a, ntiles );
+    return scratch ? launch_o2<PUSHER, true, false>( p, a, ntiles ) : launch_o2<PUSHER, false, false>( p, a, ntiles );
+}
+
 static int launch_o2_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int pusher, bool scratch )
 {
     switch( pusher ) {
-        case SB200_PUSHER_BORIS: return scratch ? launch_o2<SB200_PUSHER_BORIS, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_BORIS, false>( p, a, ntiles );
-        case SB200_PUSHER_VAY: return scratch ? launch_o2<SB200_PUSHER_VAY, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_VAY, false>( p, a, ntiles );
-        default: return scratch ? launch_o2<SB200_PUSHER_HIGUERACARY, true>( p, a, ntiles ) : launch_o2<SB200_PUSHER_HIGUERACARY, false>( p, a, ntiles );
+        case SB200_PUSHER_BORIS: return launch_o2_flags<SB200_PUSHER_BORIS>( p, a, ntiles, scratch );
+        case SB200_PUSHER_VAY: return launch_o2_flags<SB200_PUSHER_VAY>( p, a, ntiles, scratch );
+        default: return launch_o2_flags<SB200_PUSHER_HIGUERACARY>( p, a, ntiles, scratch );
     }
 }
 
@@ -1589,9 +1701,9 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
         SB200_CUDA( cudaMalloc( &p->sc_iold, 3*s.n*sizeof( int ) ) );
         p->sc_cap = s.n;
     }
-    // SB200_DYN_GENERAL=1 selects the general one-thread-per-particle kernel: A/B checks only
-    static const bool general = getenv( "SB200_DYN_GENERAL" ) != nullptr;
-    if( general && materialize( p, ispec ) ) return 1;
+#ifdef SB200_AB_KERNELS
+    if( materialize( p, ispec ) ) return 1;    // A/B build: the one-thread-per-particle kernel works in place
+#endif
     DynArgs a;
     const bool deferred = s.perm_pending;      // read through the pending sort order, write the sorted spare set
     if( deferred ) {
@@ -1634,23 +1746,20 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
         a.jscale = ldexp( 1.0, 61 - e );                // bound*jscale < 2^61
         a.jinv = ldexp( 1.0, e - 61 );
     }
-    if( !general ) {
-        if( g.order == 2 ) {
-            using T = CG<2>::T;
-            a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
-            a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
-            a.tiles[2] = ( g.ncell[2] + T::TZ - 1 )/T::TZ;
-            // SB200_DYN_CG=1: the shuffle-reduction kernel instead of the two-phase one (A/B checks only)
-            static const bool old_cg = getenv( "SB200_DYN_CG" ) != nullptr;
-            if( old_cg ) return launch_cg_pusher<2>( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
-            return launch_o2_pusher( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
-        }
-        using T = CG<4>::T;
+#ifndef SB200_AB_KERNELS
+    if( g.order == 2 ) {
+        using T = CG<2>::T;
         a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
         a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
         a.tiles[2] = ( g.ncell[2] + T::TZ - 1 )/T::TZ;
-        return launch_cg_pusher<4>( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
+        return launch_o2_pusher( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
     }
+    using T = CG<4>::T;
+    a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
+    a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
+    a.tiles[2] = ( g.ncell[2] + T::TZ - 1 )/T::TZ;
+    return launch_cg_pusher<4>( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
+#else
     using T = Tile<2>;                        // same tile footprint for both orders of the general kernel
     a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
     a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
@@ -1658,6 +1767,7 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     const int ntiles = a.tiles[0]*a.tiles[1]*a.tiles[2];
     if( g.order == 2 ) return launch_pusher<2>( p, a, ntiles, s.pusher, scratch );
     return launch_pusher<4>( p, a, ntiles, s.pusher, scratch );
+#endif
 }
 
 } // namespace sb200
