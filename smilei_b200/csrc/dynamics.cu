@@ -1163,8 +1163,25 @@ constexpr double K12 = 0.28867513459481288225;           // 1/sqrt(12)
 constexpr size_t BYTES = ( size_t )( 6*T::FBOX + 3*T::JBOX + 2*RECBUF + 8*XQD2 + 8*XSCR2 + XTAB )*sizeof( double );
 constexpr unsigned TMA_BYTES = 6u*T::FVOL*sizeof( double );
 
-__device__ __forceinline__ void bar_sync( int id, int nthreads ) { asm volatile( "bar.sync %0, %1;" :: "r"( id ), "r"( nthreads ) : "memory" ); }
-__device__ __forceinline__ void bar_arrive( int id, int nthreads ) { asm volatile( "bar.arrive %0, %1;" :: "r"( id ), "r"( nthreads ) : "memory" ); }
+__device__ __forceinline__ void mbar_arrive( unsigned long long *bar ) { asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"( smem_u32( bar ) ) : "memory" ); }
+
+// The windows of a group's stream, computed identically by every warp of the group: as many WHOLE cells as fit in
+// GROUP items, at most 8 (one per lane quad of the consumer, which then walks each cell in one go and never carries
+// a cell over a window boundary); a cell of more than GROUP items is taken in pieces.  ws/q0: first item / first cell
+// of the window; returns false when the stream is exhausted, else we (end item) and q1 (end cell; == q0 for a piece).
+__device__ __forceinline__ bool next_window( const int *coff, int total, int lane, int &ws, int &q0, int &we, int &q1 )
+{
+    while( ws < total ) {
+        const int qq = min( q0 + 1 + ( lane & 7 ), GCELLS );            // candidate ends q0+1 .. q0+8
+        const int nfit = __popc( __ballot_sync( 0xffffffffu, coff[qq] - ws <= GROUP ) & 0xffu );
+        if( nfit == 0 ) { q1 = q0; we = ws + GROUP; return true; }        // a piece of a very full cell
+        q1 = min( q0 + nfit, GCELLS );
+        we = coff[q1];
+        if( we > ws ) return true;
+        q0 = q1;                                                          // only empty cells: skip them
+    }
+    return false;
+}
 
 // Interpolator3D2Order.h:107-123 in 5 operations: c2 - c0 = d exactly
 __device__ __forceinline__ void shape2( double d, double *c )
@@ -1216,6 +1233,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
     __shared__ int cell_cnt[NCELL];
     __shared__ int cell_off[2][GCELLS+1];                // start of each cell in its group's stream
     __shared__ unsigned short xsrc[8][32];               // per producer warp: the lanes holding a single-dimension mover
+    __shared__ __align__( 8 ) unsigned long long full_bar[2], empty_bar[2];   // per group: records written (4 producer warps) / records consumed
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -1228,7 +1246,11 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
     const int zs = ( c0[2] + g.o[2] - T::H ) & 1;          // field boxes start on an even z index
     const int zj = ( c0[2] + g.o[2] - T::H - 1 ) & 1;      // J box too
 
-    if( tid == 0 ) tma_bar_init( &tma_bar, 1 );
+    if( tid == 0 ) {
+        tma_bar_init( &tma_bar, 1 );
+        tma_bar_init( &full_bar[0], 4 ); tma_bar_init( &full_bar[1], 4 );
+        tma_bar_init( &empty_bar[0], 1 ); tma_bar_init( &empty_bar[1], 1 );
+    }
     __syncthreads();
     if( tid == 0 ) {
         tma_expect( &tma_bar, TMA_BYTES );
@@ -1256,22 +1278,6 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
     const int any = __syncthreads_or( mine );
     tma_wait( &tma_bar, 0 );          // the boxes must have landed before this CTA's shared memory is used or released
     if( !any ) return;
-    // Pull the tile's particle columns into L2 while the CTA finishes its set-up: one thread per cell asks for
-    // the lines its cell's particles sit in (through the pending sort order their source slots are the old
-    // slots of the same particles, i.e. one short stretch per cell plus the few that moved in).
-    if( tid < NCELL && mine > 0 ) {
-        size_t lo = ( size_t )cell_first[tid], hi = lo + ( size_t )mine - 1;
-        if( a.perm ) {
-            const size_t p0 = ( size_t )a.perm[lo], p1 = ( size_t )a.perm[hi];
-            asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.perm + lo + 32 ) );
-            lo = p0 < p1 ? p0 : p1; hi = p0 < p1 ? p1 : p0;
-            if( hi - lo > 64 ) hi = lo + 64;                 // movers from far away: not worth chasing
-        }
-#pragma unroll
-        for( int c=0; c<7; c++ )
-            for( size_t i = lo & ~( size_t )15; i <= hi; i += 16 ) asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.in[c] + i ) );
-        asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.qin + lo ) );
-    }
     // stream offsets of the cells: exclusive prefix sum of the 64 counts of each group (warp w < 2 scans group w)
     if( warp < 2 ) {
         const int a0 = cell_cnt[GCELLS*warp + 2*lane], a1 = cell_cnt[GCELLS*warp + 2*lane + 1];
@@ -1290,25 +1296,25 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
         const int L = tid & ( GROUP-1 );
         const int *coff = cell_off[grp];
         const int total = coff[GCELLS];
-        const int nwin = ( total + GROUP - 1 )/GROUP;
         double *recbuf = recbase + grp*RECBUF;
         double *rec = recbuf + rec_off( L );
         double *xq = xqbase + XQD2*warp;
         int *xqm = reinterpret_cast<int *>( xq + 9*XQ2 );
         double *xscr = xscrbase + XSCR2*warp + CGDim<2>::XSCR*( lane >> 3 );
-        const int full_id = 1 + 2*grp, empty_id = 2 + 2*grp;
         const int base[3] = { g.begin[0] + g.o[0] + c0[0], g.begin[1] + g.o[1] + c0[1], g.begin[2] + g.o[2] + c0[2] };
-        int qh = 0, qn = 0, row = 0, bad = 0;
+        int qh = 0, qn = 0, bad = 0;
+        int ws = 0, q0 = 0, we, q1;
 
 #pragma unroll 1
-        for( int r = 0; r < nwin; r++ ) {
-            const int s = r*GROUP + L;
-            const bool active = s < total;
+        for( int r = 0; next_window( coff, total, lane, ws, q0, we, q1 ); r++, ws = we, q0 = q1 ) {
+            const int s = ws + L;
+            const bool active = s < we;
             double S0[3][NW], dl1[3] = { 0., 0., 0. }, cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
             int shifts = 0x15, cellt = 0, nx = 0;
             // ---------------- part A: gather, push, tag, key
             if( active ) {
-                while( s >= coff[T::TZ*( row+1 )] ) row++;
+                int row = q0 >> 3;                                      // the window's cells lie in at most two rows
+                row += s >= coff[T::TZ*( row+1 )];
                 const size_t ip = ( size_t )cell_first[GCELLS*grp + T::TZ*row] + ( size_t )( s - coff[T::TZ*row] );
                 const size_t is = a.perm ? ( size_t )a.perm[ip] : ip;
                 double pos[3] = { a.in[0][is], a.in[1][is], a.in[2][is] };
@@ -1392,7 +1398,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                 a.key[ip] = key;
             }
             // ---------------- the consumer must have finished with the records of the previous round
-            bar_sync( empty_id, GTHR );
+            if( r > 0 ) tma_wait( &empty_bar[grp], ( r-1 ) & 1 );
             // ---------------- part B: new shape, the record of the deposit.  Per dimension M[3], DS[3]/sqrt(12) on
             //                  the HOME nodes (the 3 nodes of S0) and the flux coefficients at the 2 home flux
             //                  points.  A particle that moved to the next node along a dimension has S1 shifted by
@@ -1429,7 +1435,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                 *reinterpret_cast<double2 *>( rec + 24 ) = make_double2( xe, xc );
             }
             __syncwarp();
-            bar_arrive( full_id, GTHR );
+            if( lane == 0 ) mbar_arrive( &full_bar[grp] );
             // ---------------- particles that moved to the next node in ONE dimension: the 21 values outside the
             //                  home window, one particle per 8-lane octet, 3 passes of 8 table items
             const bool one = active && nx == 1;
@@ -1496,9 +1502,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
         const int grp = warp - 8;
         const int *coff = cell_off[grp];
         const int total = coff[GCELLS];
-        const int nwin = ( total + GROUP - 1 )/GROUP;
         const double *recbuf = recbase + grp*RECBUF;
-        const int full_id = 1 + 2*grp, empty_id = 2 + 2*grp;
         const int c = lane >> 2;                               // z of this lane's cells
         const bool wk = ( lane & 3 ) < 3;                      // lane 3 of a quad idles
         const int cc = wk ? ( lane & 3 ) : 0;                  // current component
@@ -1516,58 +1520,75 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
             for( int j=0; j<NW; j++ )
 #pragma unroll
                 for( int k=0; k<NW; k++ ) acc[f][j][k] = 0.;
-        int rowc = 0, next = 0;                                // this lane's current row; stream position it has consumed up to
-        if( nwin > 0 ) bar_arrive( empty_id, GTHR );           // the record buffer starts out free
+        // Pull the group's particle columns into L2 while the producers work on the first window (this warp has
+        // nothing to consume yet): one lane per cell, in stream order, asks for the lines its cell's particles sit in
+        // (through the pending sort order their source slots are the old slots of the same particles, i.e. one
+        // short stretch per cell plus the few that moved in).
 #pragma unroll 1
-        for( int r = 0; r < nwin; r++ ) {
-            bar_sync( full_id, GTHR );
-            const int wlo = r*GROUP;
-            const int whi = min( wlo + GROUP, total );
-#pragma unroll 1
-            while( true ) {
-                int clo = 0, chi = 0;
-                if( rowc < ROWS ) { clo = coff[T::TZ*rowc + c]; chi = coff[T::TZ*rowc + c + 1]; }
-                int s = max( max( clo, wlo ), next );
-                const int hi = wk ? min( chi, whi ) : 0;
-                next = max( next, hi );
-#pragma unroll 1
-                while( __any_sync( 0xffffffffu, s < hi ) ) {
-                    if( s < hi ) {
-                        const double *rc = recbuf + rec_off( s - wlo );
-                        const double2 *qa = reinterpret_cast<const double2 *>( rc + oa );
-                        const double2 *qb = reinterpret_cast<const double2 *>( rc + ob );
-                        const double2 a0 = qa[0], a1 = qa[1], a2 = qa[2];
-                        const double2 b0 = qb[0], b1 = qb[1], b2 = qb[2];
-                        const double2 cf = *reinterpret_cast<const double2 *>( rc + oc );
-                        const double Ma[NW] = { a0.x, a0.y, a1.x }, Da[NW] = { a1.y, a2.x, a2.y };
-                        const double Mb[NW] = { b0.x, b0.y, b1.x }, Db[NW] = { b1.y, b2.x, b2.y };
-#pragma unroll
-                        for( int j=0; j<NW; j++ )
-#pragma unroll
-                            for( int k=0; k<NW; k++ ) {
-                                const double W = fma( Ma[j], Mb[k], Da[j]*Db[k] );
-                                acc[0][j][k] = fma( cf.x, W, acc[0][j][k] );
-                                acc[1][j][k] = fma( cf.y, W, acc[1][j][k] );
-                            }
-                    }
-                    s++;
-                }
-                const bool fin = rowc < ROWS && chi <= whi;       // this lane's cell is exhausted (or empty)
-                if( !__any_sync( 0xffffffffu, fin ) ) break;
-                if( fin ) {
-                    if( wk && chi > clo ) {
-                        jbox_t *jb = sJ + zj + ( ( 2*grp + ( rowc >> 2 ) )*T::JY + ( rowc & 3 ) )*T::JZ + c + jo_;
-#pragma unroll
-                        for( int f=0; f<2; f++ )
-#pragma unroll
-                            for( int j=0; j<NW; j++ )
-#pragma unroll
-                                for( int k=0; k<NW; k++ ) { jadd_scaled( jb + f*sf_ + j*sa_ + k*sb_, acc[f][j][k] ); acc[f][j][k] = 0.; }
-                    }
-                    rowc++;
-                }
+        for( int ct = GCELLS*grp + lane; ct < GCELLS*( grp+1 ); ct += 32 ) {
+            const int cnt = cell_cnt[ct];
+            if( cnt == 0 ) continue;
+            size_t lo = ( size_t )cell_first[ct], hi = lo + ( size_t )cnt - 1;
+            if( a.perm ) {
+                const size_t p0 = ( size_t )a.perm[lo], p1 = ( size_t )a.perm[hi];
+                asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.perm + lo + 32 ) );
+                lo = p0 < p1 ? p0 : p1; hi = p0 < p1 ? p1 : p0;
+                if( hi - lo > 64 ) hi = lo + 64;                 // movers from far away: not worth chasing
             }
-            if( r+1 < nwin ) bar_arrive( empty_id, GTHR );
+#pragma unroll 1
+            for( int c=0; c<7; c++ )
+                for( size_t i = lo & ~( size_t )15; i <= hi; i += 16 ) asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.in[c] + i ) );
+            asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.qin + lo ) );
+        }
+        int ws = 0, q0 = 0, we, q1;
+#pragma unroll 1
+        for( int r = 0; next_window( coff, total, lane, ws, q0, we, q1 ); r++, ws = we, q0 = q1 ) {
+            // this lane's cell of the window: the one with z = c among q0 .. q1-1 (the cell q0 alone when the window is a piece of it)
+            const int q = q0 + ( ( c - q0 ) & 7 );
+            const bool has = wk && q < max( q1, q0+1 );
+            int s = 0, hi = 0;
+            bool fin = false;
+            if( has ) {
+                const int chi = coff[q+1];
+                s = max( coff[q], ws ) - ws;
+                hi = min( chi, we ) - ws;
+                fin = chi <= we && hi > s;                     // the cell ends in this window: its sums go to the J box
+            }
+            tma_wait( &full_bar[grp], r & 1 );
+#pragma unroll 1
+            while( __any_sync( 0xffffffffu, s < hi ) ) {
+                if( s < hi ) {
+                    const double *rc = recbuf + rec_off( s );
+                    const double2 *qa = reinterpret_cast<const double2 *>( rc + oa );
+                    const double2 *qb = reinterpret_cast<const double2 *>( rc + ob );
+                    const double2 a0 = qa[0], a1 = qa[1], a2 = qa[2];
+                    const double2 b0 = qb[0], b1 = qb[1], b2 = qb[2];
+                    const double2 cf = *reinterpret_cast<const double2 *>( rc + oc );
+                    const double Ma[NW] = { a0.x, a0.y, a1.x }, Da[NW] = { a1.y, a2.x, a2.y };
+                    const double Mb[NW] = { b0.x, b0.y, b1.x }, Db[NW] = { b1.y, b2.x, b2.y };
+#pragma unroll
+                    for( int j=0; j<NW; j++ )
+#pragma unroll
+                        for( int k=0; k<NW; k++ ) {
+                            const double W = fma( Ma[j], Mb[k], Da[j]*Db[k] );
+                            acc[0][j][k] = fma( cf.x, W, acc[0][j][k] );
+                            acc[1][j][k] = fma( cf.y, W, acc[1][j][k] );
+                        }
+                }
+                s++;
+            }
+            __syncwarp();
+            if( lane == 0 ) mbar_arrive( &empty_bar[grp] );    // the producers may write the records of the next window
+            if( fin ) {
+                const int row = q >> 3;
+                jbox_t *jb = sJ + zj + ( ( 2*grp + ( row >> 2 ) )*T::JY + ( row & 3 ) )*T::JZ + c + jo_;
+#pragma unroll
+                for( int f=0; f<2; f++ )
+#pragma unroll
+                    for( int j=0; j<NW; j++ )
+#pragma unroll
+                        for( int k=0; k<NW; k++ ) { jadd_scaled( jb + f*sf_ + j*sa_ + k*sb_, acc[f][j][k] ); acc[f][j][k] = 0.; }
+            }
         }
     }
     __syncthreads();
