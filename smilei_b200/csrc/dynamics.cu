@@ -1303,21 +1303,36 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
         double *xscr = xscrbase + XSCR2*warp + CGDim<2>::XSCR*( lane >> 3 );
         const int base[3] = { g.begin[0] + g.o[0] + c0[0], g.begin[1] + g.o[1] + c0[1], g.begin[2] + g.o[2] + c0[2] };
         int qh = 0, qn = 0, bad = 0;
-        int ws = 0, q0 = 0, we, q1;
+        int ws = 0, q0 = 0, we = 0, q1 = 0;
+        // slot (in the sorted order) and source index (through the pending sort order) of this lane's particle in a
+        // window; looked up one window ahead so that the dependent load of the sort order is off the critical path
+        auto locate = [&]( int ws_, int q0_, int we_, int &row_, int &ip_, int &is_ ) {
+            const int s_ = ws_ + L;
+            row_ = q0_ >> 3;                                            // the window's cells lie in at most two rows
+            ip_ = -1; is_ = -1;
+            if( s_ < we_ ) {
+                row_ += s_ >= coff[T::TZ*( row_+1 )];
+                ip_ = cell_first[GCELLS*grp + T::TZ*row_] + ( s_ - coff[T::TZ*row_] );
+                is_ = a.perm ? a.perm[ip_] : ip_;
+            }
+        };
+        double pos[3] = { 0., 0., 0. };
+        bool more = next_window( coff, total, lane, ws, q0, we, q1 );
+        int row = 0, ipi = -1, isi = -1;
+        if( more ) locate( ws, q0, we, row, ipi, isi );
+        if( isi >= 0 ) { pos[0] = a.in[0][isi]; pos[1] = a.in[1][isi]; pos[2] = a.in[2][isi]; }
 
 #pragma unroll 1
-        for( int r = 0; next_window( coff, total, lane, ws, q0, we, q1 ); r++, ws = we, q0 = q1 ) {
-            const int s = ws + L;
-            const bool active = s < we;
+        for( int r = 0; more; r++ ) {
+            int nws = we, nq0 = q1, nwe = 0, nq1 = 0, nrow = 0, nip = -1, nis = -1;
+            const bool nmore = next_window( coff, total, lane, nws, nq0, nwe, nq1 );
+            if( nmore ) locate( nws, nq0, nwe, nrow, nip, nis );
+            const bool active = ipi >= 0;
             double S0[3][NW], dl1[3] = { 0., 0., 0. }, cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
             int shifts = 0x15, cellt = 0, nx = 0;
             // ---------------- part A: gather, push, tag, key
             if( active ) {
-                int row = q0 >> 3;                                      // the window's cells lie in at most two rows
-                row += s >= coff[T::TZ*( row+1 )];
-                const size_t ip = ( size_t )cell_first[GCELLS*grp + T::TZ*row] + ( size_t )( s - coff[T::TZ*row] );
-                const size_t is = a.perm ? ( size_t )a.perm[ip] : ip;
-                double pos[3] = { a.in[0][is], a.in[1][is], a.in[2][is] };
+                const size_t ip = ( size_t )ipi, is = ( size_t )isi;
                 double px = a.in[3][is], py = a.in[4][is], pz = a.in[5][is];
                 const short charge = a.qin[is];
 
@@ -1397,6 +1412,8 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                 else if( tag < -1 ) atomicAdd( &a.leave_counts[-tag-2], 1 );
                 a.key[ip] = key;
             }
+            // ---------------- the positions of the next window's particle: in flight during the rest of this round
+            if( nis >= 0 ) { pos[0] = a.in[0][nis]; pos[1] = a.in[1][nis]; pos[2] = a.in[2][nis]; }
             // ---------------- the consumer must have finished with the records of the previous round
             if( r > 0 ) tma_wait( &empty_bar[grp], ( r-1 ) & 1 );
             // ---------------- part B: new shape, the record of the deposit.  Per dimension M[3], DS[3]/sqrt(12) on
@@ -1411,16 +1428,17 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                 double xe = 0., xc = 0.;
 #pragma unroll
                 for( int d=0; d<3; d++ ) {
-                    double w1[NW];
+                    double w1[NW], s0[NW];
                     shape2( dl1[d], w1 );
+                    shape2( xdelta[d], s0 );                       // recomputed rather than kept in registers since the gather
                     const int shift = ( ( shifts >> ( 2*d ) ) & 3 ) - 1;
                     double s1a = w1[0], s1b = w1[1], s1c = w1[2], s1e = 0.;
                     if( shift > 0 ) { s1e = w1[2]; s1c = w1[1]; s1b = w1[0]; s1a = 0.; }
                     else if( shift < 0 ) { s1e = w1[0]; s1a = w1[1]; s1b = w1[2]; s1c = 0.; }
-                    const double ds0 = s1a - S0[d][0], ds1 = s1b - S0[d][1], ds2 = s1c - S0[d][2];
+                    const double ds0 = s1a - s0[0], ds1 = s1b - s0[1], ds2 = s1c - s0[2];
                     double2 *r2 = reinterpret_cast<double2 *>( rec + 6*d );
-                    r2[0] = make_double2( fma( 0.5, ds0, S0[d][0] ), fma( 0.5, ds1, S0[d][1] ) );
-                    r2[1] = make_double2( fma( 0.5, ds2, S0[d][2] ), ds0*K12 );
+                    r2[0] = make_double2( fma( 0.5, ds0, s0[0] ), fma( 0.5, ds1, s0[1] ) );
+                    r2[1] = make_double2( fma( 0.5, ds2, s0[2] ), ds0*K12 );
                     r2[2] = make_double2( ds1*K12, ds2*K12 );
                     const double crd = home ? cr[d] : 0.;
                     const double cf0 = -crd*( ( shift < 0 ? s1e : 0. ) + ds0 );
@@ -1489,6 +1507,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                     qn -= took;
                 }
             }
+            ws = nws; q0 = nq0; we = nwe; q1 = nq1; more = nmore; row = nrow; ipi = nip; isi = nis;
         }
         while( qn > 0 ) {
             cross_pass<2, XQ2>( sJ + zj, xq, xqm, xscr, qh, qn, lane & 7, lane >> 3, 1.0 );
@@ -1555,27 +1574,44 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                 fin = chi <= we && hi > s;                     // the cell ends in this window: its sums go to the J box
             }
             tma_wait( &full_bar[grp], r & 1 );
+            // software pipeline: the record of the next particle is loaded while the sums of this one are formed (its 28
+            // registers are free as soon as the nine W are known)
+            double2 a0, a1, a2, b0, b1, b2, cf;
+            a0 = a1 = a2 = b0 = b1 = b2 = cf = make_double2( 0., 0. );
+            if( s < hi ) {
+                const double *rc = recbuf + rec_off( s );
+                const double2 *qa = reinterpret_cast<const double2 *>( rc + oa );
+                const double2 *qb = reinterpret_cast<const double2 *>( rc + ob );
+                a0 = qa[0]; a1 = qa[1]; a2 = qa[2]; b0 = qb[0]; b1 = qb[1]; b2 = qb[2];
+                cf = *reinterpret_cast<const double2 *>( rc + oc );
+            }
 #pragma unroll 1
             while( __any_sync( 0xffffffffu, s < hi ) ) {
-                if( s < hi ) {
-                    const double *rc = recbuf + rec_off( s );
-                    const double2 *qa = reinterpret_cast<const double2 *>( rc + oa );
-                    const double2 *qb = reinterpret_cast<const double2 *>( rc + ob );
-                    const double2 a0 = qa[0], a1 = qa[1], a2 = qa[2];
-                    const double2 b0 = qb[0], b1 = qb[1], b2 = qb[2];
-                    const double2 cf = *reinterpret_cast<const double2 *>( rc + oc );
+                double W[NW][NW];
+                {
                     const double Ma[NW] = { a0.x, a0.y, a1.x }, Da[NW] = { a1.y, a2.x, a2.y };
                     const double Mb[NW] = { b0.x, b0.y, b1.x }, Db[NW] = { b1.y, b2.x, b2.y };
 #pragma unroll
                     for( int j=0; j<NW; j++ )
 #pragma unroll
-                        for( int k=0; k<NW; k++ ) {
-                            const double W = fma( Ma[j], Mb[k], Da[j]*Db[k] );
-                            acc[0][j][k] = fma( cf.x, W, acc[0][j][k] );
-                            acc[1][j][k] = fma( cf.y, W, acc[1][j][k] );
-                        }
+                        for( int k=0; k<NW; k++ ) W[j][k] = fma( Ma[j], Mb[k], Da[j]*Db[k] );
                 }
+                const double c0_ = s < hi ? cf.x : 0., c1_ = s < hi ? cf.y : 0.;     // a lane past its cell adds nothing
                 s++;
+                if( s < hi ) {
+                    const double *rc = recbuf + rec_off( s );
+                    const double2 *qa = reinterpret_cast<const double2 *>( rc + oa );
+                    const double2 *qb = reinterpret_cast<const double2 *>( rc + ob );
+                    a0 = qa[0]; a1 = qa[1]; a2 = qa[2]; b0 = qb[0]; b1 = qb[1]; b2 = qb[2];
+                    cf = *reinterpret_cast<const double2 *>( rc + oc );
+                }
+#pragma unroll
+                for( int j=0; j<NW; j++ )
+#pragma unroll
+                    for( int k=0; k<NW; k++ ) {
+                        acc[0][j][k] = fma( c0_, W[j][k], acc[0][j][k] );
+                        acc[1][j][k] = fma( c1_, W[j][k], acc[1][j][k] );
+                    }
             }
             __syncwarp();
             if( lane == 0 ) mbar_arrive( &empty_bar[grp] );    // the producers may write the records of the next window
