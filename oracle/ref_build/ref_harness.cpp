@@ -455,6 +455,79 @@ void ref_cell_keys( const orc_grid *g, const double *x, const double *y, const d
     free_ctx( c );
 }
 
+extern "C" char _ZTV8SpeciesV[];   /* vtable for SpeciesV (defined by the reference's SpeciesV.cpp) */
+
+/* ------------------------------------------------------------------------------
+ * The reference's OWN sort: SpeciesV::computeParticleCellKeys( params ) on the resident particles (those whose
+ * cell_keys entry is >= 0; tagged leavers carry a negative key, Species.cpp:757-775) followed by
+ * SpeciesV::sortParticles (SpeciesV.cpp:599-762) with the arrivals of the six neighbours in
+ * MPI_buffer_.partRecv[dim][side].  Inputs: n resident particles + tags (< 0: leaver), narr[6] arrivals given
+ * back to back in a*.  Outputs: the species after the sort (cap entries available), its cell keys and
+ * first_index (ncell entries) / last_index of the last cell.  Returns the particle count after the sort.
+ * ------------------------------------------------------------------------------ */
+int ref_sort( const orc_grid *g, int n,
+              const double *x, const double *y, const double *z, const double *px, const double *py, const double *pz,
+              const double *w, const short *q, const int *tags,
+              const int *narr, const double *ax, const double *ay, const double *az, const double *apx, const double *apy,
+              const double *apz, const double *aw, const short *aq,
+              int cap, double *ox, double *oy, double *oz, double *opx, double *opy, double *opz, double *ow, short *oq,
+              int *okeys, int *first_index )
+{
+    Ctx *c = make_ctx( g, 1., 1 );
+    SpeciesV &S = *c->species;
+    Params &P = *c->params;
+    P.keep_position_old = false;
+    S.nDim_particle = 3;
+    set_particles( c, x, y, z, px, py, pz, w, q, n );
+    Particles &p = *S.particles;
+    for( int i=0; i<n; i++ ) p.cell_keys[i] = tags[i] < 0 ? tags[i] : 0;
+    const unsigned int ncell = ( g->n[0]+1 )*( g->n[1]+1 )*( g->n[2]+1 );
+    new( &S.count ) std::vector<int>( ncell, 0 );
+    p.first_index.assign( ncell, 0 );
+    p.last_index.assign( ncell, 0 );
+    /* SpeciesV::computeParticleCellKeys( Params & ), SpeciesV.cpp:857-867: keys and counts of the resident particles */
+    S.SpeciesV::computeParticleCellKeys( P, &p, &p.cell_keys[0], &S.count[0], 0, n );
+    new( &S.MPI_buffer_.partRecv ) std::vector<std::vector<Particles *>>( 3, std::vector<Particles *>( 2, ( Particles * )NULL ) );
+    int off = 0;
+    for( int d=0; d<3; d++ ) {
+        for( int s=0; s<2; s++ ) {
+            Particles *b = new Particles();
+            const int m = narr[2*d+s];
+            b->initialize( m, 3, false );
+            const double *src[7] = { ax, ay, az, apx, apy, apz, aw };
+            for( int k=0; k<3; k++ ) {
+                if( m ) std::memcpy( b->Position[k].data(), src[k]+off, sizeof( double )*m );
+                if( m ) std::memcpy( b->Momentum[k].data(), src[3+k]+off, sizeof( double )*m );
+            }
+            if( m ) std::memcpy( b->Weight.data(), aw+off, sizeof( double )*m );
+            if( m ) std::memcpy( b->Charge.data(), aq+off, sizeof( short )*m );
+            b->cell_keys.assign( m, 0 );
+            S.MPI_buffer_.partRecv[d][s] = b;
+            off += m;
+        }
+    }
+    /* sortParticles calls computeParticleCellKeys through the vtable: the calloc'ed SpeciesV has none, so it is
+       given the class's own (Itanium ABI: the object's vptr points 2 words into _ZTV8SpeciesV) */
+    *reinterpret_cast<void **>( &S ) = reinterpret_cast<void *>( _ZTV8SpeciesV + 2*sizeof( void * ) );
+    S.SpeciesV::sortParticles( P );
+    const int nout = ( int )p.size();
+    if( nout <= cap ) {
+        double *dst[3] = { ox, oy, oz }, *dm[3] = { opx, opy, opz };
+        for( int k=0; k<3; k++ ) {
+            std::memcpy( dst[k], p.Position[k].data(), sizeof( double )*nout );
+            std::memcpy( dm[k], p.Momentum[k].data(), sizeof( double )*nout );
+        }
+        std::memcpy( ow, p.Weight.data(), sizeof( double )*nout );
+        std::memcpy( oq, p.Charge.data(), sizeof( short )*nout );
+        std::memcpy( okeys, p.cell_keys.data(), sizeof( int )*nout );
+        for( unsigned int ic=0; ic<ncell; ic++ ) first_index[ic] = p.first_index[ic];
+        first_index[ncell] = p.last_index[ncell-1];
+    }
+    for( int d=0; d<3; d++ ) for( int s=0; s<2; s++ ) delete S.MPI_buffer_.partRecv[d][s];
+    free_ctx( c );
+    return nout;
+}
+
 double ref_field_norm2( const orc_grid *g, const double *f, int dualx, int dualy, int dualz )
 {
     Ctx *c = make_ctx( g, 1., 1 );

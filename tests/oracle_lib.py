@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "libsmilei_oracle.so")
-REF_SO = os.path.join(ORACLE_DIR, "_ref", "libsmilei_ref.so")
+REF_SO = os.environ.get("SB200_REF_SO", os.path.join(ORACLE_DIR, "_ref", "libsmilei_ref.so"))
 REF_FAST_SO = os.path.join(ORACLE_DIR, "_ref", "libsmilei_ref_fast.so")
 
 
@@ -217,6 +217,34 @@ class Reference(_Ops):
 
     def time_maxwell(self, g, npatches, nsteps, nthreads):
         return self.lib.ref_time_maxwell(C.byref(g), npatches, nsteps, nthreads)
+
+    def sort(self, g, part, tags, arrivals=None):
+        """The reference's own SpeciesV::computeParticleCellKeys + SpeciesV::sortParticles (SpeciesV.cpp:599-762) on
+        the resident particles `part` (tags < 0: leavers, erased by the sort) with `arrivals` = six particle dicts
+        (xmin xmax ymin ymax zmin zmax neighbour, or None) in MPI_buffer_.partRecv.  Returns (particles after the
+        sort incl. 'key', first_index of ncell+1 entries)."""
+        cols = ("x", "y", "z", "px", "py", "pz", "w")
+        n = len(part["x"])
+        arrivals = arrivals or [None] * 6
+        narr = (C.c_int * 6)(*[0 if a is None else len(a["x"]) for a in arrivals])
+        na = sum(narr)
+        A = {k: np.ascontiguousarray(np.concatenate([a[k] for a in arrivals if a is not None] or [np.zeros(0)]))
+             for k in cols}
+        Aq = np.ascontiguousarray(np.concatenate([a["q"] for a in arrivals if a is not None] or
+                                                 [np.zeros(0, dtype=np.int16)]).astype(np.int16))
+        cap = n + na
+        out = {k: np.zeros(cap) for k in cols}
+        out["q"] = np.zeros(cap, dtype=np.int16)
+        out["key"] = np.zeros(cap, dtype=np.int32)
+        ncell = (g.n[0] + 1) * (g.n[1] + 1) * (g.n[2] + 1)
+        first = np.zeros(ncell + 1, dtype=np.int32)
+        tags = np.ascontiguousarray(tags, dtype=np.int32)
+        self.lib.ref_sort.restype = C.c_int
+        nout = self.lib.ref_sort(C.byref(g), n, *[_p(part[k]) for k in cols], _p(part["q"]), _p(tags), narr,
+                                 *[_p(A[k]) for k in cols], _p(Aq), cap, *[_p(out[k]) for k in cols], _p(out["q"]),
+                                 _p(out["key"]), _p(first))
+        assert 0 <= nout <= cap
+        return {k: v[:nout] for k, v in out.items()}, first
 
 
 # ---------------------------------------------------------------------------------------

@@ -156,6 +156,50 @@ def test_sort_bit_exact_dense_cells(sb, orc, N, cluster):
     p.close()
 
 
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("geom", range(len(GEOMS)))
+def test_sort_matches_reference_sortParticles(sb, geom):
+    """SURVEY a21 on the GPU path: one real step (the dynamics kernel tags the leavers), arrivals from the six
+    neighbours appended, then sb200_sort — against the reference's OWN SpeciesV::sortParticles (SpeciesV.cpp:599-762,
+    compiled from /root/reference into oracle/_ref) fed the same residents, tags and arrivals: identical first_index
+    and, per cell, the same multiset of particles (bit for bit; the order inside a cell is algorithm-dependent in
+    the reference's cycle sort)."""
+    ref = ol.Reference()
+    n, cell, dt, pc, npch = GEOMS[geom]
+    g = ol.make_grid(n, 2, cell, dt, pc, npch)
+    p = make_patch(sb, n, 2, cell, dt, 1, pc, npch)
+    rng = np.random.default_rng(900 + geom)
+    N = 30000
+    P = ol.random_particles(g, rng, N, p_scale=1.5, charge=-1)       # fast: a few per cent leave the patch
+    F = ol.random_fields(g, rng, scale=0.1)
+    for k, v in F.items():
+        p.field_set(k, v)
+    p.species_config(0, 1.0, "boris", 2 * N)
+    p.species_set(0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+    p.sort(0)
+    p.dynamics(0)
+    before = p.species_get(0)
+    n_leave = int((before["key"] < 0).sum())
+    assert n_leave > 50
+    arr = [ol.random_particles(g, rng, m) if m else None for m in (2 * n_leave // 5, 0, n_leave // 3, 70, 55, 130)]
+    for a in arr:
+        if a is not None:
+            p.species_append(0, a["x"], a["y"], a["z"], a["px"], a["py"], a["pz"], a["w"], a["q"])
+    p.sort(0)
+    after = p.species_get(0)
+    gfirst = p.first_index(0)
+    R, rfirst = ref.sort(g, before, before["key"], arr)
+    assert len(after["x"]) == len(R["x"]) == N - n_leave + sum(len(a["x"]) for a in arr if a is not None)
+    assert np.array_equal(gfirst, rfirst)
+
+    def cells(part, first):
+        cols = np.stack([part[k] for k in ("x", "y", "z", "px", "py", "pz", "w")] + [part["q"].astype(float)], axis=1)
+        return [blk[np.lexsort(blk.T[::-1])] for blk in (cols[first[c]:first[c + 1]] for c in range(len(first) - 1))]
+    for a, b in zip(cells(after, gfirst), cells(R, rfirst)):
+        assert np.array_equal(a, b)
+    p.close()
+
+
 def test_sort_empty_and_single(sb):
     p = make_patch(sb, (8, 8, 8), 2, (0.1, 0.1, 0.1), 0.05, 1)
     p.species_config(0, 1.0, "boris", 16)

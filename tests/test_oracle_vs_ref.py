@@ -251,3 +251,59 @@ def test_moved_window_origin(libs, order):
     ref.project(g, order, Jb, Pb["x"], Pb["y"], Pb["z"], Pb["q"], Pb["w"], iold, delta)
     for k in Ja:
         assert np.array_equal(Ja[k], Jb[k]), k
+
+
+def _sort_case(g, rng, N, n_leave, n_arr):
+    """Particles after a step: most still in the patch, n_leave tagged for exchange (negative key) anywhere in the
+    list, and arrivals from the six neighbours (inside the patch, as the reference's exchange delivers them)."""
+    P = ol.random_particles(g, rng, N)
+    tags = np.zeros(N, dtype=np.int32)
+    lv = rng.choice(N, n_leave, replace=False)
+    tags[lv] = -1 - rng.integers(0, 7, n_leave)
+    arr = []
+    for k in range(6):
+        m = int(n_arr[k])
+        a = ol.random_particles(g, rng, m) if m else None
+        arr.append(a)
+    return P, tags, arr
+
+
+def _cells_as_multisets(part, first):
+    """Per cell: the sorted tuple list of its particles (all columns) - order inside a cell is not specified."""
+    cols = np.stack([part[k] for k in ("x", "y", "z", "px", "py", "pz", "w")] + [part["q"].astype(float)], axis=1)
+    out = []
+    for c in range(len(first) - 1):
+        blk = cols[first[c]:first[c + 1]]
+        out.append(blk[np.lexsort(blk.T[::-1])])
+    return out
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("n_leave,n_arr", [(0, (0,) * 6), (700, (0,) * 6), (300, (90, 110, 0, 40, 70, 60)),
+                                           (50, (200, 150, 100, 120, 90, 80))])
+def test_sort_matches_reference_cycle_sort(libs, case, n_leave, n_arr):
+    """SURVEY a21: the reference's in-place cycle sort (SpeciesV::sortParticles, SpeciesV.cpp:599-762) called for
+    real — leavers erased, arrivals filling their holes (:669-697), fewer and more arrivals than leavers — against
+    the canonical order of this build (stable counting sort of residents followed by arrivals): identical
+    first_index, identical particle count, and per cell the same multiset of particles (the order inside a cell is
+    algorithm-dependent in the reference and not a specification; its cell_keys array is not moved with the
+    particles, Particles.cpp:813-830, so it is not an output)."""
+    orc, ref = libs
+    n, cell, dt, pc, npch = CASES[case]
+    g = ol.make_grid(n, 2, cell, dt, pc, npch)
+    rng = np.random.default_rng(500 + 10 * case + n_leave)
+    P, tags, arr = _sort_case(g, rng, 20000, n_leave, n_arr)
+    R, rfirst = ref.sort(g, P, tags, arr)
+    # this build's canonical sort: residents then arrivals (x then y then z, - then +), stable by key
+    cols = ("x", "y", "z", "px", "py", "pz", "w", "q")
+    allp = {k: np.concatenate([P[k]] + [a[k] for a in arr if a is not None]) for k in cols}
+    keys = np.concatenate([tags, np.zeros(sum(n_arr), dtype=np.int32)])
+    orc.cell_keys(g, np.ascontiguousarray(allp["x"]), np.ascontiguousarray(allp["y"]), np.ascontiguousarray(allp["z"]),
+                  keys=keys)
+    ncells = (n[0] + 1) * (n[1] + 1) * (n[2] + 1)
+    first, perm = orc.counting_sort_perm(keys, ncells)
+    mine = {k: allp[k][perm] for k in cols}
+    assert len(R["x"]) == len(perm) == 20000 - n_leave + sum(n_arr)
+    assert np.array_equal(rfirst, first)
+    for a, b in zip(_cells_as_multisets(R, rfirst), _cells_as_multisets(mine, first)):
+        assert np.array_equal(a, b)
