@@ -117,6 +117,18 @@ int  sb200_field_device_ptr( sb200_patch *p, int field_id, void **dev_ptr, int a
 /* ElectroMagn::restartRhoJ (src/ElectroMagn/ElectroMagn.cpp:402-408): Jx,Jy,Jz,rho <- 0. */
 int  sb200_restart_rhoJ( sb200_patch *p );
 
+/* ElectroMagn::Jx_s / Jy_s / Jz_s / rho_s of one species (src/ElectroMagn/ElectroMagn.h:129-141): the arrays a field
+ * diagnostic of that species asks for.  mask bit k (Jx_s Jy_s Jz_s rho_s) allocates / frees array k.  While a species
+ * owns an array, sb200_dynamics with SB200_DYN_DIAG_RHO deposits that component THERE instead of into the total
+ * (Projector3D2Order.cpp:756-763, Projector3D4Order.cpp:706-713); sb200_restart_rhoJ clears it
+ * (ElectroMagn::restartRhoJs, ElectroMagn.cpp:410-436).  The arrays are addressed by every sb200_field_* and sb200_halo_*
+ * call through the field id SB200_SPECIES_FIELD(ispec, k). */
+#define SB200_SPECIES_FIELD( ispec, k ) ( SB200_NFIELDS + 4*( ispec ) + ( k ) )
+int  sb200_species_diag_fields( sb200_patch *p, int ispec, int mask );
+/* ElectroMagn3D::computeTotalRhoJ (src/ElectroMagn/ElectroMagn3D.cpp:1753-1799): Jx Jy Jz rho += every species' own
+ * arrays (called after the species' dynamics on a diag step, VectorPatch.cpp: computeCharge / sumDensities). */
+int  sb200_compute_total_rhoJ( sb200_patch *p );
+
 #define SB200_DYN_KEEP_SCRATCH 1   /* also write Epart/Bpart/invgf/iold/deltaold (SmileiMPI.h:213-221) */
 #define SB200_DYN_DIAG_RHO     2   /* diag step: also deposit rho (Projector3D2Order.cpp:349-521)       */
 /* Species::dynamics for one species (src/Species/Species.cpp:524-875): fused

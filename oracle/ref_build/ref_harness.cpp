@@ -393,6 +393,45 @@ void ref_project_rho_o2( const orc_grid *g, double *Jx, double *Jy, double *Jz, 
     free_ctx( c );
 }
 
+/* currentsAndDensityWrapper with diag_flag = true, either order; with species_arrays != 0 the species owns
+ * Jx_s .. rho_s (Projector3D2Order.cpp:756-759, Projector3D4Order.cpp:706-709): the deposit goes there, the
+ * totals (Jx .. rho as handed in) are untouched until ElectroMagn3D::computeTotalRhoJ (ElectroMagn3D.cpp:1753)
+ * adds the species arrays into them.  Outputs: totals in Jx..rho, species arrays in sJx..srho. */
+void ref_project_rho_species( const orc_grid *g, int order, int species_arrays,
+                  double *Jx, double *Jy, double *Jz, double *rho,
+                  double *sJx, double *sJy, double *sJz, double *srho,
+                  const double *x, const double *y, const double *z,
+                  const short *q, const double *w, int nparts, int istart, int iend,
+                  const int *iold, const double *deltaold, int compute_total )
+{
+    Ctx *c = make_ctx( g, 1., 1 );
+    ElectroMagn3D &E = *c->em;
+    load( E.Jx_, Jx ); load( E.Jy_, Jy ); load( E.Jz_, Jz ); load( E.rho_, rho );
+    if( species_arrays ) {
+        std::vector<unsigned int> dp = E.dimPrim;
+        E.Jx_s[0] = new Field3D( dp, 0, false ); E.Jy_s[0] = new Field3D( dp, 1, false );
+        E.Jz_s[0] = new Field3D( dp, 2, false ); E.rho_s[0] = new Field3D( dp );
+        load( E.Jx_s[0], sJx ); load( E.Jy_s[0], sJy ); load( E.Jz_s[0], sJz ); load( E.rho_s[0], srho );
+    }
+    *const_cast<unsigned int *>( &E.n_species ) = 1;
+    set_particles( c, x, y, z, 0, 0, 0, w, q, nparts );
+    resize_scratch( c, nparts );
+    std::memcpy( c->smpi->dynamics_iold[0].data(), iold, sizeof( int )*3*nparts );
+    std::memcpy( c->smpi->dynamics_deltaold[0].data(), deltaold, sizeof( double )*3*nparts );
+    Projector *P = order == 2 ? ( Projector * )new Projector3D2Order( *c->params, c->patch )
+                              : ( Projector * )new Projector3D4Order( *c->params, c->patch );
+    P->currentsAndDensityWrapper( c->em, *c->species->particles, c->smpi, istart, iend, 0, true, false, 0 );
+    if( compute_total ) E.ElectroMagn3D::computeTotalRhoJ();
+    store( E.Jx_, Jx ); store( E.Jy_, Jy ); store( E.Jz_, Jz ); store( E.rho_, rho );
+    if( species_arrays ) {
+        store( E.Jx_s[0], sJx ); store( E.Jy_s[0], sJy ); store( E.Jz_s[0], sJz ); store( E.rho_s[0], srho );
+        delete E.Jx_s[0]; delete E.Jy_s[0]; delete E.Jz_s[0]; delete E.rho_s[0];
+        E.Jx_s[0] = E.Jy_s[0] = E.Jz_s[0] = E.rho_s[0] = NULL;
+    }
+    delete P;
+    free_ctx( c );
+}
+
 void ref_save_B( const orc_grid *g, const double *Bx, const double *By, const double *Bz,
                  double *Bxm, double *Bym, double *Bzm )
 {

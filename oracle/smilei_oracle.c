@@ -801,6 +801,137 @@ void orc_project_rho_o2( const orc_grid *g, double *Jx, double *Jy, double *Jz, 
     }
 }
 
+/* Projector3D4Order::currentsAndDensity, Projector/Projector3D4Order.cpp:239-432: the order-4 currents of
+ * `currents` in the same loop form plus rho on the 7-point window (S1 only). */
+void orc_project_rho_o4( const orc_grid *g, double *Jx, double *Jy, double *Jz, double *rho,
+                  const double *x, const double *y, const double *z,
+                  const short *q, const double *w, int nparts, int istart, int iend,
+                  const int *iold_, const double *deltaold_ )
+{
+    double d_inv[3], d_ov_dt[3], mn[3], mx[3];
+    int begin[3], p[3], d[3];
+    const double cell_volume = 1.0 * g->cell[0] * g->cell[1] * g->cell[2];
+    const double inv_cell_volume = 1. / cell_volume;
+    for( int i=0; i<3; i++ ) {
+        d_inv[i]   = 1.0/g->cell[i];
+        d_ov_dt[i] = g->cell[i] / g->dt;
+    }
+    orc_patch_bounds( g, mn, mx, begin );
+    orc_dims( g, p, d );
+    const int nprimy = p[1], nprimz = p[2];
+
+    for( int ipart=istart ; ipart<iend; ipart++ ) {
+        const int *iold = &iold_[ipart];
+        const double *deltaold = &deltaold_[ipart];
+        double charge_weight = inv_cell_volume * ( double )( q[ipart] )*w[ipart];
+        double crx_p = charge_weight*d_ov_dt[0];
+        double cry_p = charge_weight*d_ov_dt[1];
+        double crz_p = charge_weight*d_ov_dt[2];
+        double S0[3][7], S1[3][7], DS[3][7];
+        double tmpJx[7][7], tmpJy[7][7], tmpJz[7][7];
+        memset( S1, 0, sizeof( S1 ) );
+        memset( tmpJx, 0, sizeof( tmpJx ) );
+        memset( tmpJy, 0, sizeof( tmpJy ) );
+        memset( tmpJz, 0, sizeof( tmpJz ) );
+        const double pos[3] = { x[ipart], y[ipart], z[ipart] };
+        int po[3];
+        for( int c=0; c<3; c++ ) {                 /* :284-318 */
+            S0[c][0] = 0.;
+            w4( deltaold[c*nparts], &S0[c][1] );
+            S0[c][6] = 0.;
+        }
+        for( int c=0; c<3; c++ ) {                 /* :321-361 */
+            double pn = pos[c] * d_inv[c];
+            int ip = ( int )round( pn );
+            po[c] = iold[c*nparts];
+            int ip_m_ipo = ip-po[c]-begin[c];
+            w4( pn - ( double )ip, &S1[c][ip_m_ipo+1] );
+        }
+        for( unsigned int i=0; i < 7; i++ ) {
+            DS[0][i] = S1[0][i] - S0[0][i];
+            DS[1][i] = S1[1][i] - S0[1][i];
+            DS[2][i] = S1[2][i] - S0[2][i];
+        }
+        const double *Sx0 = S0[0], *Sy0 = S0[1], *Sz0 = S0[2];
+        const double *Sx1 = S1[0], *Sy1 = S1[1], *Sz1 = S1[2];
+        const double *DSx = DS[0], *DSy = DS[1], *DSz = DS[2];
+        int ipo = po[0]-3, jpo = po[1]-3, kpo = po[2]-3;       /* :373-377 */
+        int iloc, jloc, kloc, linindex;
+        for( unsigned int i=1 ; i<7 ; i++ ) {                  /* :382-393 */
+            iloc = i+ipo;
+            for( unsigned int j=0 ; j<7 ; j++ ) {
+                jloc = j+jpo;
+                for( unsigned int k=0 ; k<7 ; k++ ) {
+                    tmpJx[j][k] -= crx_p * DSx[i-1] * ( Sy0[j]*Sz0[k] + 0.5*DSy[j]*Sz0[k] + 0.5*DSz[k]*Sy0[j] + one_third*DSy[j]*DSz[k] );
+                    kloc = k+kpo;
+                    linindex = iloc*nprimz*nprimy+jloc*nprimz+kloc;
+                    Jx [linindex] += tmpJx[j][k];
+                }
+            }
+        }
+        for( unsigned int i=0 ; i<7 ; i++ ) {                  /* :396-407 */
+            iloc = i+ipo;
+            for( unsigned int j=1 ; j<7 ; j++ ) {
+                jloc = j+jpo;
+                for( unsigned int k=0 ; k<7 ; k++ ) {
+                    tmpJy[i][k] -= cry_p * DSy[j-1] * ( Sz0[k]*Sx0[i] + 0.5*DSz[k]*Sx0[i] + 0.5*DSx[i]*Sz0[k] + one_third*DSz[k]*DSx[i] );
+                    kloc = k+kpo;
+                    linindex = iloc*nprimz*( nprimy+1 )+jloc*nprimz+kloc;
+                    Jy [linindex] += tmpJy[i][k];
+                }
+            }
+        }
+        for( unsigned int i=0 ; i<7 ; i++ ) {                  /* :410-421 */
+            iloc = i+ipo;
+            for( unsigned int j=0 ; j<7 ; j++ ) {
+                jloc = j+jpo;
+                for( unsigned int k=1 ; k<7 ; k++ ) {
+                    tmpJz[i][j] -= crz_p * DSz[k-1] * ( Sx0[i]*Sy0[j] + 0.5*DSx[i]*Sy0[j] + 0.5*DSy[j]*Sx0[i] + one_third*DSx[i]*DSy[j] );
+                    kloc = k+kpo;
+                    linindex = iloc*( nprimz+1 )*nprimy+jloc*( nprimz+1 )+kloc;
+                    Jz [linindex] += tmpJz[i][j];
+                }
+            }
+        }
+        for( unsigned int i=0 ; i<7 ; i++ ) {                  /* :424-434 */
+            iloc = i+ipo;
+            for( unsigned int j=0 ; j<7 ; j++ ) {
+                jloc = j+jpo;
+                for( unsigned int k=0 ; k<7 ; k++ ) {
+                    kloc = k+kpo;
+                    linindex = iloc*nprimz*nprimy+jloc*nprimz+kloc;
+                    rho[linindex] += charge_weight * Sx1[i]*Sy1[j]*Sz1[k];
+                }
+            }
+        }
+    }
+}
+
+/* Projector3D{2,4}Order::currentsAndDensityWrapper with diag_flag = true (Projector3D2Order.cpp:753-763,
+ * Projector3D4Order.cpp:703-713): the arrays handed in are either the totals or the species' own Jx_s .. rho_s. */
+void orc_project_rho( const orc_grid *g, int order, double *Jx, double *Jy, double *Jz, double *rho,
+                  const double *x, const double *y, const double *z,
+                  const short *q, const double *w, int nparts, int istart, int iend,
+                  const int *iold, const double *deltaold )
+{
+    if( order == 2 ) orc_project_rho_o2( g, Jx, Jy, Jz, rho, x, y, z, q, w, nparts, istart, iend, iold, deltaold );
+    else orc_project_rho_o4( g, Jx, Jy, Jz, rho, x, y, z, q, w, nparts, istart, iend, iold, deltaold );
+}
+
+/* ElectroMagn3D::computeTotalRhoJ, ElectroMagn/ElectroMagn3D.cpp:1753-1799, one species: total += species array */
+void orc_compute_total_rhoJ( const orc_grid *g, double *Jx, double *Jy, double *Jz, double *rho,
+                             const double *Jx_s, const double *Jy_s, const double *Jz_s, const double *rho_s )
+{
+    double *tot[4] = { Jx, Jy, Jz, rho };
+    const double *sp[4] = { Jx_s, Jy_s, Jz_s, rho_s };
+    const int id[4] = { 0, 1, 2, 6 };       /* orc_field_size ids: Jx Jy Jz as Ex Ey Ez, rho all primal */
+    for( int a=0; a<4; a++ ) {
+        if( !sp[a] ) continue;
+        const size_t n = orc_field_size( g, id[a] );
+        for( size_t i=0; i<n; i++ ) tot[a][i] += sp[a][i];
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* a16-a19 Maxwell                                                            */
 /* ------------------------------------------------------------------------- */

@@ -81,6 +81,18 @@ void orc_project_rho_o2( const orc_grid *g, double *Jx, double *Jy, double *Jz, 
                   const double *x, const double *y, const double *z,
                   const short *q, const double *w, int nparts, int istart, int iend,
                   const int *iold, const double *deltaold );
+void orc_project_rho_o4( const orc_grid *g, double *Jx, double *Jy, double *Jz, double *rho,
+                  const double *x, const double *y, const double *z,
+                  const short *q, const double *w, int nparts, int istart, int iend,
+                  const int *iold, const double *deltaold );
+/* currentsAndDensityWrapper with diag_flag (either order); the arrays are the totals or the species' own */
+void orc_project_rho( const orc_grid *g, int order, double *Jx, double *Jy, double *Jz, double *rho,
+                  const double *x, const double *y, const double *z,
+                  const short *q, const double *w, int nparts, int istart, int iend,
+                  const int *iold, const double *deltaold );
+/* ElectroMagn3D::computeTotalRhoJ for one species (null arrays are skipped) */
+void orc_compute_total_rhoJ( const orc_grid *g, double *Jx, double *Jy, double *Jz, double *rho,
+                             const double *Jx_s, const double *Jy_s, const double *Jz_s, const double *rho_s );
 
 /* a16-a19 Maxwell */
 void orc_save_B( const orc_grid *g, const double *Bx, const double *By, const double *Bz,

@@ -16,6 +16,19 @@ FIELDS = ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm", "Jx", "Jy", "
 FIELD_ID = {name: i for i, name in enumerate(FIELDS)}
 # namelist aliases (src/ElectroMagn/ElectroMagn.h:163-190)
 FIELD_ID.update({"Bx_m": FIELD_ID["Bxm"], "By_m": FIELD_ID["Bym"], "Bz_m": FIELD_ID["Bzm"], "Rho": FIELD_ID["rho"]})
+SPECIES_FIELDS = ("Jx", "Jy", "Jz", "rho")
+
+
+def field_id(name):
+    """Field id of a name: one of FIELDS (or a namelist alias), or a species' own array written ("Jx", ispec) /
+    "Jx_s<ispec>" (SB200_SPECIES_FIELD of include/smilei_b200.h; ElectroMagn::Jx_s .. rho_s)."""
+    if isinstance(name, tuple):
+        return len(FIELDS) + 4 * int(name[1]) + SPECIES_FIELDS.index(name[0])
+    if "_s" in name and name.split("_s")[0] in SPECIES_FIELDS and name.split("_s")[1].isdigit():
+        return len(FIELDS) + 4 * int(name.split("_s")[1]) + SPECIES_FIELDS.index(name.split("_s")[0])
+    return FIELD_ID[name]
+
+
 PUSHERS = {"boris": 0, "vay": 1, "higueracary": 2}
 PBC = {"periodic": 0, "remove": 1}
 DYN_KEEP_SCRATCH = 1
@@ -34,7 +47,7 @@ SYMBOLS = (
     "sb200_halo_exchange_self", "sb200_leaving_count", "sb200_leaving_pack", "sb200_leaving_pack_known", "sb200_arriving_unpack",
     "sb200_debug_flags", "sb200_species_init_thermal", "sb200_launch_count",
     "sb200_species_set_bc", "sb200_species_lost_energy", "sb200_apply_SM", "sb200_window_shift", "sb200_species_append",
-    "sb200_hilbert_index3d", "sb200_create_particles_ref",
+    "sb200_hilbert_index3d", "sb200_create_particles_ref", "sb200_species_diag_fields", "sb200_compute_total_rhoJ",
 )
 
 
@@ -258,27 +271,36 @@ class Patch:
     def field_dims(self, name):
         dims = (C.c_int * 3)()
         n = C.c_size_t(0)
-        _check(lib().sb200_field_size(self._h, FIELD_ID[name], C.byref(n), dims), "sb200_field_size")
+        _check(lib().sb200_field_size(self._h, field_id(name), C.byref(n), dims), "sb200_field_size")
         return tuple(dims)
 
     def field_set(self, name, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
-        _check(lib().sb200_field_set(self._h, FIELD_ID[name], _p(a, np.float64), C.c_size_t(a.size)),
+        _check(lib().sb200_field_set(self._h, field_id(name), _p(a, np.float64), C.c_size_t(a.size)),
                "sb200_field_set")
 
     def field_get(self, name):
         a = np.empty(self.field_dims(name))
-        _check(lib().sb200_field_get(self._h, FIELD_ID[name], _p(a, np.float64), C.c_size_t(a.size)),
+        _check(lib().sb200_field_get(self._h, field_id(name), _p(a, np.float64), C.c_size_t(a.size)),
                "sb200_field_get")
         return a
 
     def field_device_ptr(self, name):
         ptr = C.c_void_p()
         alloc = (C.c_int * 3)()
-        _check(lib().sb200_field_device_ptr(self._h, FIELD_ID[name], C.byref(ptr), alloc), "sb200_field_device_ptr")
+        _check(lib().sb200_field_device_ptr(self._h, field_id(name), C.byref(ptr), alloc), "sb200_field_device_ptr")
         return ptr.value, tuple(alloc)
 
     # -- time step
+    def species_diag_fields(self, ispec, Jx=True, Jy=True, Jz=True, rho=True):
+        """The species' own Jx_s / Jy_s / Jz_s / rho_s (what a DiagFields of that species asks for): diag-step deposits
+        of this species go there; field_get(("Jx", ispec)) reads them."""
+        mask = int(bool(Jx)) | int(bool(Jy)) << 1 | int(bool(Jz)) << 2 | int(bool(rho)) << 3
+        _check(lib().sb200_species_diag_fields(self._h, ispec, mask), "sb200_species_diag_fields")
+
+    def compute_total_rhoJ(self):
+        _check(lib().sb200_compute_total_rhoJ(self._h), "sb200_compute_total_rhoJ")
+
     def restart_rhoJ(self):
         _check(lib().sb200_restart_rhoJ(self._h), "sb200_restart_rhoJ")
 
@@ -318,22 +340,22 @@ class Patch:
     # -- halos (device buffers are raw pointers: torch tensors' data_ptr())
     def halo_plane_elems(self, name, dim):
         n = C.c_size_t(0)
-        _check(lib().sb200_halo_plane_elems(self._h, FIELD_ID[name], dim, C.byref(n)), "sb200_halo_plane_elems")
+        _check(lib().sb200_halo_plane_elems(self._h, field_id(name), dim, C.byref(n)), "sb200_halo_plane_elems")
         return n.value
 
     def halo_pack(self, name, dim, first_plane, nplanes, dev_ptr):
-        _check(lib().sb200_halo_pack(self._h, FIELD_ID[name], dim, first_plane, nplanes, C.c_void_p(dev_ptr)),
+        _check(lib().sb200_halo_pack(self._h, field_id(name), dim, first_plane, nplanes, C.c_void_p(dev_ptr)),
                "sb200_halo_pack")
 
     def halo_unpack(self, name, dim, first_plane, nplanes, dev_ptr, mode):
-        _check(lib().sb200_halo_unpack(self._h, FIELD_ID[name], dim, first_plane, nplanes, C.c_void_p(dev_ptr), mode),
+        _check(lib().sb200_halo_unpack(self._h, field_id(name), dim, first_plane, nplanes, C.c_void_p(dev_ptr), mode),
                "sb200_halo_unpack")
 
     def halo_sum_self(self, name, dim):
-        _check(lib().sb200_halo_sum_self(self._h, FIELD_ID[name], dim), "sb200_halo_sum_self")
+        _check(lib().sb200_halo_sum_self(self._h, field_id(name), dim), "sb200_halo_sum_self")
 
     def halo_exchange_self(self, name, dim):
-        _check(lib().sb200_halo_exchange_self(self._h, FIELD_ID[name], dim), "sb200_halo_exchange_self")
+        _check(lib().sb200_halo_exchange_self(self._h, field_id(name), dim), "sb200_halo_exchange_self")
 
     # -- particle migration
     def leaving_count(self, ispec):

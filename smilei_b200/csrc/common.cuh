@@ -41,6 +41,8 @@ struct GridDev {
 // dual flags per field id (ElectroMagn3D.cpp:115-123)
 __host__ __device__ inline int field_dual( int id, int dim )
 {
+    // a species' own Jx_s Jy_s Jz_s rho_s (SB200_SPECIES_FIELD) are shaped like Jx Jy Jz rho
+    if( id >= SB200_NFIELDS ) id = SB200_JX + ( id - SB200_NFIELDS ) % 4;
     // E/J: dual along own direction; B/Bm: primal along own direction, dual elsewhere
     switch( id ) {
         case SB200_EX: case SB200_JX: return dim==0;
@@ -80,6 +82,9 @@ struct SpeciesDev {
     int    *perm = nullptr;
     size_t perm_cap = 0;
     bool   perm_pending = false;
+    // the species' own Jx_s Jy_s Jz_s rho_s (ElectroMagn::Jx_s .. rho_s): allocated on request, the target of the
+    // deposit on diag steps (Projector3D2Order.cpp:756-759), nullptr = deposit into the totals
+    double *fs[4] = { nullptr, nullptr, nullptr, nullptr };
 };
 
 struct ParticleBuf {               // spare SoA set the sort scatters into, then swaps with the species
@@ -128,6 +133,15 @@ struct sb200_patch {
 };
 
 namespace sb200 {
+// device array of a field id: one of the 13 patch fields or a species' own array (SB200_SPECIES_FIELD); nullptr if
+// the id is out of range or the species array was not requested
+inline double *field_ptr( sb200_patch *p, int id )
+{
+    if( !p || id < 0 ) return nullptr;
+    if( id < SB200_NFIELDS ) return p->f[id];
+    const int is = ( id - SB200_NFIELDS )/4;
+    return is < p->nspec ? p->sp[is].fs[( id - SB200_NFIELDS ) % 4] : nullptr;
+}
 // implemented across the .cu files; all enqueue on p->stream
 int launch_maxwell( sb200_patch *p );
 int launch_center_shell( sb200_patch *p );

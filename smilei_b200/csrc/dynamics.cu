@@ -1647,7 +1647,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
 
 // Tensor maps of the six gathered fields for a given box: element (k,j,i) innermost first, row pitch AZ*8 B
 // (a multiple of 128 B by construction of the padded layout), out-of-bounds elements read as zero.
-static int field_maps( sb200_patch *p, int fx, int fy, int fz, int jx, int jy, int jz, FieldMaps &out )
+static int field_maps( sb200_patch *p, double *const *J, int fx, int fy, int fz, int jx, int jy, int jz, FieldMaps &out )
 {
     typedef CUresult ( *encode_t )( CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1674,7 +1674,7 @@ static int field_maps( sb200_patch *p, int fx, int fy, int fz, int jx, int jy, i
     }
     const cuuint32_t jbox[3] = { ( cuuint32_t )jz, ( cuuint32_t )jy, ( cuuint32_t )jx };
     for( int c=0; c<3; c++ ) {
-        const CUresult r = encode( &out.j[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p->f[SB200_JX+c], dims, strides, jbox, estr,
+        const CUresult r = encode( &out.j[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, J[c], dims, strides, jbox, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
         SB200_CHECK( r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for a J box" );
@@ -1687,7 +1687,7 @@ static int launch_cg( sb200_patch *p, const DynArgs &a, int ntiles )
 {
     using T = typename CG<ORDER>::T;
     FieldMaps tm;
-    if( field_maps( p, T::FX, T::FY, T::FZ, T::JX, T::JY, T::JZ, tm ) ) return 1;
+    if( field_maps( p, a.J, T::FX, T::FY, T::FZ, T::JX, T::JY, T::JZ, tm ) ) return 1;
     auto kern = k_dynamics_cg<ORDER, PUSHER, SCRATCH>;
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )CGDim<ORDER>::BYTES ) );
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
@@ -1702,7 +1702,7 @@ static int launch_o2( sb200_patch *p, const DynArgs &a, int ntiles )
 {
     using T = o2::T;
     FieldMaps tm;
-    if( field_maps( p, T::FX, T::FY, T::FZ, T::JX, T::JY, T::JZ, tm ) ) return 1;
+    if( field_maps( p, a.J, T::FX, T::FY, T::FZ, T::JX, T::JY, T::JZ, tm ) ) return 1;
     auto kern = k_dynamics_o2<PUSHER, SCRATCH, REMOVE>;
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )o2::BYTES ) );
     SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
@@ -1776,7 +1776,8 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     a.first = s.first;
     const int fid[6] = { SB200_EX, SB200_EY, SB200_EZ, SB200_BXM, SB200_BYM, SB200_BZM };
     for( int c=0; c<6; c++ ) a.F[c] = p->f[fid[c]];
-    a.J[0] = p->f[SB200_JX]; a.J[1] = p->f[SB200_JY]; a.J[2] = p->f[SB200_JZ];
+    // diag step: the species' own Jx_s Jy_s Jz_s when it has them (Projector3D2Order.cpp:756-758), else the totals
+    for( int c=0; c<3; c++ ) a.J[c] = ( ( flags & SB200_DYN_DIAG_RHO ) && s.fs[c] ) ? s.fs[c] : p->f[SB200_JX+c];
     a.count = s.count;
     a.leave_counts = p->leave_counts + 8*ispec;
     a.leave_idx = s.leave_idx;

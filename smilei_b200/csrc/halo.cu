@@ -61,7 +61,7 @@ __global__ void __launch_bounds__( 256 ) k_slab_exch_self( SlabGeom s, double *_
 
 static int slab_geom( sb200_patch *p, int field_id, int dim, int first, int nplanes, SlabGeom &s, long long &total )
 {
-    SB200_CHECK( p && field_id >= 0 && field_id < SB200_NFIELDS && dim >= 0 && dim < 3, "halo: bad field or dimension" );
+    SB200_CHECK( p && field_ptr( p, field_id ) && dim >= 0 && dim < 3, "halo: bad field or dimension (or a species array that was not requested)" );
     const GridDev &g = p->gd;
     for( int i=0; i<3; i++ ) s.dims[i] = field_dual( field_id, i ) ? g.d[i] : g.p[i];
     SB200_CHECK( first >= 0 && nplanes >= 0 && first+nplanes <= s.dims[dim], "halo: plane range outside the field" );
@@ -273,7 +273,7 @@ int sb200_halo_pack( sb200_patch *p, int field_id, int dim, int first_plane, int
     SB200_CHECK( dev_buf, "sb200_halo_pack: null buffer" );
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( total == 0 ) return 0;
-    k_slab_pack<<<nblocks( total ), 256, 0, p->stream>>>( s, p->f[field_id], dev_buf, total );
+    k_slab_pack<<<nblocks( total ), 256, 0, p->stream>>>( s, field_ptr( p, field_id ), dev_buf, total );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
@@ -287,7 +287,7 @@ int sb200_halo_unpack( sb200_patch *p, int field_id, int dim, int first_plane, i
     SB200_CHECK( mode == SB200_UNPACK_COPY || mode == SB200_UNPACK_ADD, "sb200_halo_unpack: bad mode" );
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( total == 0 ) return 0;
-    k_slab_unpack<<<nblocks( total ), 256, 0, p->stream>>>( s, p->f[field_id], dev_buf, total, mode == SB200_UNPACK_ADD );
+    k_slab_unpack<<<nblocks( total ), 256, 0, p->stream>>>( s, field_ptr( p, field_id ), dev_buf, total, mode == SB200_UNPACK_ADD );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
@@ -303,7 +303,7 @@ int sb200_halo_sum_self( sb200_patch *p, int field_id, int dim )
     SB200_CHECK( g.n[dim] >= gsp, "sb200_halo_sum_self: patch too small for a self wrap" );
     SB200_CUDA( cudaSetDevice( p->device ) );
     const long long stride = dim==0 ? g.sx : dim==1 ? g.sy : 1;
-    k_slab_sum_self<<<nblocks( total ), 256, 0, p->stream>>>( s, p->f[field_id], total, ( long long )g.n[dim]*stride );
+    k_slab_sum_self<<<nblocks( total ), 256, 0, p->stream>>>( s, field_ptr( p, field_id ), total, ( long long )g.n[dim]*stride );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;
@@ -319,7 +319,7 @@ int sb200_halo_exchange_self( sb200_patch *p, int field_id, int dim )
     if( slab_geom( p, field_id, dim, 0, o, s, total ) ) return 1;
     SB200_CUDA( cudaSetDevice( p->device ) );
     const long long stride = dim==0 ? g.sx : dim==1 ? g.sy : 1;
-    k_slab_exch_self<<<nblocks( total ), 256, 0, p->stream>>>( s, p->f[field_id], total, ( long long )g.n[dim]*stride, ( long long )gsp*stride );
+    k_slab_exch_self<<<nblocks( total ), 256, 0, p->stream>>>( s, field_ptr( p, field_id ), total, ( long long )g.n[dim]*stride, ( long long )gsp*stride );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;

@@ -183,6 +183,7 @@ int sb200_patch_destroy( sb200_patch *p )
         if( p->sp[s].count ) cudaFree( p->sp[s].count );
         if( p->sp[s].d_qwmax ) cudaFree( p->sp[s].d_qwmax );
         if( p->sp[s].leave_idx ) cudaFree( p->sp[s].leave_idx );
+        for( int k=0; k<4; k++ ) if( p->sp[s].fs[k] ) cudaFree( p->sp[s].fs[k] );
         if( p->sp[s].perm ) cudaFree( p->sp[s].perm );
         if( p->sp[s].d_lost ) cudaFree( p->sp[s].d_lost );
     }
@@ -441,7 +442,7 @@ int sb200_species_first_index( sb200_patch *p, int ispec, int *first, size_t n )
 
 int sb200_field_size( sb200_patch *p, int field_id, size_t *n, int dims[3] )
 {
-    SB200_CHECK( p && field_id >= 0 && field_id < SB200_NFIELDS, "sb200_field_size: bad field id" );
+    SB200_CHECK( p && field_id >= 0 && field_id < SB200_NFIELDS + 4*p->nspec, "sb200_field_size: bad field id" );
     int d[3];
     field_dims( p->gd, field_id, d );
     if( n ) *n = ( size_t )d[0]*d[1]*d[2];
@@ -451,7 +452,7 @@ int sb200_field_size( sb200_patch *p, int field_id, size_t *n, int dims[3] )
 
 int sb200_field_set( sb200_patch *p, int field_id, const double *host, size_t n )
 {
-    SB200_CHECK( p && host && field_id >= 0 && field_id < SB200_NFIELDS, "sb200_field_set: bad arguments" );
+    SB200_CHECK( p && host && field_ptr( p, field_id ), "sb200_field_set: bad arguments (or a species array that was not requested)" );
     int d[3];
     field_dims( p->gd, field_id, d );
     size_t total = ( size_t )d[0]*d[1]*d[2];
@@ -459,8 +460,8 @@ int sb200_field_set( sb200_patch *p, int field_id, const double *host, size_t n 
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( ensure_stage( p, total ) ) return 1;
     SB200_CUDA( cudaMemcpyAsync( p->stage, host, total*sizeof( double ), cudaMemcpyHostToDevice, p->stream ) );
-    SB200_CUDA( cudaMemsetAsync( p->f[field_id], 0, p->falloc*sizeof( double ), p->stream ) );
-    k_field_pad<<<1184, 256, 0, p->stream>>>( p->stage, p->f[field_id], d[0], d[1], d[2], p->gd.sx, p->gd.sy, 1 );
+    SB200_CUDA( cudaMemsetAsync( field_ptr( p, field_id ), 0, p->falloc*sizeof( double ), p->stream ) );
+    k_field_pad<<<1184, 256, 0, p->stream>>>( p->stage, field_ptr( p, field_id ), d[0], d[1], d[2], p->gd.sx, p->gd.sy, 1 );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     SB200_CUDA( cudaStreamSynchronize( p->stream ) );
@@ -469,14 +470,14 @@ int sb200_field_set( sb200_patch *p, int field_id, const double *host, size_t n 
 
 int sb200_field_get( sb200_patch *p, int field_id, double *host, size_t n )
 {
-    SB200_CHECK( p && host && field_id >= 0 && field_id < SB200_NFIELDS, "sb200_field_get: bad arguments" );
+    SB200_CHECK( p && host && field_ptr( p, field_id ), "sb200_field_get: bad arguments (or a species array that was not requested)" );
     int d[3];
     field_dims( p->gd, field_id, d );
     size_t total = ( size_t )d[0]*d[1]*d[2];
     SB200_CHECK( n == total, "sb200_field_get: size does not match the field dims" );
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( ensure_stage( p, total ) ) return 1;
-    k_field_pad<<<1184, 256, 0, p->stream>>>( p->stage, p->f[field_id], d[0], d[1], d[2], p->gd.sx, p->gd.sy, 0 );
+    k_field_pad<<<1184, 256, 0, p->stream>>>( p->stage, field_ptr( p, field_id ), d[0], d[1], d[2], p->gd.sx, p->gd.sy, 0 );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     SB200_CUDA( cudaMemcpyAsync( host, p->stage, total*sizeof( double ), cudaMemcpyDeviceToHost, p->stream ) );
@@ -486,8 +487,8 @@ int sb200_field_get( sb200_patch *p, int field_id, double *host, size_t n )
 
 int sb200_field_device_ptr( sb200_patch *p, int field_id, void **dev_ptr, int alloc[3] )
 {
-    SB200_CHECK( p && dev_ptr && field_id >= 0 && field_id < SB200_NFIELDS, "sb200_field_device_ptr: bad arguments" );
-    *dev_ptr = p->f[field_id];
+    SB200_CHECK( p && dev_ptr && field_ptr( p, field_id ), "sb200_field_device_ptr: bad arguments (or a species array that was not requested)" );
+    *dev_ptr = field_ptr( p, field_id );
     if( alloc ) { alloc[0] = p->gd.ax; alloc[1] = p->gd.ay; alloc[2] = p->gd.az; }
     return 0;
 }
@@ -513,6 +514,52 @@ int sb200_restart_rhoJ( sb200_patch *p )
     SB200_CHECK( p, "sb200_restart_rhoJ: null patch" );
     SB200_CUDA( cudaSetDevice( p->device ) );
     for( int f=SB200_JX; f<=SB200_RHO; f++ ) SB200_CUDA( cudaMemsetAsync( p->f[f], 0, p->falloc*sizeof( double ), p->stream ) );
+    // ElectroMagn::restartRhoJs (ElectroMagn.cpp:410-436): the species' own arrays too
+    for( int is=0; is<p->nspec; is++ )
+        for( int k=0; k<4; k++ )
+            if( p->sp[is].fs[k] ) SB200_CUDA( cudaMemsetAsync( p->sp[is].fs[k], 0, p->falloc*sizeof( double ), p->stream ) );
+    return 0;
+}
+
+// ElectroMagn::Jx_s .. rho_s of one species: allocated when a field diagnostic asks for them
+// (ElectroMagn.cpp: the per-species arrays exist only for the species a DiagFields names)
+int sb200_species_diag_fields( sb200_patch *p, int ispec, int mask )
+{
+    SB200_CHECK( p && ispec >= 0 && ispec < p->nspec && mask >= 0 && mask < 16, "sb200_species_diag_fields: bad arguments" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    SpeciesDev &s = p->sp[ispec];
+    for( int k=0; k<4; k++ ) {
+        const bool want = ( mask >> k ) & 1;
+        if( want && !s.fs[k] ) {
+            SB200_CUDA( cudaMalloc( &s.fs[k], p->falloc*sizeof( double ) ) );
+            SB200_CUDA( cudaMemsetAsync( s.fs[k], 0, p->falloc*sizeof( double ), p->stream ) );
+        } else if( !want && s.fs[k] ) {
+            SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+            cudaFree( s.fs[k] );
+            s.fs[k] = nullptr;
+        }
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__( 256 ) k_add_into( double *__restrict__ tot, const double *__restrict__ sp, size_t n )
+{
+    for( size_t i = blockIdx.x*( size_t )blockDim.x + threadIdx.x; i < n; i += ( size_t )gridDim.x*blockDim.x ) tot[i] += sp[i];
+}
+
+// ElectroMagn3D::computeTotalRhoJ (ElectroMagn3D.cpp:1753-1799): totals += every species' own arrays, species by
+// species (the padding of the device layout is zero in both, so the whole allocation is added)
+int sb200_compute_total_rhoJ( sb200_patch *p )
+{
+    SB200_CHECK( p, "sb200_compute_total_rhoJ: null patch" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    for( int is=0; is<p->nspec; is++ )
+        for( int k=0; k<4; k++ )
+            if( p->sp[is].fs[k] ) {
+                k_add_into<<<148*8, 256, 0, p->stream>>>( p->f[SB200_JX+k], p->sp[is].fs[k], p->falloc );
+                sb200::g_launches++;
+                SB200_CUDA( cudaGetLastError() );
+            }
     return 0;
 }
 

@@ -72,8 +72,9 @@ int launch_rho( sb200_patch *p, int ispec )
     SpeciesDev &s = p->sp[ispec];
     if( s.n == 0 ) return 0;
     const unsigned blocks = ( unsigned )( ( s.n + 255 )/256 < 148*16 ? ( s.n + 255 )/256 : 148*16 );
-    if( p->gd.order == 2 ) k_deposit_rho<2><<<blocks, 256, 0, p->stream>>>( p->gd, s.col[0], s.col[1], s.col[2], s.col[6], s.q, s.n, p->f[SB200_RHO] );
-    else k_deposit_rho<4><<<blocks, 256, 0, p->stream>>>( p->gd, s.col[0], s.col[1], s.col[2], s.col[6], s.q, s.n, p->f[SB200_RHO] );
+    double *rho = s.fs[3] ? s.fs[3] : p->f[SB200_RHO];        // the species' own rho_s when it has one (Projector3D2Order.cpp:759)
+    if( p->gd.order == 2 ) k_deposit_rho<2><<<blocks, 256, 0, p->stream>>>( p->gd, s.col[0], s.col[1], s.col[2], s.col[6], s.q, s.n, rho );
+    else k_deposit_rho<4><<<blocks, 256, 0, p->stream>>>( p->gd, s.col[0], s.col[1], s.col[2], s.col[6], s.q, s.n, rho );
     sb200::g_launches++;
     SB200_CUDA( cudaGetLastError() );
     return 0;

@@ -147,7 +147,7 @@ class Exchanger:
             has_lo, has_hi = self.nbr[dim][0] is not None, self.nbr[dim][1] is not None
             sizes, gsp = [], []
             for f in fields:
-                g = 1 + 2 * self.o[dim] + _DUAL[f][dim]            # SyncVectorPatch.cpp:235-237,284
+                g = 1 + 2 * self.o[dim] + _DUAL[f[0] if isinstance(f, tuple) else f][dim]   # SyncVectorPatch.cpp:235-237,284; (name, ispec): a species' own array
                 gsp.append(g)
                 sizes.append(g * p.halo_plane_elems(f, dim))
             tot = sum(sizes)

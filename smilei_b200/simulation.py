@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 
 from . import particles_init
-from .exchange import Exchanger, rank_to_pcoord
+from .exchange import Exchanger, J_FIELDS, rank_to_pcoord
 from .operators import InterpolatorFactory, PusherFactory, ProjectorFactory, SolverFactory
 
 
@@ -69,6 +69,17 @@ class ElectroMagn:
 
     def restartRhoJ(self):
         self.patch.restart_rhoJ()
+
+    def allocateSpeciesFields(self, ispec, Jx=True, Jy=True, Jz=True, rho=True):
+        """ElectroMagn::Jx_s[ispec] .. rho_s[ispec] (ElectroMagn.h:129-141): the arrays a DiagFields naming that
+        species needs; diag-step deposits of the species then go there (Projector3D2Order.cpp:756-759)."""
+        self.patch.species_diag_fields(ispec, Jx, Jy, Jz, rho)
+        self.species_fields = getattr(self, "species_fields", {})
+        self.species_fields[ispec] = tuple(n for n, on in zip(("Jx", "Jy", "Jz", "rho"), (Jx, Jy, Jz, rho)) if on)
+
+    def computeTotalRhoJ(self):
+        """ElectroMagn3D::computeTotalRhoJ (ElectroMagn3D.cpp:1753-1799)."""
+        self.patch.compute_total_rhoJ()
 
     def centerMagneticFields(self):
         self.patch.center_B()
@@ -224,8 +235,16 @@ class Simulation:
             sp.dynamics(self.EMfields, self.smpi, diag_flag)          # VectorPatch.cpp:4821
         # ---- initExchParticles .. finalizeExchParticles (Smilei.cpp:528,637)
         self.exchanger.exchange_particles(len(self.vecSpecies))
-        # ---- sumDensities (Smilei.cpp:531)
-        self.exchanger.sum_J()
+        # ---- sumDensities (Smilei.cpp:531; VectorPatch.cpp:905-963).  On a diag step the totals first receive the
+        #      species' own arrays (computeTotalRhoJ), rho is summed with J (sumRhoJ), and so are the species' arrays
+        #      (sumRhoJs) so that a field diagnostic reads complete values on the shared planes
+        if diag_flag:
+            self.EMfields.computeTotalRhoJ()
+            self.exchanger.sum_J(fields=J_FIELDS + ("rho",))
+            for ispec, names in getattr(self.EMfields, "species_fields", {}).items():
+                self.exchanger.sum_J(fields=tuple((n, ispec) for n in names))
+        else:
+            self.exchanger.sum_J()
         # ---- solveMaxwell (Smilei.cpp:547): saveMagneticFields, Ampere, Faraday, exchangeB
         self.EMfields.MaxwellAmpereSolver_(self.EMfields)
         self.EMfields.MaxwellFaradaySolver_(self.EMfields)

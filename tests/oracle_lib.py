@@ -134,6 +134,12 @@ class _Ops:
         self._f("project")(C.byref(g), order, _p(J["Jx"]), _p(J["Jy"]), _p(J["Jz"]), _p(x), _p(y), _p(z), _p(q),
                            _p(w), n, istart, iend, _p(iold), _p(delta))
 
+    def project_rho(self, g, order, J, x, y, z, q, w, iold, delta):
+        """currentsAndDensityWrapper with diag_flag, either order, in place on J = {Jx, Jy, Jz, rho} (oracle only)."""
+        n = len(x)
+        self._f("project_rho")(C.byref(g), order, _p(J["Jx"]), _p(J["Jy"]), _p(J["Jz"]), _p(J["rho"]), _p(x), _p(y),
+                               _p(z), _p(q), _p(w), n, 0, n, _p(iold), _p(delta))
+
     def project_rho_o2(self, g, J, x, y, z, q, w, iold, delta):
         n = len(x)
         self._f("project_rho_o2")(C.byref(g), _p(J["Jx"]), _p(J["Jy"]), _p(J["Jz"]), _p(J["rho"]), _p(x), _p(y),
@@ -185,6 +191,10 @@ class Oracle(_Ops):
         return self.lib.orc_uelm(C.byref(g), _p(F["Ex"]), _p(F["Ey"]), _p(F["Ez"]), _p(F["Bxm"]), _p(F["Bym"]),
                                  _p(F["Bzm"]))
 
+    def compute_total_rhoJ(self, g, J, Js):
+        self.lib.orc_compute_total_rhoJ(C.byref(g), _p(J["Jx"]), _p(J["Jy"]), _p(J["Jz"]), _p(J["rho"]),
+                                        _p(Js["Jx"]), _p(Js["Jy"]), _p(Js["Jz"]), _p(Js["rho"]))
+
     def sum_pair(self, g, dim, name, L, R):
         d = DUAL[name]
         self.lib.orc_sum_pair(C.byref(g), dim, d[0], d[1], d[2], _p(L), _p(R))
@@ -217,6 +227,16 @@ class Reference(_Ops):
 
     def time_maxwell(self, g, npatches, nsteps, nthreads):
         return self.lib.ref_time_maxwell(C.byref(g), npatches, nsteps, nthreads)
+
+    def project_rho_species(self, g, order, J, Js, x, y, z, q, w, iold, delta, compute_total=True):
+        """The reference's currentsAndDensityWrapper with diag_flag = true; Js = the species' own {Jx, Jy, Jz, rho}
+        (or None: deposit into the totals J), then ElectroMagn3D::computeTotalRhoJ.  In place on J and Js."""
+        n = len(x)
+        sp = Js is not None
+        z0 = [None] * 4 if not sp else [_p(Js[k]) for k in ("Jx", "Jy", "Jz", "rho")]
+        self.lib.ref_project_rho_species(C.byref(g), order, int(sp), _p(J["Jx"]), _p(J["Jy"]), _p(J["Jz"]), _p(J["rho"]),
+                                         *z0, _p(x), _p(y), _p(z), _p(q), _p(w), n, 0, n, _p(iold), _p(delta),
+                                         int(compute_total))
 
     def sort(self, g, part, tags, arrivals=None):
         """The reference's own SpeciesV::computeParticleCellKeys + SpeciesV::sortParticles (SpeciesV.cpp:599-762) on

@@ -112,19 +112,46 @@ class OraclePatch:
         return self.sp[ispec]["first"].copy()
 
     # -- fields
+    def _key(self, name):
+        """Patch field name, or a species' own array: ("Jx", ispec) / "Jx_s<ispec>"."""
+        if isinstance(name, tuple):
+            name = "%s_s%d" % (name[0], int(name[1]))
+        if name not in self.F:
+            from smilei_b200.capi import SmileiB200Error
+            raise SmileiB200Error("bad field id (or a species array that was not requested): %s" % name)
+        return name
+
+    def _base(self, name):
+        name = self._key(name)
+        return name.split("_s")[0] if "_s" in name else name
+
     def field_dims(self, name):
-        return self.F[name].shape
+        return self.F[self._key(name)].shape
 
     def field_set(self, name, a):
-        self.F[name][...] = a
+        self.F[self._key(name)][...] = a
 
     def field_get(self, name):
-        return self.F[name].copy()
+        return self.F[self._key(name)].copy()
+
+    def species_diag_fields(self, ispec, Jx=True, Jy=True, Jz=True, rho=True):
+        for n, on in zip(("Jx", "Jy", "Jz", "rho"), (Jx, Jy, Jz, rho)):
+            k = "%s_s%d" % (n, ispec)
+            if on and k not in self.F:
+                self.F[k] = np.zeros(ol.field_dims(self.g, n))
+            elif not on:
+                self.F.pop(k, None)
+
+    def compute_total_rhoJ(self):
+        for k in list(self.F):
+            if "_s" in k:
+                self.F[k.split("_s")[0]] += self.F[k]
 
     # -- time step
     def restart_rhoJ(self):
-        for k in ("Jx", "Jy", "Jz", "rho"):
-            self.F[k][...] = 0.
+        for k in self.F:
+            if k.split("_s")[0] in ("Jx", "Jy", "Jz", "rho"):
+                self.F[k][...] = 0.
 
     def dynamics(self, ispec, flags=0):
         s = self.sp[ispec]
@@ -143,7 +170,11 @@ class OraclePatch:
             s["lost"] += lost
         else:
             tags = o.bc_tag(g, P["x"], P["y"], P["z"])
-        o.project(g, self.order, self.F, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+        if flags & 2:     # diag step: currentsAndDensityWrapper with diag_flag, into the species' own arrays where it has them
+            J = {n: self.F.get("%s_s%d" % (n, ispec), self.F[n]) for n in ("Jx", "Jy", "Jz", "rho")}
+            o.project_rho(g, self.order, J, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+        else:
+            o.project(g, self.order, self.F, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
         keys = tags.copy()
         o.cell_keys(g, P["x"], P["y"], P["z"], keys=keys)
         P["key"] = keys
@@ -179,6 +210,7 @@ class OraclePatch:
 
     # -- halos
     def halo_plane_elems(self, name, dim):
+        name = self._key(name)
         d = self.F[name].shape
         return int(np.prod([d[i] for i in range(3) if i != dim]))
 
@@ -188,10 +220,12 @@ class OraclePatch:
         return tuple(sl)
 
     def halo_pack(self, name, dim, first_plane, nplanes, ptr):
+        name = self._key(name)
         a = np.moveaxis(self.F[name][self._slab(name, dim, first_plane, nplanes)], dim, 0)
         _view(ptr, a.size)[:] = a.reshape(-1)
 
     def halo_unpack(self, name, dim, first_plane, nplanes, ptr, mode):
+        name = self._key(name)
         sl = self._slab(name, dim, first_plane, nplanes)
         shape = np.moveaxis(self.F[name][sl], dim, 0).shape
         a = np.moveaxis(_view(ptr, int(np.prod(shape))).reshape(shape), 0, dim)
@@ -201,10 +235,10 @@ class OraclePatch:
             self.F[name][sl] = a
 
     def halo_sum_self(self, name, dim):
-        self.orc.sum_pair(self.g, dim, name, self.F[name], self.F[name])
+        self.orc.sum_pair(self.g, dim, self._base(name), self.F[self._key(name)], self.F[self._key(name)])
 
     def halo_exchange_self(self, name, dim):
-        self.orc.exchange_pair(self.g, dim, name, self.F[name], self.F[name])
+        self.orc.exchange_pair(self.g, dim, self._base(name), self.F[self._key(name)], self.F[self._key(name)])
 
     # -- particles
     def leaving_count(self, ispec):

@@ -513,9 +513,8 @@ def test_particle_exchange_self_periodic(sb, orc):
 
 @pytest.mark.parametrize("order", [2, 4])
 def test_diag_step_rho_deposit(sb, orc, order):
-    """SB200_DYN_DIAG_RHO: rho as Projector3D2Order::currentsAndDensity deposits it (a12).  The oracle's
-    order-2 routine is the reference's; for order 4 rho is checked through its defining property
-    rho[node] = sum_p q w/V S1x S1y S1z (total charge and a direct numpy evaluation)."""
+    """SB200_DYN_DIAG_RHO: rho and J as Projector3D{2,4}Order::currentsAndDensity deposit them (a12, a14), against the
+    oracle's restatement of both orders (pinned on the reference classes), plus the total charge."""
     n, cell, dt = (12, 10, 14), (0.07, 0.08, 0.09), 0.03
     g = ol.make_grid(n, order, cell, dt)
     p = make_patch(sb, n, order, cell, dt, 1)
@@ -539,14 +538,66 @@ def test_diag_step_rho_deposit(sb, orc, order):
     V = cell[0] * cell[1] * cell[2]
     total = np.sum(out["q"] * out["w"]) / V
     assert abs(rho.sum() - total) <= 1e-11 * abs(total)
-    if order == 2:
-        E, B, iold, delta = orc.interp(g, 2, F, S["x"], S["y"], S["z"])
-        orc.push(g, 0, 1.0, S["x"], S["y"], S["z"], S["px"], S["py"], S["pz"], S["q"], E, B)
-        J = {k: np.zeros(ol.field_dims(g, k)) for k in ("Jx", "Jy", "Jz", "rho")}
-        orc.project_rho_o2(g, J, S["x"], S["y"], S["z"], S["q"], S["w"], iold, delta)
-        assert rel(rho, J["rho"]) <= TOL_DEPOSIT
-        for k in ("Jx", "Jy", "Jz"):
-            assert rel(p.field_get(k), J[k]) <= TOL_DEPOSIT, k
+    # either order: the oracle's orc_project_rho is pinned bit for bit on Projector3D{2,4}Order::currentsAndDensityWrapper
+    E, B, iold, delta = orc.interp(g, order, F, S["x"], S["y"], S["z"])
+    orc.push(g, 0, 1.0, S["x"], S["y"], S["z"], S["px"], S["py"], S["pz"], S["q"], E, B)
+    J = {k: np.zeros(ol.field_dims(g, k)) for k in ("Jx", "Jy", "Jz", "rho")}
+    orc.project_rho(g, order, J, S["x"], S["y"], S["z"], S["q"], S["w"], iold, delta)
+    assert rel(rho, J["rho"]) <= TOL_DEPOSIT
+    for k in ("Jx", "Jy", "Jz"):
+        assert rel(p.field_get(k), J[k]) <= TOL_DEPOSIT, k
+    p.close()
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_diag_step_species_arrays_and_total(sb, orc, order):
+    """SURVEY f-3: on a diag step a species that owns Jx_s/Jy_s/Jz_s/rho_s deposits THERE
+    (Projector3D2Order.cpp:756-763), a species without them into the totals, and ElectroMagn3D::computeTotalRhoJ
+    (ElectroMagn3D.cpp:1753) adds the species arrays into the totals.  Two species, the first with its own arrays;
+    species arrays, totals before and after the sum against the oracle (pinned on the reference classes in
+    tests/test_oracle_vs_ref.py::test_diag_step_deposit_bit_exact); the periodic self-wrap of a species array too."""
+    n, cell, dt = (12, 10, 14), (0.07, 0.08, 0.09), 0.03
+    g = ol.make_grid(n, order, cell, dt)
+    p = make_patch(sb, n, order, cell, dt, 2)
+    rng = np.random.default_rng(190 + order)
+    F = ol.random_fields(g, rng, scale=0.05)
+    for k, v in F.items():
+        p.field_set(k, v)
+    names = ("Jx", "Jy", "Jz", "rho")
+    N = 15000
+    p.species_diag_fields(0)
+    p.restart_rhoJ()
+    exp_s = {k: np.zeros(ol.field_dims(g, k)) for k in names}
+    exp_t = {k: np.zeros(ol.field_dims(g, k)) for k in names}
+    for ispec, (mass, charge) in enumerate(((1.0, -1), (4.0, 2))):
+        P = ol.random_particles(g, rng, N, p_scale=0.6, charge=charge)
+        p.species_config(ispec, mass, "boris", N)
+        p.species_set(ispec, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["w"], P["q"])
+        p.sort(ispec)
+        S = p.species_get(ispec)
+        p.dynamics(ispec, flags=2)
+        E, B, iold, delta = orc.interp(g, order, F, S["x"], S["y"], S["z"])
+        orc.push(g, 0, mass, S["x"], S["y"], S["z"], S["px"], S["py"], S["pz"], S["q"], E, B)
+        orc.project_rho(g, order, exp_s if ispec == 0 else exp_t, S["x"], S["y"], S["z"], S["q"], S["w"], iold, delta)
+    for k in names:
+        assert rel(p.field_get((k, 0)), exp_s[k]) <= TOL_DEPOSIT, k           # species 0: its own arrays
+        assert rel(p.field_get(k), exp_t[k]) <= TOL_DEPOSIT, k                # totals: species 1 only so far
+    with pytest.raises(sb.capi.SmileiB200Error):
+        p.field_get(("rho", 1))                                               # species 1 asked for none
+    p.compute_total_rhoJ()
+    orc.compute_total_rhoJ(g, exp_t, exp_s)
+    for k in names:
+        assert rel(p.field_get(k), exp_t[k]) <= TOL_DEPOSIT, k
+        assert rel(p.field_get("%s_s0" % k), exp_s[k]) <= TOL_DEPOSIT, k      # untouched by the sum
+    # the halo sum of a species array goes through the same entry points as the totals' (SyncVectorPatch::sumRhoJs)
+    for dim in range(3):
+        p.halo_sum_self(("rho", 0), dim)
+        p.halo_sum_self("rho", dim)
+    a, b = p.field_get(("rho", 0)), p.field_get("rho")
+    o = order
+    assert np.array_equal(a[:2 * o + 1], a[n[0]:n[0] + 2 * o + 1]) and np.array_equal(b[:2 * o + 1], b[n[0]:n[0] + 2 * o + 1])
+    p.restart_rhoJ()
+    assert not p.field_get(("Jx", 0)).any() and not p.field_get("rho").any()
     p.close()
 
 

@@ -498,16 +498,26 @@ DiagScalar(every=10)
 
 @pytest.mark.skipif(os.environ.get("SB200_TEST_MEDIUM") != "1",
                     reason="268 M particles created on the host (minutes, ~35 GB of host memory): set SB200_TEST_MEDIUM=1")
-def test_reference_validation_thermal_plasma_medium():
+def test_reference_validation_thermal_plasma_medium_within_seed_scatter_1e_2():
     """benchmarks/gpu/tst3d_v_o2_thermal_plasma_medium.py at FULL size (128^3 cells in 16^3 patches, 64 ppc regular,
-    2 x 134 M particles, 500 steps) from the reference's particles, against the reference's stored energy curves
-    (validation/references/tst3d_v_o2_thermal_plasma_medium.py.txt == tst3d_gpu_o2_...; tolerance 1e-3 on Ukin/avg,
-    Uelm/avg and Utot/avg, validate_tst3d_v_o2_thermal_plasma_medium.py)."""
+    2 x 134 M particles, 500 steps) from the reference's particles.
+
+    (1) trajectory parity at the benchmark's own size: Ukin per species and Uelm after each of the first 4 steps
+        against the CPU oracle's run of the same namelist from the same particles
+        (tests/golden/make_oracle_thermal_medium.py -> oracle_thermal_medium_curves.npz), 1e-10 / 1e-8 relative;
+    (2) the reference's stored energy curves (validation/references/tst3d_v_o2_thermal_plasma_medium.py.txt, its
+        tolerance: 1e-3 on Ukin/avg, Uelm/avg, Utot/avg).  Ukin and Utot are held to the reference's 1e-3.  Uelm/avg
+        is held to 1e-2, NOT to the reference's 1e-3: three realisations of this benchmark (random_seed 0, 1, 2, same
+        build, tools/thermal_medium_seeds.py) differ from one another by 4.6e-3 .. 8.3e-3 in Uelm/avg and each is
+        3.8e-3 .. 4.9e-3 from the stored curve (profiles/r2_thermal_medium_seed_scatter.json): the stored curve is
+        one more realisation, and 1e-3 is below the realisation scatter for any implementation that does not
+        replay the random stream it was recorded with."""
     import time
     from smilei_b200 import namelist
     from smilei_b200.simulation import Simulation
-    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
-                                "ref_validation_thermal_plasma_medium.npz"))
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = np.load(os.path.join(here, "golden", "ref_validation_thermal_plasma_medium.npz"))
+    oracle = np.load(os.path.join(here, "golden", "oracle_thermal_medium_curves.npz"))
     params = namelist.load_namelist(THERMAL_MEDIUM, is_source=True)
     assert params.n_time == 500 and params.global_size == [128, 128, 128]
     t0 = time.time()
@@ -517,7 +527,14 @@ def test_reference_validation_thermal_plasma_medium():
     assert sim.n_particles() == [128 ** 3 * 64] * 2
     uk, ue = sim.scalars()
     ukin, uelm = [float(uk.sum())], [ue]
-    for _, k, e in sim.run(500, scalars_every=10):
+    nor = len(oracle["uelm"]) - 1
+    assert np.max(np.abs(uk - oracle["ukin"][0]) / oracle["ukin"][0]) <= 1e-12
+    for i, (_, k, e) in enumerate(sim.run(nor, scalars_every=1)):
+        dk = np.max(np.abs(np.asarray(k) - oracle["ukin"][i + 1]) / oracle["ukin"][i + 1])
+        de = abs(e - oracle["uelm"][i + 1]) / oracle["uelm"][i + 1]
+        print(f"thermal_plasma_medium step {i + 1}: GPU vs oracle Ukin {dk:.2e}  Uelm {de:.2e}")
+        assert dk <= 1e-10 and de <= 1e-8, (i, dk, de)
+    for _, k, e in sim.run(10 - nor, scalars_every=10) + sim.run(490, scalars_every=10):
         ukin.append(float(k.sum()))
         uelm.append(e)
     t2 = time.time()
@@ -529,15 +546,9 @@ def test_reference_validation_thermal_plasma_medium():
     for name, mine in (("ukin", ukin), ("uelm", uelm), ("utot", utot)):
         d = np.abs(mine / mine.mean() - gold[name])
         err[name] = float(d.max())
-        print(f"thermal_plasma_medium {name}/avg: max |GPU - reference| = {err[name]:.3e} (tolerance 1e-3); first samples",
-              d[:4])
+        print(f"thermal_plasma_medium {name}/avg: max |GPU - reference| = {err[name]:.3e}; first samples", d[:4])
     print(f"particle creation + upload {t1 - t0:.1f} s, 500 steps {t2 - t1:.1f} s")
     assert err["ukin"] <= 1e-3 and err["utot"] <= 1e-3, err
-    # Uelm/avg: the reference's 1e-3 is NOT met (measured 4.9e-3, profiles/r1_thermal_plasma_medium_validation.txt).
-    # The stored curves are an independent random realisation of the benchmark, not the seed-0 stream of the present
-    # sources: tools/thermal_short_seeds.py shows that runs from seeds 0/1/2 differ from each other exactly as much as
-    # each differs from the stored curve (profiles/r1_thermal_short_seed_scatter.json), and 1e-3 on Uelm is below that
-    # scatter.  The bound asserted here is the realisation scatter, stated for what it is.
     assert err["uelm"] <= 1e-2, err
 
 

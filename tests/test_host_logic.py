@@ -433,3 +433,68 @@ def test_reference_streams_two_ranks_gloo_match_single_rank(rank_grid):
         assert len(a["x"]) == len(b["x"]) == 16 ** 3 * 8
         for k in a:
             assert np.allclose(a[k], b[k], rtol=0, atol=1e-11), k
+
+
+def _run_rank_diag(rank, world, rank_grid, n, port, ret):
+    """Two ordinary steps then a diag step (diag_flag = True) with the electrons owning Jx_s .. rho_s; returns the
+    interior (non-ghost) part of rho, Jx and the electrons' rho_s of this rank with its global offset."""
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p = make_params(n=n)
+    sim = Simulation(p, rank_grid=rank_grid, rank=rank, patch_factory=OraclePatch)
+    state = _global_state(n, 9)
+    mn, mx = sim.patch.mn, sim.patch.mx
+    for sp in sim.vecSpecies:
+        a = state[sp.name]
+        inside = np.ones(len(a["x"]), bool)
+        for d, c in enumerate("xyz"):
+            inside &= (a[c] >= mn[d]) & (a[c] < mx[d])
+        sim.set_particles(sp.ispec, **{k: v[inside] for k, v in a.items()})
+    sim.EMfields.allocateSpeciesFields(1)
+    sim.run(2)
+    sim.step(diag_flag=True)
+    o = sim.patch.g.o[0]
+    nloc = [sim.patch.g.n[d] for d in range(3)]
+    out = {}
+    for name in ("rho", "Jx", ("rho", 1), ("Jy", 1)):
+        a = sim.patch.field_get(name)
+        out[str(name)] = a[o:o + nloc[0], o:o + nloc[1], o:o + nloc[2]].copy()     # nodes [0, n) of the patch
+    out["origin"] = [sim.pcoord[d] * nloc[d] for d in range(3)]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, out)
+        dist.barrier()
+        dist.destroy_process_group()
+    else:
+        gathered = [out]
+    if rank == 0:
+        ret["fields"] = gathered
+
+
+def _assemble(pieces, n, key):
+    full = np.zeros(n)
+    for pc in pieces:
+        a, o = pc[key], pc["origin"]
+        full[o[0]:o[0] + a.shape[0], o[1]:o[1] + a.shape[1], o[2]:o[2] + a.shape[2]] = a
+    return full
+
+
+@pytest.mark.parametrize("rank_grid", [(2, 1, 1), (1, 1, 2)])
+def test_diag_step_two_ranks_gloo_match_single_rank(rank_grid):
+    """Diag step across ranks: rho is halo-summed with J (SyncVectorPatch::sumRhoJ with diag_flag), the species' own
+    arrays too (sumRhoJs), and the totals contain the species arrays (computeTotalRhoJ) — the global rho, Jx and the
+    electrons' rho_s / Jy_s of a 2-rank run equal the 1-rank run's on every node, shared planes and periodic wrap
+    included."""
+    n = (12, 12, 12)
+    one = {}
+    _run_rank_diag(0, 1, (1, 1, 1), n, 0, one)
+    mgr = mp.Manager()
+    two = mgr.dict()
+    mp.spawn(_run_rank_diag, args=(2, rank_grid, n, _free_port(), two), nprocs=2, join=True)
+    for key in ("rho", "Jx", "('rho', 1)", "('Jy', 1)"):
+        a = _assemble(one["fields"], n, key)
+        b = _assemble(two["fields"], n, key)
+        assert np.abs(a).max() > 0
+        assert np.max(np.abs(a - b)) <= 1e-11 * np.abs(a).max(), key
+    # the totals hold BOTH species: rho of a neutral plasma is far smaller than the electrons' own rho_s
+    assert np.abs(_assemble(one["fields"], n, "rho")).max() < np.abs(_assemble(one["fields"], n, "('rho', 1)")).max()

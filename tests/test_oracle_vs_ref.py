@@ -307,3 +307,41 @@ def test_sort_matches_reference_cycle_sort(libs, case, n_leave, n_arr):
     assert np.array_equal(rfirst, first)
     for a, b in zip(_cells_as_multisets(R, rfirst), _cells_as_multisets(mine, first)):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("species_arrays", [False, True])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_diag_step_deposit_bit_exact(libs, order, species_arrays, case):
+    """SURVEY f-3: Projector3D{2,4}Order::currentsAndDensityWrapper with diag_flag = true — into the totals, or into
+    the species' own Jx_s/Jy_s/Jz_s/rho_s (Projector3D2Order.cpp:756-763) followed by ElectroMagn3D::computeTotalRhoJ
+    (ElectroMagn3D.cpp:1753-1799) — run on the reference's classes, against the oracle's orc_project_rho /
+    orc_compute_total_rhoJ: every double equal."""
+    orc, ref = libs
+    n, cell, dt, pc, npch = CASES[case]
+    if order == 4:
+        n = tuple(max(v, 10) for v in n)
+    g = ol.make_grid(n, order, cell, dt, pc, npch)
+    rng = np.random.default_rng(700 + 10 * case + order)
+    F = ol.random_fields(g, rng)
+    P = ol.random_particles(g, rng, 4000, p_scale=1.0)
+    E, B, iold, delta = orc.interp(g, order, F, P["x"], P["y"], P["z"])
+    orc.push(g, 0, 1.0, P["x"], P["y"], P["z"], P["px"], P["py"], P["pz"], P["q"], E, B)
+    names = ("Jx", "Jy", "Jz", "rho")
+    dims = {k: ol.field_dims(g, k) for k in names}
+    tot0 = {k: np.ascontiguousarray(rng.standard_normal(dims[k])) for k in names}     # what other species left there
+    Ja, Jb = {k: v.copy() for k, v in tot0.items()}, {k: v.copy() for k, v in tot0.items()}
+    if species_arrays:
+        Sa = {k: np.zeros(dims[k]) for k in names}
+        Sb = {k: np.zeros(dims[k]) for k in names}
+        orc.project_rho(g, order, Sa, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+        orc.compute_total_rhoJ(g, Ja, Sa)
+        ref.project_rho_species(g, order, Jb, Sb, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+        for k in names:
+            assert np.array_equal(Sa[k], Sb[k]), k
+            assert np.abs(Sb[k]).max() > 0
+    else:
+        orc.project_rho(g, order, Ja, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+        ref.project_rho_species(g, order, Jb, None, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
+    for k in names:
+        assert np.array_equal(Ja[k], Jb[k]), k
