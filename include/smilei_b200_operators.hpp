@@ -3,8 +3,11 @@
 // of include/smilei_b200.h.
 //
 // This header is compiled AGAINST THE REFERENCE TREE (its include paths), nothing in it is used by the
-// product library itself.  tests/test_adapter_header.py type-checks it with the reference headers when
-// /root/reference is present.  INTEGRATION.md shows the four factory branches that return these classes.
+// product library itself.  tests/test_capi_symbols.py type-checks it with the reference headers when
+// /root/reference is present, and oracle/ref_build/adapter_harness.cpp EXECUTES it: the classes below are created
+// on the reference's Params / Patch / Species / ElectroMagn3D objects and driven through Interpolator* / Pusher* /
+// Projector* / Solver* (tests/test_gpu_parity.py::test_adapter_executes_through_reference_vtable, on a B200).
+// INTEGRATION.md shows the four factory branches that return these classes.
 //
 //   Interpolator3D2OrderB200 / Interpolator3D4OrderB200 : Interpolator3D   (src/Interpolator/Interpolator3D.h)
 //   PusherB200                                          : Pusher           (src/Pusher/Pusher.h)

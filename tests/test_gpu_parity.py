@@ -9,6 +9,8 @@ Bars (BASELINE.json north_star):
 Relative means: max |a-b| / max |b| over the array (fields and currents have cancelling
 terms, so a per-element ratio is meaningless where the value is ~0).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -683,3 +685,66 @@ def test_silver_muller_bit_exact(sb, orc, i_boundary):
     for name in ("Bx", "By", "Bz"):
         assert np.array_equal(p.field_get(name), F[name])
     p.close()
+
+
+ADAPTER_SO = os.path.join(ol.ORACLE_DIR, "_ref", "libsmilei_adapter.so")
+
+
+@pytest.mark.skipif(not (ol.have_ref() and os.path.exists(ADAPTER_SO)),
+                    reason="oracle/_ref/libsmilei_adapter.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("order,pusher", [(2, 0), (2, 1), (4, 2)])
+def test_adapter_executes_through_reference_vtable(order, pusher):
+    """SURVEY f-2: include/smilei_b200_operators.hpp EXECUTED.  oracle/ref_build/adapter_harness.cpp creates
+    Interpolator3DB200 / PusherB200 / Projector3DB200 / MA_Solver3D_B200 / MF_Solver3D_B200 on the reference's
+    Params / Patch / SpeciesV / ElectroMagn3D objects and calls them through Interpolator* / Pusher* / Projector* /
+    Solver* — the virtual surface Species::dynamics and VectorPatch::solveMaxwell use — with real reference Particles
+    and Field3D objects uploaded through the C ABI.  What comes back is compared with the reference's OWN operator
+    classes (oracle/_ref/libsmilei_ref.so) applied to the same objects in the same (cell-sorted) order."""
+    import ctypes as C
+    lib = C.CDLL(ADAPTER_SO)
+    assert lib.adapter_device_count() >= 1
+    ref = ol.Reference()
+    n, cell, dt, pc, npch = GEOMS[1]
+    if order == 4:
+        n = tuple(max(v, 10) for v in n)
+    g = ol.make_grid(n, order, cell, dt, pc, npch)
+    rng = np.random.default_rng(1000 + 10 * order + pusher)
+    names = ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm", "Jx", "Jy", "Jz")
+    F0 = ol.random_fields(g, rng, names=names, scale=0.3)
+    for k in ("Jx", "Jy", "Jz"):
+        F0[k][:] = 0.                                   # restartRhoJ
+    N = 20000
+    mass, charge = (1.0, -1) if pusher != 1 else (3.0, 2)
+    P = ol.random_particles(g, rng, N, p_scale=1.0, charge=charge)
+    F = {k: v.copy() for k, v in F0.items()}
+    out = {k: P[k].copy() for k in P}
+    S = {k: np.zeros(N) for k in ("x", "y", "z", "px", "py", "pz")}
+    keys = np.zeros(N, dtype=np.int32)
+    fptr = (C.c_void_p * 12)(*[F[k].ctypes.data for k in names])
+    p_ = lambda a: a.ctypes.data_as(C.c_void_p)
+    nout = lib.adapter_step(C.byref(g), order, pusher, C.c_double(mass), fptr, N,
+                            *[p_(out[k]) for k in ("x", "y", "z", "px", "py", "pz", "w", "q")],
+                            *[p_(S[k]) for k in ("x", "y", "z", "px", "py", "pz")], p_(keys))
+    assert nout == N
+    # ---- the reference's own operators on the same particles in the same order
+    w, q = out["w"], out["q"]                          # weight / charge travel with the sort
+    E, B, iold, delta = ref.interp(g, order, F0, S["x"], S["y"], S["z"])
+    R = {k: v.copy() for k, v in S.items()}
+    ref.push(g, pusher, mass, R["x"], R["y"], R["z"], R["px"], R["py"], R["pz"], q, E, B)
+    X = {k: v.copy() for k, v in F0.items()}
+    ref.project(g, order, X, R["x"], R["y"], R["z"], q, w, iold, delta)
+    ref.save_B(g, X)
+    ref.maxwell_ampere(g, X)
+    ref.maxwell_faraday(g, X)
+    ref.center_B(g, X)
+    for k in ("px", "py", "pz"):
+        assert rel(out[k], R[k]) <= TOL_PUSH, k
+    mn, mx = ol.patch_bounds(g)
+    for i, k in enumerate("xyz"):
+        assert np.max(np.abs(out[k] - R[k])) <= TOL_PUSH * max(abs(mx[i]), g.cell[i]), k
+    for k in ("Jx", "Jy", "Jz"):
+        assert np.abs(X[k]).max() > 0
+        assert rel(F[k], X[k]) <= TOL_DEPOSIT, k
+    for k in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm"):
+        assert rel(F[k], X[k]) <= TOL_PUSH, k
+    assert (keys < 0).sum() > 0                         # some particles left the patch: the fused kernel tagged them
