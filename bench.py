@@ -195,13 +195,122 @@ def measured_traffic(args):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture, when this run is the captured
     configuration (it is not re-measured here: a number taken under a profiler is never a bench value)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f)["k_dynamics_o2"]
         if t["config"]["ncell"] == args.ncell and t["config"]["order"] == args.order:
             return t["mean_bytes_per_launch"]
     except Exception:
         pass
     return None
+
+
+
+def order4_run(args, local):
+    """BASELINE.json configs[2] (tst3d_v_o4_thermal_plasma scaled to 256^3): the same box, 16 ppc, order-4 interpolation
+    and projection, Boris, one GPU; the dominant kernel timed with CUDA events exactly like the order-2 line."""
+    import torch
+    from smilei_b200 import namelist
+    from smilei_b200.simulation import Simulation
+    n = args.ncell
+    params = namelist.load_namelist(namelist_source([n, n, n], 4, args.pusher), is_source=True)
+    sim = Simulation(params, rank_grid=(1, 1, 1), rank=0, device=f"cuda:{local}", capacity_factor=1.08)
+    T, dx, dt = plasma_constants()
+    sim.init_thermal(PPC, density=1.0, temperature=T, seed=0)
+    for _ in range(3):
+        sim.step()
+    torch.cuda.synchronize()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    steps = max(3, min(args.steps, 5))
+    e0, e1, dyn_ev = ev(), ev(), []
+    e0.record()
+    for _ in range(steps):
+        sim.EMfields.restartRhoJ()
+        for sp in sim.vecSpecies:
+            a, b = ev(), ev()
+            a.record()
+            sp.dynamics(sim.EMfields, sim.smpi)
+            b.record()
+            dyn_ev.append((a, b))
+        sim.exchanger.exchange_particles(2)
+        sim.exchanger.sum_J()
+        sim.EMfields.MaxwellAmpereSolver_(sim.EMfields)
+        sim.EMfields.MaxwellFaradaySolver_(sim.EMfields)
+        sim.exchanger.exchange_B()
+        for sp in sim.vecSpecies:
+            sim.patch.sort(sp.ispec)
+        sim.EMfields.centerMagneticFields()
+        sim.itime += 1
+    e1.record()
+    torch.cuda.synchronize()
+    npart = sum(sim.patch.species_count(s) for s in range(2))
+    ms_step = e0.elapsed_time(e1) / steps
+    dyn_ms = sum(a.elapsed_time(b) for a, b in dyn_ev) / len(dyn_ev)
+    dyn_bytes = 110. * (npart / 2.) + 96. * n ** 3
+    peak, _ = measured_peak()
+    uk, ue = sim.scalars()
+    sim.close()
+    return {"workload": f"synthetic 3D thermal plasma {n}^3 cells, 16 ppc, 2 species, order 4, {args.pusher} "
+                        "(BASELINE.json configs[2] scaled to the bench box)",
+            "steps": steps, "ms_per_step": ms_step, "value": npart / (ms_step * 1e-3), "unit": UNIT,
+            "ms_per_launch": dyn_ms, "pushes_per_s_dynamics_kernel": (npart / 2.) / (dyn_ms * 1e-3),
+            "roofline_frac": dyn_bytes / (dyn_ms * 1e-3) / 1e9 / peak, "kernel": "k_dynamics_o4 (one species)",
+            "energies": {"Ukin": [float(v) for v in uk], "Uelm": ue}}
+
+
+def multi_gpu_parity(world, rank, local, grid, steps=6, nloc=24, ppc=8):
+    """The N-rank run against ONE rank from the same global state (driver-visible correctness of the exchange path):
+    a box of nloc^3 cells per rank, thermal plasma with fast electrons (plenty cross rank faces, edges and corners),
+    `steps` steps on the N ranks and on rank 0 alone; Ukin per species, Uelm and the particle counts are compared
+    after every step."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from smilei_b200 import namelist
+    from smilei_b200.simulation import Simulation
+    gsize = [nloc * g for g in grid]
+    T, dx, dt = plasma_constants()
+    rng = np.random.default_rng(2024)
+    N = gsize[0] * gsize[1] * gsize[2] * ppc
+    pos = [rng.random(N) * gsize[d] * dx for d in range(3)]
+    state = {}
+    for name, mass, q in (("proton", 1836., 1), ("electron", 1., -1)):
+        s = (T / mass) ** 0.5 * 3.0
+        state[name] = dict(x=pos[0].copy(), y=pos[1].copy(), z=pos[2].copy(), px=s * rng.standard_normal(N),
+                           py=s * rng.standard_normal(N), pz=s * rng.standard_normal(N), w=np.full(N, dx ** 3 / ppc),
+                           q=np.full(N, q, dtype=np.int16))
+
+    def run(rank_grid, r):
+        params = namelist.load_namelist(namelist_source(gsize, 2, "boris"), is_source=True)
+        sim = Simulation(params, rank_grid=rank_grid, rank=r, device=f"cuda:{local}")
+        mn = [sim.pcoord[d] * sim.n[d] * dx for d in range(3)]
+        mx = [(sim.pcoord[d] + 1) * sim.n[d] * dx for d in range(3)]
+        for sp in sim.vecSpecies:
+            a = state[sp.name]
+            inside = np.ones(N, bool)
+            for d, c in enumerate("xyz"):
+                inside &= (a[c] >= mn[d]) & (a[c] < mx[d])
+            sim.set_particles(sp.ispec, **{k: np.ascontiguousarray(v[inside]) for k, v in a.items()})
+        hist = []
+        for _ in range(steps):
+            sim.step()
+            uk, ue = sim.scalars()
+            hist.append((list(uk), ue, sim.n_particles()))
+        sim.close()
+        return hist
+    many = run(grid, rank)
+    out = None
+    if rank == 0:
+        import torch.distributed as d2
+        # rank 0 alone: a world of one (no collectives are issued by a 1x1x1 rank grid)
+        one = run((1, 1, 1), 0)
+        ukin_rel = max(abs(a - b) / abs(b) for (ua, _, _), (ub, _, _) in zip(many, one) for a, b in zip(ua, ub))
+        uelm_rel = max(abs(ea - eb) / abs(eb) for (_, ea, _), (_, eb, _) in zip(many, one))
+        out = {"ranks": world, "rank_grid": list(grid), "cells_per_rank": nloc ** 3, "particles": 2 * N, "steps": steps,
+               "ukin_rel": ukin_rel, "uelm_rel": uelm_rel,
+               "n_particles_equal": all(na == nb for (_, _, na), (_, _, nb) in zip(many, one)),
+               "what": "N ranks vs rank 0 alone from the same global particles, max over steps and species"}
+    dist.barrier()
+    return out
 
 
 def main():
@@ -216,6 +325,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-order4", action="store_true", help="skip the order-4 sub-measurement (configs[2])")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank vs 1-rank parity run at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -334,8 +445,8 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_dynamics (gather+push+BC+deposit, one species)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dyn_bytes, "ms_per_launch": dyn_ms,
-                     "note": "FP64-issue / latency bound, not HBM bound (DESIGN.md §4.2, profiles/r1_final_dynamics_256.txt); "
-                             "traffic = DRAM bytes per launch from the ncu --set full capture recorded in profiles/r1_traffic.json"},
+                     "note": "FP64-issue / latency bound, not HBM bound (DESIGN.md §4.2, profiles/r2_final_dynamics_256.txt); "
+                             "traffic = DRAM bytes per launch from the ncu --set full capture recorded in profiles/r2_traffic.json"},
         "energies": {"Ukin": [float(v) for v in uk], "Uelm": ue},
         "gpu_launches": int(launches),
     }
@@ -352,9 +463,17 @@ def main():
         if r is not None:
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                     "sample": r["sample"]}
+    sim.close()
+    # ---- configs[2]: the order-4 kernel on the same box (N = 1 only; a sub-object of the same line)
+    if world == 1 and args.order == 2 and not args.no_order4:
+        line["order4"] = order4_run(args, local)
+    # ---- N > 1: the exchange path checked against one rank, where the driver sees it
+    if world > 1 and not args.no_parity:
+        par = multi_gpu_parity(world, rank, local, grid)
+        if rank == 0:
+            line["multi_gpu_parity"] = par
     if rank == 0:
         emit(line)
-    sim.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -187,6 +187,13 @@ class Patch:
         self.own_stream = bool(cuda_stream)
         _check(lib().sb200_patch_set_stream(self._h, C.c_void_p(cuda_stream)), "sb200_patch_set_stream")
 
+    def bind_stream(self, cuda_stream):
+        """Run the patch on the caller's stream (torch's current stream) and remember which one it was: the exchange
+        layer checks that torch's current stream is still this one before every collective."""
+        _check(lib().sb200_patch_set_stream(self._h, C.c_void_p(cuda_stream)), "sb200_patch_set_stream")
+        self.bound_stream = int(cuda_stream)
+        self.own_stream = False
+
     def synchronize(self):
         _check(lib().sb200_patch_synchronize(self._h), "sb200_patch_synchronize")
 

@@ -150,6 +150,7 @@ int launch_sort( sb200_patch *p, int ispec );
 int launch_rho( sb200_patch *p, int ispec );
 int launch_energy( sb200_patch *p, double *ukin, double *uelm );
 int ensure_spare( sb200_patch *p, size_t cap );
+int grow_species( sb200_patch *p, int ispec, size_t need );        // room for `need` particles (larger arrays, device copy)
 int ensure_perm( sb200_patch *p, size_t cap );
 void swap_with_spare( sb200_patch *p, SpeciesDev &s );
 int materialize( sb200_patch *p, int ispec );                    // apply a pending sort permutation to the columns (k_gather + swap)

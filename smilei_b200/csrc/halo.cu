@@ -334,6 +334,35 @@ int sb200_leaving_count( sb200_patch *p, int ispec, int counts[6] )
     return 0;
 }
 
+// stable compaction of the particles tagged `tag` over ALL keys (no cell runs needed): count per block, scan, write.
+// known < 0: the total is read back and returned in *total; else it is taken as known (no host round trip).
+static int pack_all_keys( sb200_patch *p, SpeciesDev &s, const ConstCols &in, int tag, int dim, double wrap, double hi,
+                          double *dev_buf, size_t max_records, long long known, size_t *total_out )
+{
+    const size_t nb = ( s.n + CP_B - 1 )/CP_B;
+    if( ensure_perm( p, nb + 1 > s.cap ? nb + 1 : s.cap ) ) return 1;
+    int *bc = p->perm;             // perm is free between sorts
+    k_leave_count<<<( unsigned )nb, CP_T, 0, p->stream>>>( s.key, s.n, tag, bc );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    SB200_CUDA( cudaMemsetAsync( bc+nb, 0, sizeof( int ), p->stream ) );
+    if( exclusive_scan_int( p, bc, nb+1 ) ) return 1;
+    int total = ( int )known;
+    if( known < 0 ) {
+        SB200_CUDA( cudaMemcpyAsync( &total, bc+nb, sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
+        SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    }
+    SB200_CHECK( ( size_t )total <= max_records, "sb200_leaving_pack: buffer too small for the leaving particles" );
+    if( total > 0 ) {
+        SB200_CHECK( dev_buf, "sb200_leaving_pack: null buffer" );
+        k_leave_write<<<( unsigned )nb, CP_T, 0, p->stream>>>( in, s.key, s.n, tag, dim, wrap, 0., hi, bc, dev_buf, max_records );
+        sb200::g_launches++;
+        SB200_CUDA( cudaGetLastError() );
+    }
+    if( total_out ) *total_out = ( size_t )total;
+    return 0;
+}
+
 int sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wrap, double *dev_buf, size_t max_records, size_t *n_packed )
 {
     SB200_CHECK( p && ispec >= 0 && ispec < p->nspec && dim >= 0 && dim < 3 && ( side==0 || side==1 ), "sb200_leaving_pack: bad arguments" );
@@ -362,27 +391,8 @@ int sb200_leaving_pack( sb200_patch *p, int ispec, int dim, int side, double wra
         *n_packed = ( size_t )cnt;
         return 0;
     }
-    // general path (list overflow or very many leavers): stable compaction over all keys
-    const size_t nb = ( s.n + CP_B - 1 )/CP_B;
-    if( ensure_perm( p, nb + 1 > s.cap ? nb + 1 : s.cap ) ) return 1;
-    int *bc = p->perm;             // perm is free between sorts
-    k_leave_count<<<( unsigned )nb, CP_T, 0, p->stream>>>( s.key, s.n, tag, bc );
-    sb200::g_launches++;
-    SB200_CUDA( cudaGetLastError() );
-    SB200_CUDA( cudaMemsetAsync( bc+nb, 0, sizeof( int ), p->stream ) );
-    if( exclusive_scan_int( p, bc, nb+1 ) ) return 1;
-    int total = 0;
-    SB200_CUDA( cudaMemcpyAsync( &total, bc+nb, sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
-    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
-    SB200_CHECK( ( size_t )total <= max_records, "sb200_leaving_pack: buffer too small for the leaving particles" );
-    if( total > 0 ) {
-        SB200_CHECK( dev_buf, "sb200_leaving_pack: null buffer" );
-        k_leave_write<<<( unsigned )nb, CP_T, 0, p->stream>>>( in, s.key, s.n, tag, dim, wrap, 0., hi, bc, dev_buf, max_records );
-        sb200::g_launches++;
-        SB200_CUDA( cudaGetLastError() );
-    }
-    *n_packed = ( size_t )total;
-    return 0;
+    // general path (no valid cell runs, or leavers tagged by a window shift): stable compaction over all keys
+    return pack_all_keys( p, s, in, tag, dim, wrap, hi, dev_buf, max_records, -1, n_packed );
 }
 
 int sb200_leaving_pack_known( sb200_patch *p, int ispec, int dim, int side, double wrap, double *dev_buf, size_t max_records, size_t n_known )
@@ -394,10 +404,18 @@ int sb200_leaving_pack_known( sb200_patch *p, int ispec, int dim, int side, doub
     SB200_CHECK( dev_buf, "sb200_leaving_pack_known: null buffer" );
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( materialize( p, ispec ) ) return 1;
-    SB200_CHECK( s.n_sorted > 0 && !s.window_tagged, "sb200_leaving_pack_known: the species has no valid cell runs (use sb200_leaving_pack)" );
     const int tag = -2 - 2*dim - side;
     const GridDev &g = p->gd;
     const double hi = g.cell[dim]*( double )( g.n[dim]*g.npatch[dim] );
+    if( s.n_sorted == 0 || s.window_tagged ) {
+        // a species that was empty at its last sort (vacuum / slab outside this rank) or whose leavers a window shift
+        // tagged has no cell runs to walk: its leavers — corner particles just received and re-tagged, typically —
+        // are compacted over all keys, with the count the caller already knows
+        ConstCols in;
+        for( int c=0; c<7; c++ ) in.c[c] = s.col[c];
+        in.q = s.q;
+        return pack_all_keys( p, s, in, tag, dim, wrap, hi, dev_buf, max_records, ( long long )n_known, nullptr );
+    }
     return pack_boundary_layer( p, s, tag, dim, side, wrap, hi, dev_buf, max_records, nullptr );
 }
 
@@ -407,9 +425,9 @@ int sb200_arriving_unpack( sb200_patch *p, int ispec, const double *dev_buf, siz
     SpeciesDev &s = p->sp[ispec];
     if( n == 0 ) return 0;
     SB200_CHECK( dev_buf, "sb200_arriving_unpack: null buffer" );
-    SB200_CHECK( s.n + n <= s.cap, "sb200_arriving_unpack: species capacity exceeded" );
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( materialize( p, ispec ) ) return 1;
+    if( grow_species( p, ispec, s.n + n ) ) return 1;            // Particles::resize of the reference: room on demand
     MutCols out;
     for( int c=0; c<7; c++ ) out.c[c] = s.col[c];
     out.q = s.q; out.key = s.key;

@@ -78,6 +78,33 @@ int ensure_spare( sb200_patch *p, size_t cap )
     return 0;
 }
 
+// The reference resizes Particles whenever arrivals or created particles need room (Particles::resize,
+// SpeciesV.cpp:660-665).  Here: a larger column set, the live particles copied on the device, the old set freed.
+int grow_species( sb200_patch *p, int ispec, size_t need )
+{
+    SpeciesDev &s = p->sp[ispec];
+    if( need <= s.cap ) return 0;
+    SB200_CHECK( need < ( size_t )2000000000u, "species capacity must fit int indices" );
+    if( materialize( p, ispec ) ) return 1;                // no pending sort order refers to the old arrays afterwards
+    size_t cap = s.cap + s.cap/2 + 4096;
+    if( cap < need ) cap = need;
+    if( cap >= ( size_t )2000000000u ) cap = ( size_t )2000000000u - 1;
+    double *col[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    short *q = nullptr;
+    int *key = nullptr;
+    if( alloc_particle_cols( col, &q, &key, cap ) ) return 1;
+    if( s.n > 0 ) {
+        for( int c=0; c<7; c++ ) SB200_CUDA( cudaMemcpyAsync( col[c], s.col[c], s.n*sizeof( double ), cudaMemcpyDeviceToDevice, p->stream ) );
+        SB200_CUDA( cudaMemcpyAsync( q, s.q, s.n*sizeof( short ), cudaMemcpyDeviceToDevice, p->stream ) );
+        SB200_CUDA( cudaMemcpyAsync( key, s.key, s.n*sizeof( int ), cudaMemcpyDeviceToDevice, p->stream ) );
+    }
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );
+    free_particle_cols( s.col, &s.q, &s.key );
+    for( int c=0; c<7; c++ ) s.col[c] = col[c];
+    s.q = q; s.key = key; s.cap = cap;
+    return 0;
+}
+
 int ensure_perm( sb200_patch *p, size_t cap )
 {
     if( cap <= p->perm_cap ) return 0;
@@ -222,10 +249,11 @@ int sb200_species_config( sb200_patch *p, int ispec, double mass, int pusher, si
     s.mass = mass;
     s.pusher = pusher;
     if( capacity > s.cap ) {
-        SB200_CHECK( s.n == 0, "sb200_species_config: cannot grow a populated species" );
-        free_particle_cols( s.col, &s.q, &s.key );
-        if( alloc_particle_cols( s.col, &s.q, &s.key, capacity ) ) return 1;
-        s.cap = capacity;
+        if( s.n == 0 ) {
+            free_particle_cols( s.col, &s.q, &s.key );
+            if( alloc_particle_cols( s.col, &s.q, &s.key, capacity ) ) return 1;
+            s.cap = capacity;
+        } else if( grow_species( p, ispec, capacity ) ) return 1;
     }
     {
         const size_t want = capacity/64 > ( size_t )65536 ? capacity/64 : ( size_t )65536;
@@ -315,7 +343,7 @@ int sb200_species_append( sb200_patch *p, int ispec,
     SB200_CUDA( cudaSetDevice( p->device ) );
     if( materialize( p, ispec ) ) return 1;
     SpeciesDev &s = p->sp[ispec];
-    SB200_CHECK( s.n + n <= s.cap, "sb200_species_append: species capacity exceeded" );
+    if( grow_species( p, ispec, s.n + n ) ) return 1;            // Particles::resize of the reference: room on demand
     const double *src[7] = { x, y, z, px, py, pz, w };
     for( int c=0; c<7; c++ ) SB200_CUDA( cudaMemcpyAsync( s.col[c] + s.n, src[c], n*sizeof( double ), cudaMemcpyHostToDevice, p->stream ) );
     SB200_CUDA( cudaMemcpyAsync( s.q + s.n, q, n*sizeof( short ), cudaMemcpyHostToDevice, p->stream ) );

@@ -339,11 +339,17 @@ class Exchanger:
             self._pcap = int(need * 1.5) + 16
 
     def _sync_patch_stream(self):
-        # Pack / unpack kernels run on the patch's stream and the collective on torch's current stream.  On
-        # the GPU both are the legacy default stream (the library's default, and torch's default stream), so
-        # everything is already stream-ordered and no host synchronisation is needed; a patch on its own
-        # stream, or the CPU stand-in of the tests, synchronises here.
+        # Pack / unpack kernels run on the patch's stream and the collective on torch's current stream.  On the GPU
+        # the two are kept THE SAME stream: Simulation hands torch's current stream to the library at start-up
+        # (sb200_patch_set_stream) and this check refuses to go on if the caller switched torch's stream since —
+        # NCCL would otherwise order against a stream the pack kernels do not run on.  The CPU stand-in of the
+        # tests synchronises here.
         if self.device.type == "cuda" and not getattr(self.patch, "own_stream", False):
+            import torch
+            bound = getattr(self.patch, "bound_stream", None)
+            if bound is not None and torch.cuda.current_stream(self.device).cuda_stream != bound:
+                raise RuntimeError("torch's current CUDA stream changed after the Simulation was created: the exchange "
+                                   "kernels and the collectives would no longer be stream-ordered")
             return
         sync = getattr(self.patch, "synchronize", None)
         if sync is not None:

@@ -246,6 +246,13 @@ class Params:
                 raise NamelistError(f"EM_boundary_conditions {bc} along dim {d}: periodic and silver-muller are on the B200 hot path")
         if self.has_window and self.EM_BCs[0][0] == "periodic":
             raise NamelistError("MovingWindow with a periodic x direction is not supported")
+        if self.has_window and int(getattr(self.window, "number_of_additional_shifts", 0) or 0) != 0:
+            # SimWindow::isMoving / shift take extra shifts at additional_shifts_time (SimWindow.cpp:95,100): not built
+            raise NamelistError("MovingWindow.number_of_additional_shifts != 0 is outside the B200 hot path")
+        if self.has_window and self.number_of_patches[0] < 2:
+            # the window slides by one patch of the NAMELIST (SimWindow.cpp:136): with a single patch along x the
+            # stride would be the whole box
+            raise NamelistError("MovingWindow needs number_of_patches[0] >= 2 (the window slides by one patch along x)")
         for s in self.species:
             if s.pusher not in ("boris", "vay", "higueracary"):
                 raise NamelistError(f"pusher `{s.pusher}` is outside the B200 hot path (boris, vay, higueracary)")

@@ -139,6 +139,9 @@ class Simulation:
         self.patch = patch_factory(n=self.n, cell_length=tuple(params.cell_length), dt=params.timestep,
                                    interp_order=params.interpolation_order, n_species=len(params.species),
                                    pcoord=self.pcoord, npatch=self.rank_grid, oversize=tuple(params.oversize))
+        if self.device.type == "cuda" and hasattr(self.patch, "bind_stream"):
+            # the library's kernels and torch.distributed's collectives share ONE stream: torch's current one
+            self.patch.bind_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.EMfields = ElectroMagn(params, self.patch)
         self.vecSpecies = [Species(params, sp, self.patch, i) for i, sp in enumerate(params.species)]
         self.smpi = _Smpi()

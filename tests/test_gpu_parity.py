@@ -748,3 +748,48 @@ def test_adapter_executes_through_reference_vtable(order, pusher):
     for k in ("Ex", "Ey", "Ez", "Bx", "By", "Bz", "Bxm", "Bym", "Bzm"):
         assert rel(F[k], X[k]) <= TOL_PUSH, k
     assert (keys < 0).sum() > 0                         # some particles left the patch: the fused kernel tagged them
+
+
+def test_species_grows_on_demand_and_empty_rank_forwards_corner_particles(sb, orc):
+    """ The reference resizes Particles whenever arrivals need room; a species whose capacity was sized from
+    a nearly empty initial state must not abort when plasma flows in.  And a species that was EMPTY at its last sort
+    (vacuum on this rank) has no cell runs: particles it receives in the x pass and re-tags for y must still be
+    packed by sb200_leaving_pack_known (the path Exchanger.exchange_particles always takes)."""
+    import torch
+    n, cell, dt = (8, 8, 8), (0.1, 0.1, 0.1), 0.05
+    g = ol.make_grid(n, 2, cell, dt)
+    p = make_patch(sb, n, 2, cell, dt, 1)
+    rng = np.random.default_rng(321)
+    p.species_config(0, 1.0, "boris", 16)                  # capacity of an (almost) empty rank
+    p.sort(0)                                              # sorted while empty: n_sorted == 0
+    assert p.species_count(0) == 0
+    # arrivals: 5000 records, 700 of them beyond ymax (corner particles: received in x, to be forwarded in y)
+    N = 5000
+    A = ol.random_particles(g, rng, N)
+    A["y"][:700] = n[1] * cell[1] + 0.01 * rng.random(700)
+    rec = np.zeros((N, 8))
+    for c, k in enumerate(("x", "y", "z", "px", "py", "pz", "w")):
+        rec[:, c] = A[k]
+    rec[:, 7] = A["q"]
+    buf = torch.from_numpy(rec.reshape(-1).copy()).cuda()
+    p.arriving_unpack(0, buf.data_ptr(), N)                # 16 -> room for 5000
+    assert p.species_count(0) == N
+    assert p.leaving_count(0)[3] == 700                    # re-tagged for +y
+    out = torch.zeros(8 * 1000, dtype=torch.float64, device="cuda")
+    k = p.leaving_pack_known(0, 1, 1, -n[1] * cell[1], out.data_ptr(), 1000, 700)
+    got = out.cpu().numpy()[:8 * 700].reshape(700, 8)
+    exp = rec[:700].copy()
+    exp[:, 1] -= n[1] * cell[1]
+    assert np.array_equal(got, exp)                        # index order, wrapped across the box
+    # appended beyond capacity once more, then sorted: everything that stayed is there, bit for bit
+    B = ol.random_particles(g, rng, 20000)
+    p.species_append(0, B["x"], B["y"], B["z"], B["px"], B["py"], B["pz"], B["w"], B["q"])
+    p.sort(0)
+    after = p.species_get(0)
+    assert len(after["x"]) == N - 700 + 20000
+    allp = {c: np.concatenate([A[c][700:], B[c]]) for c in ("x", "y", "z", "px", "py", "pz", "w")}
+    keys = orc.cell_keys(g, np.ascontiguousarray(allp["x"]), np.ascontiguousarray(allp["y"]), np.ascontiguousarray(allp["z"]))
+    first, perm = orc.counting_sort_perm(keys, 9 ** 3)
+    for c in allp:
+        assert np.array_equal(after[c], allp[c][perm]), c
+    p.close()

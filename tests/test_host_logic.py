@@ -498,3 +498,18 @@ def test_diag_step_two_ranks_gloo_match_single_rank(rank_grid):
         assert np.max(np.abs(a - b)) <= 1e-11 * np.abs(a).max(), key
     # the totals hold BOTH species: rho of a neutral plasma is far smaller than the electrons' own rho_s
     assert np.abs(_assemble(one["fields"], n, "rho")).max() < np.abs(_assemble(one["fields"], n, "('rho', 1)")).max()
+
+
+def test_moving_window_options_outside_the_path_are_rejected():
+    """ MovingWindow keywords the path does not implement are refused at start-up, not ignored:
+    additional shifts (SimWindow.cpp:95,100) and a stride equal to the whole box (a single patch along x)."""
+    ok = namelist.load_namelist(WINDOW_NAMELIST, is_source=True)
+    ok.check_hot_path()
+    extra = WINDOW_NAMELIST.replace("MovingWindow(time_start=2.5, velocity_x=0.9997)",
+                                    "MovingWindow(time_start=2.5, velocity_x=0.9997, number_of_additional_shifts=2, "
+                                    "additional_shifts_time=3.)")
+    with pytest.raises(namelist.NamelistError):
+        namelist.load_namelist(extra, is_source=True).check_hot_path()
+    one = WINDOW_NAMELIST.replace("number_of_patches=[12, 1, 1]", "number_of_patches=[1, 1, 1]")
+    with pytest.raises(namelist.NamelistError):
+        namelist.load_namelist(one, is_source=True).check_hot_path()
