@@ -1645,6 +1645,481 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
     }
 }
 
+// =================================================================================================
+// Order-4 production kernel: the design of k_dynamics_o2 (particle stream walked by producer warps, per-cell current
+// sums formed by consumer warps) with the order-4 sizes.
+//
+// Interpolator3D4Order / Projector3D4Order work on 5 nodes per dimension: the home window of a (cell, component) is
+// 4 flux points x 5 x 5 nodes = 100 values, too many for one lane.  The consumer lane is therefore one ROW of that
+// window — (cell, component, j), 4 x 5 = 20 running sums — 15 lanes per cell, two cells per consumer warp, four
+// consumer warps per group.  One CTA (512 threads: 8 producer + 8 consumer warps, 128 registers each) per SM: the
+// order-4 boxes (6 x 9 x 9 x 14 field values, 3 x 10 x 10 x 16 currents) and the 46-double records of two groups
+// fill the shared memory of an SM.
+//   record   per dimension M[5] = (S0+S1)/2 and DS[5]/sqrt(12) on the home nodes; 4 flux coefficients per component
+//            (fixed-point units); the weight on the node outside the home window and the flux coefficient of the
+//            flux point outside it for a particle that moved to the next node in one dimension;
+//   consumer J_c[f][j][k] += Cf_c[f] * ( M_a[j] M_b[k] + DS_a[j] DS_b[k] / 12 ),   f < 4, k < 5, one j per lane;
+//   one-dimension movers: 25 + 2 x 20 = 65 values outside the home window, table-driven, one particle per octet;
+//   movers in 2 or 3 dimensions: the warp's queue (cross_pass<4>).
+// The gather keeps its loop over the six components rolled (the unrolled body is 750 loads + 930 FMA).
+// =================================================================================================
+namespace o4 {
+using T = CG<4>::T;
+constexpr int NW = 5;
+constexpr int NF = NW - 1;                               // home flux points
+constexpr int NPROD = 256;
+constexpr int NCONS = 256;                               // 4 consumer warps per group
+constexpr int NTHR = NPROD + NCONS;
+constexpr int GROUP = 128;
+constexpr int NCELL = T::TX*T::TY*T::TZ;
+constexpr int GCELLS = NCELL/2;
+static_assert( T::TX == 4 && T::TY == 4 && T::TZ == 8, "the row / group arithmetic below is written for 4 x 4 x 8 tiles" );
+constexpr int CFO = 6*NW;                                // record: cf[3][NF] after the 3 x (M[5], DS[5])
+constexpr int SEO = CFO + 3*NF;                          // weight on the outer node
+constexpr int XCO = SEO + 1;                             // flux coefficient at the outer flux point
+constexpr int REC = 46;                                  // 44 used; 46 doubles = 92 words: consecutive slots fall in distinct 16-byte bank groups
+__device__ __forceinline__ int rec_off( int L ) { return L*REC + 2*( L >> 4 ); }
+constexpr int RECBUF = GROUP*REC + 2*( GROUP/16 );
+constexpr int XQ4 = 8;
+constexpr int XQD4 = 9*XQ4 + XQ4/2;
+constexpr int XSCR4 = 4*CGDim<4>::XSCR;                  // cross_pass scratch per producer warp (4 octets x 36)
+constexpr int NITEM = NW*NW + 2*NF*NW;                   // 65 values outside the home window of a one-dimension mover
+constexpr int NPASS = ( NITEM + 7 )/8;                   // 9 passes of an octet
+constexpr int XTAB = 6*8*NPASS;                          // table entries (int2 each)
+constexpr double K12 = 0.28867513459481288225;
+constexpr size_t BYTES = ( size_t )( 6*T::FBOX + 3*T::JBOX + 2*RECBUF + 8*XQD4 + 8*XSCR4 + XTAB )*sizeof( double );
+constexpr unsigned TMA_BYTES = 6u*T::FVOL*sizeof( double );
+
+// windows as in o2 (next_window of namespace o2 works on GROUP = 128 items and at most 8 cells)
+using sb200::o2::next_window;
+using sb200::o2::mbar_arrive;
+
+// entry `it` (0 .. 8*NPASS-1) of the outer-part table, see o2::xtab_entry: value = rec[iC] * ( cP rec[iP] rec[iB] + cQ rec[iQ] rec[iB+NW] )
+__device__ __forceinline__ int2 xtab_entry( int m, int it )
+{
+    const int d = m % 3, up = m / 3;
+    const int a1 = d == 0 ? 1 : 0, a2 = d == 2 ? 1 : 2;
+    const int st[3] = { T::JY*T::JZ, T::JZ, 1 };
+    int comp = 0, iC = 0, iP = 0, iQ = 0, iB = 0, isb = 0, off = 0, valid = 1;
+    if( it < NW*NW ) {                                   // flux component d at the outer flux point, 5 x 5 home nodes
+        const int j = it/NW, kk = it - NW*j;
+        comp = d; iC = XCO; iP = 2*NW*a1 + j; iQ = iP + NW; iB = 2*NW*a2 + kk;
+        off = ( up ? NW+1 : 1 )*st[d] + ( 1+j )*st[a1] + ( 1+kk )*st[a2];
+    } else if( it < NITEM ) {                            // the two other components on the outer node plane: 4 flux points x 5 nodes
+        const int t = it - NW*NW, second = t >= NF*NW ? 1 : 0, u = t - NF*NW*second, f = u/NW, kk = u - NW*f;
+        const int bdim = second ? a1 : a2;
+        comp = second ? a2 : a1;
+        iC = CFO + NF*comp + f; iP = SEO; iQ = SEO; iB = 2*NW*bdim + kk; isb = 1;
+        off = ( 2+f )*st[comp] + ( up ? NW+1 : 0 )*st[d] + ( 1+kk )*st[bdim];
+    } else valid = 0;
+    return make_int2( iC | ( iP << 6 ) | ( iQ << 12 ) | ( iB << 18 ) | ( isb << 24 ) | ( valid << 25 ), comp*T::JBOX + off );
+}
+}
+
+template<int PUSHER, bool SCRATCH, bool REMOVE>
+__global__ void __launch_bounds__( o4::NTHR, 1 ) k_dynamics_o4( const GridDev g, const DynArgs a, const __grid_constant__ FieldMaps tm )
+{
+    using namespace o4;
+    extern __shared__ __align__( 128 ) double smem[];
+    double *sF = smem;
+    jbox_t *sJ = reinterpret_cast<jbox_t *>( smem + 6*T::FBOX );
+    double *recbase = smem + 6*T::FBOX + 3*T::JBOX;
+    double *xqbase = recbase + 2*RECBUF;
+    double *xscrbase = xqbase + 8*XQD4;
+    int2 *xtab = reinterpret_cast<int2 *>( xscrbase + 8*XSCR4 );
+    __shared__ __align__( 8 ) unsigned long long tma_bar;
+    __shared__ int cell_first[NCELL];
+    __shared__ int cell_cnt[NCELL];
+    __shared__ int cell_off[2][GCELLS+1];
+    __shared__ unsigned short xsrc[8][32];
+    __shared__ __align__( 8 ) unsigned long long full_bar[2], empty_bar[2];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    int b = blockIdx.x;
+    const int tz = b % a.tiles[2]; b /= a.tiles[2];
+    const int ty = b % a.tiles[1];
+    const int tx = b / a.tiles[1];
+    const int c0[3] = { tx*T::TX, ty*T::TY, tz*T::TZ };
+    const int zs = ( c0[2] + g.o[2] - T::H ) & 1;
+    const int zj = ( c0[2] + g.o[2] - T::H - 1 ) & 1;
+
+    if( tid == 0 ) {
+        tma_bar_init( &tma_bar, 1 );
+        tma_bar_init( &full_bar[0], 4 ); tma_bar_init( &full_bar[1], 4 );       // 4 producer warps write a window
+        tma_bar_init( &empty_bar[0], 4 ); tma_bar_init( &empty_bar[1], 4 );     // 4 consumer warps read it
+    }
+    __syncthreads();
+    if( tid == 0 ) {
+        tma_expect( &tma_bar, TMA_BYTES );
+#pragma unroll
+        for( int c=0; c<6; c++ )
+            tma_load_3d( sF + c*T::FBOX, &tm.m[c], &tma_bar, c0[2] + g.o[2] - T::H - zs, c0[1] + g.o[1] - T::H, c0[0] + g.o[0] - T::H );
+    }
+    int mine = 0;
+    if( tid < NCELL ) {
+        const int lz = tid % T::TZ, ly = ( tid / T::TZ ) % T::TY, lx = tid / ( T::TZ*T::TY );
+        const int ix = c0[0]+lx, iy = c0[1]+ly, iz = c0[2]+lz;
+        int beg = 0, cnt = 0;
+        if( ix < g.ncell[0] && iy < g.ncell[1] && iz < g.ncell[2] ) {
+            const int cell = ( ix*g.ncell[1] + iy )*g.ncell[2] + iz;
+            beg = a.first[cell];
+            cnt = a.first[cell+1] - beg;
+        }
+        cell_first[tid] = beg;
+        cell_cnt[tid] = cnt;
+        mine = cnt;
+    } else {
+        for( int t = tid - NCELL; t < XTAB; t += NTHR - NCELL ) xtab[t] = xtab_entry( t/( 8*NPASS ), t%( 8*NPASS ) );
+    }
+    for( int t = tid; t < 3*T::JBOX; t += NTHR ) sJ[t] = 0ull;
+    const int any = __syncthreads_or( mine );
+    tma_wait( &tma_bar, 0 );
+    if( !any ) return;
+    if( warp < 2 ) {
+        const int a0 = cell_cnt[GCELLS*warp + 2*lane], a1 = cell_cnt[GCELLS*warp + 2*lane + 1];
+        int inc = a0 + a1;
+#pragma unroll
+        for( int d=1; d<32; d<<=1 ) { const int u = __shfl_up_sync( 0xffffffffu, inc, d ); if( lane >= d ) inc += u; }
+        cell_off[warp][2*lane] = inc - a0 - a1;
+        cell_off[warp][2*lane+1] = inc - a1;
+        if( lane == 31 ) cell_off[warp][GCELLS] = inc;
+    }
+    __syncthreads();
+
+    if( warp < 8 ) {
+        // ============================================================ producers
+        const int grp = warp >> 2;
+        const int L = tid & ( GROUP-1 );
+        const int *coff = cell_off[grp];
+        const int total = coff[GCELLS];
+        double *recbuf = recbase + grp*RECBUF;
+        double *rec = recbuf + rec_off( L );
+        double *xq = xqbase + XQD4*warp;
+        int *xqm = reinterpret_cast<int *>( xq + 9*XQ4 );
+        double *xscr = xscrbase + XSCR4*warp + CGDim<4>::XSCR*( lane >> 3 );
+        const int base[3] = { g.begin[0] + g.o[0] + c0[0], g.begin[1] + g.o[1] + c0[1], g.begin[2] + g.o[2] + c0[2] };
+        int qh = 0, qn = 0, bad = 0;
+        int ws = 0, q0 = 0, we = 0, q1 = 0;
+        auto locate = [&]( int ws_, int q0_, int we_, int &row_, int &ip_, int &is_ ) {
+            const int s_ = ws_ + L;
+            row_ = q0_ >> 3;
+            ip_ = -1; is_ = -1;
+            if( s_ < we_ ) {
+                row_ += s_ >= coff[T::TZ*( row_+1 )];
+                ip_ = cell_first[GCELLS*grp + T::TZ*row_] + ( s_ - coff[T::TZ*row_] );
+                is_ = a.perm ? a.perm[ip_] : ip_;
+            }
+        };
+        bool more = next_window( coff, total, lane, ws, q0, we, q1 );
+        int row = 0, ipi = -1, isi = -1;
+        if( more ) locate( ws, q0, we, row, ipi, isi );
+
+#pragma unroll 1
+        for( int r = 0; more; r++ ) {
+            int nws = we, nq0 = q1, nwe = 0, nq1 = 0, nrow = 0, nip = -1, nis = -1;
+            const bool nmore = next_window( coff, total, lane, nws, nq0, nwe, nq1 );
+            if( nmore ) locate( nws, nq0, nwe, nrow, nip, nis );
+            const bool active = ipi >= 0;
+            double dl1[3] = { 0., 0., 0. }, cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
+            int shifts = 0x15, cellt = 0, nx = 0;
+            // ---------------- part A: gather, push, tag, key
+            if( active ) {
+                const size_t ip = ( size_t )ipi, is = ( size_t )isi;
+                const double pos[3] = { a.in[0][is], a.in[1][is], a.in[2][is] };
+                double px = a.in[3][is], py = a.in[4][is], pz = a.in[5][is];
+                const short charge = a.qin[is];
+
+                double S0[3][NW], cd[3][NW];
+                int sp[3], sd[3], cl[3];
+#pragma unroll
+                for( int d=0; d<3; d++ ) {
+                    const double pn = __dmul_rn( pos[d], g.dxi[d] );
+                    const int ipn = ( int )round( pn );
+                    xdelta[d] = pn - ( double )ipn;
+                    Shape<4>::w( xdelta[d], S0[d] );
+                    const int idn = ( int )round( pn + 0.5 );
+                    Shape<4>::w( pn - ( double )idn + 0.5, cd[d] );
+                    cl[d] = ipn - base[d];
+                    sd[d] = idn - ipn;
+                }
+                {
+                    const int lx = 2*grp + ( row >> 2 ), ly = row & 3;
+                    if( cl[0] != lx || cl[1] != ly || ( unsigned )cl[2] >= ( unsigned )T::TZ ) {
+                        bad++;
+                        cl[0] = lx; cl[1] = ly; cl[2] = cl[2] < 0 ? 0 : ( cl[2] >= T::TZ ? T::TZ-1 : cl[2] );
+                    }
+                }
+                cellt = ( cl[0]*T::TY + cl[1] )*T::TZ + cl[2];
+#pragma unroll
+                for( int d=0; d<3; d++ ) {
+                    sp[d] = cl[d] + T::H + ( d == 2 ? zs : 0 );
+                    sd[d] += sp[d];
+                }
+                double EB[6];
+                EB[0] = gather<T>( sF+0*T::FBOX, cd[0], S0[1], S0[2], sd[0], sp[1], sp[2] );
+                EB[1] = gather<T>( sF+1*T::FBOX, S0[0], cd[1], S0[2], sp[0], sd[1], sp[2] );
+                EB[2] = gather<T>( sF+2*T::FBOX, S0[0], S0[1], cd[2], sp[0], sp[1], sd[2] );
+                EB[3] = gather<T>( sF+3*T::FBOX, S0[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
+                EB[4] = gather<T>( sF+4*T::FBOX, cd[0], S0[1], cd[2], sd[0], sp[1], sd[2] );
+                EB[5] = gather<T>( sF+5*T::FBOX, cd[0], cd[1], S0[2], sd[0], sd[1], sp[2] );
+                const double Ex = EB[0], Ey = EB[1], Ez = EB[2], Bx = EB[3], By = EB[4], Bz = EB[5];
+
+                const double cmd = ( double )charge*a.one_over_mass*g.dts2;
+                double dxp, dyp, dzp, invgf;
+                push<PUSHER>( cmd, g.dt, px, py, pz, Ex, Ey, Ez, Bx, By, Bz, dxp, dyp, dzp, invgf );
+                const double npos[3] = { pos[0] + dxp, pos[1] + dyp, pos[2] + dzp };
+                a.col[0][ip] = npos[0]; a.col[1][ip] = npos[1]; a.col[2][ip] = npos[2];
+                a.col[3][ip] = px; a.col[4][ip] = py; a.col[5][ip] = pz;
+                const double weight = a.in[6][is];
+                if( a.perm ) { a.col[6][ip] = weight; a.q[ip] = charge; }
+                if( SCRATCH ) {
+                    a.sc_E[0*a.n+ip] = Ex; a.sc_E[1*a.n+ip] = Ey; a.sc_E[2*a.n+ip] = Ez;
+                    a.sc_B[0*a.n+ip] = Bx; a.sc_B[1*a.n+ip] = By; a.sc_B[2*a.n+ip] = Bz;
+                    a.sc_invgf[ip] = invgf;
+#pragma unroll
+                    for( int d=0; d<3; d++ ) {
+                        a.sc_iold[d*a.n+ip] = cl[d] + c0[d] + g.o[d];
+                        a.sc_delta[d*a.n+ip] = xdelta[d];
+                    }
+                }
+
+                bool removed;
+                const int tag = boundary_tag<REMOVE>( a, g, npos, px, py, pz, weight, ip, removed );
+                const double charge_weight = removed ? 0. : g.inv_cell_volume*( double )charge*weight*a.jscale;
+                cr[0] = charge_weight*g.d_ov_dt[0]; cr[1] = charge_weight*g.d_ov_dt[1]; cr[2] = charge_weight*g.d_ov_dt[2];
+
+                int nkey[3];
+                shifts = 0;
+#pragma unroll
+                for( int d=0; d<3; d++ ) {
+                    const double pn = __dmul_rn( npos[d], g.dxi[d] );
+                    const int ipn = ( int )round( pn );
+                    dl1[d] = pn - ( double )ipn;
+                    const int shift = ipn - base[d] - cl[d];
+                    shifts |= ( shift+1 ) << ( 2*d );
+                    nx += shift != 0;
+                    nkey[d] = ( int )( ( double )ipn - g.min_loc_round[d] );
+                    xnpos[d] = pn;
+                }
+                int key = tag;
+                if( tag == 0 ) { key = ( nkey[0]*g.ncell[1] + nkey[1] )*g.ncell[2] + nkey[2]; atomicAdd( &a.count[key], 1 ); }
+                else if( tag < -1 ) atomicAdd( &a.leave_counts[-tag-2], 1 );
+                a.key[ip] = key;
+            }
+            // ---------------- the consumers must have finished with the records of the previous round
+            if( r > 0 ) tma_wait( &empty_bar[grp], ( r-1 ) & 1 );
+            // ---------------- part B: new shape, the record of the deposit (see k_dynamics_o2), 5 home nodes per dimension
+            int xmeta = 0;
+            if( active ) {
+                const bool home = nx <= 1;
+                double xe = 0., xc = 0.;
+#pragma unroll
+                for( int d=0; d<3; d++ ) {
+                    double w1[NW], s0[NW], s1[NW], ds[NW];
+                    Shape<4>::w( dl1[d], w1 );
+                    Shape<4>::w( xdelta[d], s0 );
+                    const int shift = ( ( shifts >> ( 2*d ) ) & 3 ) - 1;
+                    double s1e = 0.;
+#pragma unroll
+                    for( int s=0; s<NW; s++ ) s1[s] = w1[s];
+                    if( shift > 0 ) {
+                        s1e = w1[NW-1];
+#pragma unroll
+                        for( int s=NW-1; s>0; s-- ) s1[s] = w1[s-1];
+                        s1[0] = 0.;
+                    } else if( shift < 0 ) {
+                        s1e = w1[0];
+#pragma unroll
+                        for( int s=0; s<NW-1; s++ ) s1[s] = w1[s+1];
+                        s1[NW-1] = 0.;
+                    }
+                    double *rd = rec + 2*NW*d;
+#pragma unroll
+                    for( int s=0; s<NW; s++ ) {
+                        ds[s] = s1[s] - s0[s];
+                        rd[s] = fma( 0.5, ds[s], s0[s] );
+                        rd[NW+s] = ds[s]*K12;
+                    }
+                    const double crd = home ? cr[d] : 0.;
+                    double run = -crd*( ( shift < 0 ? s1e : 0. ) + ds[0] );
+                    double *rcf = rec + CFO + NF*d;
+                    rcf[0] = run;
+#pragma unroll
+                    for( int f=1; f<NF; f++ ) { run = fma( -crd, ds[f], run ); rcf[f] = run; }
+                    if( shift != 0 ) {
+                        xmeta = d + ( shift > 0 ? 3 : 0 );
+                        xe = s1e;
+                        xc = shift > 0 ? fma( -crd, ds[NW-1], run ) : -crd*s1e;
+                    }
+                }
+                rec[SEO] = xe; rec[XCO] = xc;
+            }
+            __syncwarp();
+            if( lane == 0 ) mbar_arrive( &full_bar[grp] );
+            // ---------------- one-dimension movers: the 65 values outside the home window, one particle per octet
+            const bool one = active && nx == 1;
+            const unsigned rem = __ballot_sync( 0xffffffffu, one );
+            if( rem ) {
+                if( one ) xsrc[warp][__popc( rem & ( ( 1u << lane ) - 1u ) )] = ( unsigned short )( lane | ( xmeta << 5 ) | ( cellt << 8 ) );
+                __syncwarp();
+                const int n1 = __popc( rem );
+#pragma unroll 1
+                for( int k = lane >> 3; k < n1; k += 4 ) {
+                    const int e = xsrc[warp][k];
+                    const double *rc = recbuf + rec_off( ( L & ~31 ) + ( e & 31 ) );
+                    const int2 *tb = xtab + 8*NPASS*( ( e >> 5 ) & 7 ) + ( lane & 7 );
+                    const int cx = e >> 8;
+                    jbox_t *jbx = sJ + zj + ( ( cx >> 5 )*T::JY + ( ( cx >> 3 ) & 3 ) )*T::JZ + ( cx & 7 );
+#pragma unroll 1
+                    for( int h=0; h<NPASS; h++ ) {
+                        const int2 en = tb[8*h];
+                        if( en.x & ( 1 << 25 ) ) {
+                            const bool isb = en.x & ( 1 << 24 );
+                            const double C = rc[en.x & 63];
+                            const double P = rc[( en.x >> 6 ) & 63]*( isb ? 0.5 : 1.0 );
+                            const double Q = rc[( en.x >> 12 ) & 63]*( isb ? K12 : 1.0 );
+                            const double *bp = rc + ( ( en.x >> 18 ) & 63 );
+                            jadd_scaled( jbx + en.y, C*fma( P, bp[0], Q*bp[NW] ) );
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // ---------------- movers in 2 or 3 dimensions: the warp's queue, 4 at a time (cross_pass)
+            unsigned xmask = __ballot_sync( 0xffffffffu, active && nx > 1 );
+            while( xmask ) {
+                const int room = XQ4 - qn;
+                const int rank = __popc( xmask & ( ( 1u << lane ) - 1u ) );
+                const bool mineq = ( ( xmask >> lane ) & 1u ) && rank < room;
+                if( mineq ) {
+                    const int e = ( qh + qn + rank ) % XQ4;
+#pragma unroll
+                    for( int d=0; d<3; d++ ) { xq[( 0+d )*XQ4+e] = xdelta[d]; xq[( 3+d )*XQ4+e] = xnpos[d]; xq[( 6+d )*XQ4+e] = cr[d]; }
+                    xqm[e] = cellt | ( shifts << 16 );
+                }
+                const unsigned done = __ballot_sync( 0xffffffffu, mineq );
+                xmask &= ~done;
+                qn += __popc( done );
+                __syncwarp();
+                while( qn >= 4 || ( xmask && qn > 0 ) ) {
+                    cross_pass<4, XQ4>( sJ + zj, xq, xqm, xscr, qh, qn, lane & 7, lane >> 3, 1.0 );
+                    const int took = qn < 4 ? qn : 4;
+                    qh = ( qh + took ) % XQ4;
+                    qn -= took;
+                }
+            }
+            ws = nws; q0 = nq0; we = nwe; q1 = nq1; more = nmore; row = nrow; ipi = nip; isi = nis;
+        }
+        while( qn > 0 ) {
+            cross_pass<4, XQ4>( sJ + zj, xq, xqm, xscr, qh, qn, lane & 7, lane >> 3, 1.0 );
+            const int took = qn < 4 ? qn : 4;
+            qh = ( qh + took ) % XQ4;
+            qn -= took;
+        }
+        if( bad ) atomicAdd( &a.iflags[1], bad );
+    } else {
+        // ============================================================ consumers: warp 8 + 4 grp + cw, cells 2 cw and 2 cw + 1 of a window
+        const int grp = ( warp - 8 ) >> 2, cw = ( warp - 8 ) & 3;
+        const int *coff = cell_off[grp];
+        const int total = coff[GCELLS];
+        const double *recbuf = recbase + grp*RECBUF;
+        const int half = lane >> 4, hl = lane & 15;            // cell of the pair, lane in the half warp
+        const int c = 2*cw + half;                             // z of this lane's cells
+        const bool wk = hl < 15;
+        const int cc = wk ? hl / NW : 0;                       // current component
+        const int j = wk ? hl - NW*cc : 0;                     // its row of the transverse window
+        const int da = cc == 0 ? 1 : 0, db = cc == 2 ? 1 : 2;
+        const int oa = 2*NW*da + j, ob = 2*NW*db, oc = CFO + NF*cc;
+        const int sf_ = cc == 0 ? T::JY*T::JZ : ( cc == 1 ? T::JZ : 1 );
+        const int sa_ = cc == 0 ? T::JZ : T::JY*T::JZ;
+        const int sb_ = cc == 2 ? T::JZ : 1;
+        const int jo_ = cc*T::JBOX + 2*sf_ + ( 1+j )*sa_ + sb_;
+        double acc[NF][NW];
+#pragma unroll
+        for( int f=0; f<NF; f++ )
+#pragma unroll
+            for( int k=0; k<NW; k++ ) acc[f][k] = 0.;
+        // L2 prefetch of the group's particle columns (see k_dynamics_o2): the four consumer warps share the 64 cells
+#pragma unroll 1
+        for( int ct = GCELLS*grp + 32*cw + lane; ct < GCELLS*( grp+1 ); ct += 128 ) {
+            const int cnt = cell_cnt[ct];
+            if( cnt == 0 ) continue;
+            size_t lo = ( size_t )cell_first[ct], hi = lo + ( size_t )cnt - 1;
+            if( a.perm ) {
+                const size_t p0 = ( size_t )a.perm[lo], p1 = ( size_t )a.perm[hi];
+                asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.perm + lo + 32 ) );
+                lo = p0 < p1 ? p0 : p1; hi = p0 < p1 ? p1 : p0;
+                if( hi - lo > 64 ) hi = lo + 64;
+            }
+#pragma unroll 1
+            for( int cc2=0; cc2<7; cc2++ )
+                for( size_t i = lo & ~( size_t )15; i <= hi; i += 16 ) asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.in[cc2] + i ) );
+            asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.qin + lo ) );
+        }
+        int ws = 0, q0 = 0, we, q1;
+#pragma unroll 1
+        for( int r = 0; next_window( coff, total, lane, ws, q0, we, q1 ); r++, ws = we, q0 = q1 ) {
+            const int q = q0 + ( ( c - q0 ) & 7 );
+            const bool has = wk && q < max( q1, q0+1 );
+            int s = 0, hi = 0;
+            bool fin = false;
+            if( has ) {
+                const int chi = coff[q+1];
+                s = max( coff[q], ws ) - ws;
+                hi = min( chi, we ) - ws;
+                fin = chi <= we && hi > s;
+            }
+            tma_wait( &full_bar[grp], r & 1 );
+#pragma unroll 1
+            while( __any_sync( 0xffffffffu, s < hi ) ) {
+                if( s < hi ) {
+                    const double *rc = recbuf + rec_off( s );
+                    const double ma = rc[oa], dj = rc[oa+NW];
+                    const double2 *qb = reinterpret_cast<const double2 *>( rc + ob );
+                    const double2 b0 = qb[0], b1 = qb[1], b2 = qb[2], b3 = qb[3], b4 = qb[4];
+                    const double Mb[NW] = { b0.x, b0.y, b1.x, b1.y, b2.x }, Db[NW] = { b2.y, b3.x, b3.y, b4.x, b4.y };
+                    double cf[NF];
+#pragma unroll
+                    for( int f=0; f<NF; f++ ) cf[f] = rc[oc+f];
+#pragma unroll
+                    for( int k=0; k<NW; k++ ) {
+                        const double W = fma( ma, Mb[k], dj*Db[k] );
+#pragma unroll
+                        for( int f=0; f<NF; f++ ) acc[f][k] = fma( cf[f], W, acc[f][k] );
+                    }
+                }
+                s++;
+            }
+            __syncwarp();
+            if( lane == 0 ) mbar_arrive( &empty_bar[grp] );
+            if( fin ) {
+                const int row = q >> 3;
+                jbox_t *jb = sJ + zj + ( ( 2*grp + ( row >> 2 ) )*T::JY + ( row & 3 ) )*T::JZ + c + jo_;
+#pragma unroll
+                for( int f=0; f<NF; f++ )
+#pragma unroll
+                    for( int k=0; k<NW; k++ ) { jadd_scaled( jb + f*sf_ + k*sb_, acc[f][k] ); acc[f][k] = 0.; }
+            }
+        }
+    }
+    __syncthreads();
+
+    for( int t = tid; t < 3*T::JBOX; t += NTHR ) {
+        const long long iv = ( long long )sJ[t];
+        reinterpret_cast<double *>( sJ )[t] = ( double )iv*a.jinv;
+    }
+    tma_store_fence();
+    __syncthreads();
+    if( tid == 0 ) {
+#pragma unroll
+        for( int c=0; c<3; c++ )
+            tma_reduce_add_3d( &tm.j[c], sJ + c*T::JBOX, c0[2] + g.o[2] - T::H - 1 - zj, c0[1] + g.o[1] - T::H - 1, c0[0] + g.o[0] - T::H - 1 );
+        tma_commit_and_wait_read();
+    }
+}
+
 // Tensor maps of the six gathered fields for a given box: element (k,j,i) innermost first, row pitch AZ*8 B
 // (a multiple of 128 B by construction of the padded layout), out-of-bounds elements read as zero.
 static int field_maps( sb200_patch *p, double *const *J, int fx, int fy, int fz, int jx, int jy, int jz, FieldMaps &out )
@@ -1725,6 +2200,37 @@ static int launch_o2_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int p
         case SB200_PUSHER_BORIS: return launch_o2_flags<SB200_PUSHER_BORIS>( p, a, ntiles, scratch );
         case SB200_PUSHER_VAY: return launch_o2_flags<SB200_PUSHER_VAY>( p, a, ntiles, scratch );
         default: return launch_o2_flags<SB200_PUSHER_HIGUERACARY>( p, a, ntiles, scratch );
+    }
+}
+
+template<int PUSHER, bool SCRATCH, bool REMOVE>
+static int launch_o4( sb200_patch *p, const DynArgs &a, int ntiles )
+{
+    using T = o4::T;
+    FieldMaps tm;
+    if( field_maps( p, a.J, T::FX, T::FY, T::FZ, T::JX, T::JY, T::JZ, tm ) ) return 1;
+    auto kern = k_dynamics_o4<PUSHER, SCRATCH, REMOVE>;
+    SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )o4::BYTES ) );
+    SB200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
+    kern<<<ntiles, o4::NTHR, o4::BYTES, p->stream>>>( p->gd, a, tm );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    return 0;
+}
+
+template<int PUSHER>
+static int launch_o4_flags( sb200_patch *p, const DynArgs &a, int ntiles, bool scratch )
+{
+    if( a.any_remove ) return scratch ? launch_o4<PUSHER, true, true>( p, a, ntiles ) : launch_o4<PUSHER, false, true>( p, a, ntiles );
+    return scratch ? launch_o4<PUSHER, true, false>( p, a, ntiles ) : launch_o4<PUSHER, false, false>( p, a, ntiles );
+}
+
+static int launch_o4_pusher( sb200_patch *p, const DynArgs &a, int ntiles, int pusher, bool scratch )
+{
+    switch( pusher ) {
+        case SB200_PUSHER_BORIS: return launch_o4_flags<SB200_PUSHER_BORIS>( p, a, ntiles, scratch );
+        case SB200_PUSHER_VAY: return launch_o4_flags<SB200_PUSHER_VAY>( p, a, ntiles, scratch );
+        default: return launch_o4_flags<SB200_PUSHER_HIGUERACARY>( p, a, ntiles, scratch );
     }
 }
 
@@ -1816,7 +2322,7 @@ int launch_dynamics( sb200_patch *p, int ispec, int flags )
     a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
     a.tiles[1] = ( g.ncell[1] + T::TY - 1 )/T::TY;
     a.tiles[2] = ( g.ncell[2] + T::TZ - 1 )/T::TZ;
-    return launch_cg_pusher<4>( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
+    return launch_o4_pusher( p, a, a.tiles[0]*a.tiles[1]*a.tiles[2], s.pusher, scratch );
 #else
     using T = Tile<2>;                        // same tile footprint for both orders of the general kernel
     a.tiles[0] = ( g.ncell[0] + T::TX - 1 )/T::TX;
