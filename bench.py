@@ -122,51 +122,72 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's OWN operator classes on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(order, pusher_id, steps, warmup, target_seconds=12.):
-    """Times Species::dynamics' operator chain (Interpolator3D2Order, PusherBoris, internal_inf/sup,
-    Projector3D2Order) + solveMaxwell (saveMagneticFields, MA_Solver3D_norm, MF_Solver3D_Yee,
-    centerMagneticFields) from oracle/_ref on patches of 16^3 cells x 16 ppc x 2 species, one OpenMP thread
-    per patch (the reference's own patch parallelism), all host threads."""
+def cpu_reference_run(order, pusher_id, steps, warmup, target_seconds=12., min_particles=32 * 1024 * 1024):
+    """The reference's own CPU implementation of the path on the host cores, all threads, one OpenMP thread per patch
+    at a time (VectorPatch.cpp:4777), on DISTINCT patches of 16^3 cells x 16 ppc x 2 species whose total
+    (>= min_particles) leaves the caches:
+
+      * order 2: the VECTORISED path a production CPU run uses (SpeciesV::dynamics with vectorization_mode "on":
+        Interpolator3D2OrderV, the pusher, computeParticleCellKeys, Projector3D2OrderV, then SpeciesV::sortParticles
+        with the leavers coming back through the receive buffer) + solveMaxwell  -> kind "reference-V";
+        the scalar operator classes (no sort) are timed beside it on the same sample for comparison;
+      * order 4 (no V classes in the reference for 3D order 4): the scalar operators, kind "reference"."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import oracle_lib as ol
     if not ol.have_ref():
         return None
     ref = ol.Reference(fast=True)
+    orc = ol.Oracle()
     T, dx, dt = plasma_constants()
     n = (16, 16, 16)
     g = ol.make_grid(n, order, (dx, dx, dx), dt)
     rng = np.random.default_rng(0)
     F = ol.random_fields(g, rng, scale=1e-3)
     cores = os.cpu_count() or 1
-    npatch = cores
     nper = 16 ** 3 * 16
+    npatch = max(cores, -(-min_particles // (2 * nper)))
+    npatch = -(-npatch // cores) * cores                 # whole rounds of the thread team
     parts = []
     for mass, q in ((1836., 1), (1., -1)):
         P = ol.random_particles(g, rng, nper, p_scale=(T / mass) ** 0.5, charge=q)
         P["w"][:] = dx ** 3 / 16.
-        parts.append((mass, P))
+        keys = orc.cell_keys(g, P["x"], P["y"], P["z"])
+        first, perm = orc.counting_sort_perm(keys, 17 ** 3)
+        parts.append((mass, {k: np.ascontiguousarray(v[perm]) for k, v in P.items()}, first))
+    vector = order == 2
 
-    def one(nsteps):
+    def one(nsteps, use_vector):
         t = 0.
-        for mass, P in parts:
-            tt, _ = ref.time_dynamics(g, order, pusher_id, mass, F, P, npatch, nsteps, cores)
+        for mass, P, first in parts:
+            if use_vector:
+                tt, _ = ref.time_dynamics_V(g, pusher_id, mass, F, P, first, npatch, nsteps, cores, with_sort=True)
+            else:
+                tt, _ = ref.time_dynamics(g, order, pusher_id, mass, F, P, npatch, nsteps, cores)
             t += tt
         t += ref.time_maxwell(g, npatch, nsteps, cores)
         return t
-    one(1)                                   # warm-up (page faults, OpenMP team)
-    t1 = one(1)
+    one(1, vector)                           # warm-up (page faults, OpenMP team)
+    t1 = one(1, vector)
     per_call = max(1, min(50, int(target_seconds / max(t1, 1e-3) / max(steps, 1))))
     for _ in range(max(warmup - 1, 0)):
-        one(1)
-    times = [one(per_call) / per_call for _ in range(steps)]
+        one(1, vector)
+    times = [one(per_call, vector) / per_call for _ in range(steps)]
     t_step = sum(times) / len(times)
     pushes = 2 * nper * npatch
-    return {"value": pushes / t_step, "t_step": t_step, "cores": cores, "kind": "reference",
-            "lib": os.path.basename(ref.path),
-            "sample": f"{npatch} patches of 16^3 cells x 16 ppc x 2 species ({pushes} particles/step), reference "
-                      f"operators (oracle/_ref, -O3 -march=native) over gather+push+BC+deposit+Yee, {per_call} "
-                      f"steps per timing, sort and exchange not included"}
+    out = {"value": pushes / t_step, "t_step": t_step, "cores": cores, "kind": "reference-V" if vector else "reference",
+           "lib": os.path.basename(ref.path),
+           "sample": f"{npatch} distinct patches of 16^3 cells x 16 ppc x 2 species ({pushes} particles/step), the "
+                     f"reference's own classes (oracle/_ref, -O3 -march=native), " +
+                     ("vectorised species path: Interpolator3D2OrderV + pusher + computeParticleCellKeys + "
+                      "Projector3D2OrderV + sortParticles (leavers return through the receive buffer)" if vector else
+                      "scalar operators: gather + push + BC tag + deposit, no sort") +
+                     f" + solveMaxwell, {per_call} step(s) per timing, {cores} OpenMP threads"}
+    if vector:
+        ts = one(1, False)
+        out["scalar_value"] = pushes / ts
+        out["scalar_what"] = "the scalar operator classes (Interpolator3D2Order, Projector3D2Order, no sort) on the same sample"
+    return out
 
 
 def run_reference_arm(args):
@@ -180,9 +201,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["t_step"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic 3D thermal plasma, 16 ppc, 2 species, order 2, Boris (bounded CPU sample of configs[1])",
+            "config": {"workload": "synthetic 3D thermal plasma, 16 ppc, 2 species, order 2, Boris (bounded CPU sample of configs[1], >= 32 M particles)",
                        "sample": r["sample"]},
-            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "cores", "kind", "sample", "scalar_value", "scalar_what") if k in r} | {"unit": UNIT},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -461,8 +482,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.order, capi.PUSHERS[args.pusher], 3, 1, target_seconds=10.)
         if r is not None:
-            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                                    "sample": r["sample"]}
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "cores", "kind", "sample", "scalar_value", "scalar_what")
+                                    if k in r} | {"unit": UNIT}
     sim.close()
     # ---- configs[2]: the order-4 kernel on the same box (N = 1 only; a sub-object of the same line)
     if world == 1 and args.order == 2 and not args.no_order4:

@@ -41,6 +41,8 @@ Projector/Projector.cpp
 Projector/Projector3D.cpp
 Projector/Projector3D2Order.cpp
 Projector/Projector3D4Order.cpp
+Interpolator/Interpolator3D2OrderV.cpp
+Projector/Projector3D2OrderV.cpp
 ElectroMagnSolver/MA_Solver3D_norm.cpp
 ElectroMagnSolver/MF_Solver3D_Yee.cpp
 ElectroMagn/ElectroMagn3D.cpp

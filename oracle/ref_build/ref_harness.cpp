@@ -74,6 +74,8 @@
 #include "PusherHigueraCary.h"
 #include "Projector3D2Order.h"
 #include "Projector3D4Order.h"
+#include "Interpolator3D2OrderV.h"
+#include "Projector3D2OrderV.h"
 #include "MA_Solver3D_norm.h"
 #include "MF_Solver3D_Yee.h"
 #include "BoundaryConditionType.h"
@@ -658,6 +660,122 @@ double ref_time_dynamics( const orc_grid *g, int order, int pusher, double mass,
         *checksum = s;
     }
     for( int ip=0; ip<npatches; ip++ ) {
+        delete I[ip]; delete Pu[ip]; delete Pr[ip];
+        free_ctx( ctx[ip] );
+    }
+    return t1-t0;
+}
+
+/* ------------------------------------------------------------------------------
+ * Timed CPU baseline, the reference's VECTORISED path (SpeciesV::dynamics, SpeciesV.cpp:131-563, what a production CPU
+ * run uses with vectorization_mode = "on"): per patch and per step, in that function's order,
+ *     Interpolator3D2OrderV::fieldsWrapper per cell          (SpeciesV.cpp:208-212)
+ *     PusherBoris / Vay / HigueraCary over the patch         (:375-378; the pushers carry `omp simd` loops)
+ *     [particles that left the periodic patch are wrapped back — what the exchange with the periodic neighbour does]
+ *     SpeciesV::computeParticleCellKeys                      (:472-477)
+ *     Projector3D2OrderV::currentsAndDensityWrapper per cell (:493-500)
+ *     SpeciesV::sortParticles                                (importAndSortParticles, SpeciesV.cpp:599-762)
+ * on npatches DISTINCT patches (each its own fields and particles: the sample leaves the caches when npatches x
+ * patch is large), one OpenMP thread per patch at a time (VectorPatch.cpp:4777).  The particles handed in must be
+ * cell-sorted with first_index (ncell+1 entries).  Returns seconds for nsteps steps.
+ * ------------------------------------------------------------------------------ */
+double ref_time_dynamics_V( const orc_grid *g, int pusher, double mass,
+                            const double *fields6,
+                            const double *x, const double *y, const double *z,
+                            const double *px, const double *py, const double *pz,
+                            const double *w, const short *q, const int *first_index, int nparts,
+                            int npatches, int nsteps, int nthreads, int with_sort, double *checksum, double *J_out )
+{
+    const unsigned int ncell = ( g->n[0]+1 )*( g->n[1]+1 )*( g->n[2]+1 );
+    std::vector<Ctx *> ctx( npatches );
+    std::vector<Interpolator *> I( npatches );
+    std::vector<Pusher *> Pu( npatches );
+    std::vector<Projector *> Pr( npatches );
+    for( int ip=0; ip<npatches; ip++ ) {
+        Ctx *c = ctx[ip] = make_ctx( g, mass, 1 );
+        Params &P = *c->params;
+        P.keep_position_old = false;
+        new( &P.vectorization_mode ) std::string( "on" );
+        const double *f = fields6;
+        Field *dst[6] = { c->em->Ex_, c->em->Ey_, c->em->Ez_, c->em->Bx_m, c->em->By_m, c->em->Bz_m };
+        for( int k=0; k<6; k++ ) { load( dst[k], f ); f += dst[k]->number_of_points_; }
+        set_particles( c, x, y, z, px, py, pz, w, q, nparts );
+        resize_scratch( c, nparts );
+        SpeciesV &S = *c->species;
+        S.nDim_particle = 3;
+        new( &S.count ) std::vector<int>( ncell, 0 );
+        new( &S.MPI_buffer_.partRecv ) std::vector<std::vector<Particles *>>( 3, std::vector<Particles *>( 2, ( Particles * )NULL ) );
+        for( int d=0; d<3; d++ ) for( int sd=0; sd<2; sd++ ) { S.MPI_buffer_.partRecv[d][sd] = new Particles(); S.MPI_buffer_.partRecv[d][sd]->initialize( 0, 3, false ); }
+        *reinterpret_cast<void **>( &S ) = reinterpret_cast<void *>( _ZTV8SpeciesV + 2*sizeof( void * ) );
+        Particles &p = *S.particles;
+        p.first_index.assign( first_index, first_index + ncell );
+        p.last_index.assign( first_index + 1, first_index + ncell + 1 );
+        I[ip]  = new Interpolator3D2OrderV( P, c->patch );
+        Pu[ip] = pusher==0 ? ( Pusher * )new PusherBoris( P, c->species )
+                 : pusher==1 ? ( Pusher * )new PusherVay( P, c->species )
+                 : ( Pusher * )new PusherHigueraCary( P, c->species );
+        Pr[ip] = new Projector3D2OrderV( P, c->patch );
+    }
+    omp_set_num_threads( nthreads );
+    double t0 = omp_get_wtime();
+    for( int it=0; it<nsteps; it++ ) {
+        #pragma omp parallel for schedule(dynamic,1)
+        for( int ip=0; ip<npatches; ip++ ) {
+            Ctx *c = ctx[ip];
+            SpeciesV &S = *c->species;
+            Particles &p = *S.particles;
+            const int n = ( int )p.size();
+            c->em->Jx_->put_to( 0. ); c->em->Jy_->put_to( 0. ); c->em->Jz_->put_to( 0. );
+            for( unsigned int scell=0; scell<ncell; scell++ )
+                I[ip]->fieldsWrapper( c->em, p, c->smpi, &p.first_index[scell], &p.last_index[scell], 0, scell, 0 );
+            ( *Pu[ip] )( p, c->smpi, 0, n, 0, 0 );
+            /* PartBoundCond::apply: internal_inf / internal_sup tag the leavers (cell_keys = -1), Species.cpp:757 */
+            for( int i=0; i<n; i++ ) p.cell_keys[i] = 0;
+            {
+                std::vector<double> invgf;
+                double e = 0.;
+                for( int d=0; d<3; d++ ) {
+                    internal_inf( c->species, 0, n, d, c->patch->min_local_[d], g->dt, invgf, NULL, e );
+                    internal_sup( c->species, 0, n, d, c->patch->max_local_[d], g->dt, invgf, NULL, e );
+                }
+            }
+            for( unsigned int ic=0; ic<ncell; ic++ ) S.count[ic] = 0;
+            S.SpeciesV::computeParticleCellKeys( *c->params, &p, &p.cell_keys[0], &S.count[0], 0, n );
+            for( unsigned int scell=0; scell<ncell; scell++ )
+                Pr[ip]->currentsAndDensityWrapper( c->em, p, c->smpi, p.first_index[scell], p.last_index[scell], 0, false, false, 0, scell, 0 );
+            /* the exchange: the patch spans the periodic sample box, so its leavers come back through the receive
+               buffer of the first neighbour, wrapped across the box (SmileiMPI / Patch::exchParticles) */
+            if( with_sort ) {
+                Particles &rcv = *S.MPI_buffer_.partRecv[0][0];
+                rcv.resize( 0, 3, false );
+                for( int i=0; i<n; i++ ) {
+                    if( p.cell_keys[i] >= 0 ) continue;
+                    p.copyParticle( i, rcv );
+                    const int k = rcv.size() - 1;
+                    for( int d=0; d<3; d++ ) {
+                        const double lo = c->patch->min_local_[d], hi = c->patch->max_local_[d];
+                        double &X = rcv.Position[d][k];
+                        if( X < lo ) X += hi - lo; else if( X >= hi ) X -= hi - lo;
+                    }
+                }
+                rcv.cell_keys.assign( rcv.size(), 0 );
+            }
+            if( with_sort ) S.SpeciesV::sortParticles( *c->params );
+        }
+    }
+    double t1 = omp_get_wtime();
+    if( checksum ) {
+        double s = 0.;
+        Field *J = ctx[0]->em->Jx_;
+        for( unsigned int i=0; i<J->number_of_points_; i++ ) s += J->data_[i];
+        *checksum = s;
+    }
+    if( J_out ) {          /* Jx Jy Jz of patch 0 after the last step, back to back (for checks against the scalar operators) */
+        Field *J[3] = { ctx[0]->em->Jx_, ctx[0]->em->Jy_, ctx[0]->em->Jz_ };
+        for( int k=0; k<3; k++ ) { store( J[k], J_out ); J_out += J[k]->number_of_points_; }
+    }
+    for( int ip=0; ip<npatches; ip++ ) {
+        for( int d=0; d<3; d++ ) for( int sd=0; sd<2; sd++ ) delete ctx[ip]->species->MPI_buffer_.partRecv[d][sd];
         delete I[ip]; delete Pu[ip]; delete Pr[ip];
         free_ctx( ctx[ip] );
     }

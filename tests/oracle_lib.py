@@ -225,6 +225,20 @@ class Reference(_Ops):
                                        C.byref(chk))
         return t, chk.value
 
+    def time_dynamics_V(self, g, pusher, mass, F, part, first, npatches, nsteps, nthreads, with_sort=True, J_out=None):
+        """Seconds for nsteps steps of the reference's VECTORISED species path (Interpolator3D2OrderV, pusher,
+        computeParticleCellKeys, Projector3D2OrderV, sortParticles) on npatches patches; `part` cell-sorted with
+        first_index `first`.  Returns (seconds, checksum of Jx of patch 0)."""
+        fields6 = np.concatenate([F[k].ravel() for k in ("Ex", "Ey", "Ez", "Bxm", "Bym", "Bzm")])
+        chk = C.c_double(0.)
+        self.lib.ref_time_dynamics_V.restype = C.c_double
+        first = np.ascontiguousarray(first, dtype=np.int32)
+        t = self.lib.ref_time_dynamics_V(C.byref(g), pusher, C.c_double(mass), _p(fields6), _p(part["x"]), _p(part["y"]),
+                                         _p(part["z"]), _p(part["px"]), _p(part["py"]), _p(part["pz"]), _p(part["w"]),
+                                         _p(part["q"]), _p(first), len(part["x"]), npatches, nsteps, nthreads,
+                                         int(with_sort), C.byref(chk), _p(J_out))
+        return t, chk.value
+
     def time_maxwell(self, g, npatches, nsteps, nthreads):
         return self.lib.ref_time_maxwell(C.byref(g), npatches, nsteps, nthreads)
 

@@ -345,3 +345,38 @@ def test_diag_step_deposit_bit_exact(libs, order, species_arrays, case):
         ref.project_rho_species(g, order, Jb, None, P["x"], P["y"], P["z"], P["q"], P["w"], iold, delta)
     for k in names:
         assert np.array_equal(Ja[k], Jb[k]), k
+
+
+def test_vectorised_reference_path_matches_scalar_operators(libs):
+    """The timed CPU baseline drives the reference's VECTORISED species path (Interpolator3D2OrderV, pusher,
+    computeParticleCellKeys, Projector3D2OrderV per cell, then sortParticles with the leavers coming back through the
+    receive buffer — oracle/ref_build/ref_harness.cpp::ref_time_dynamics_V).  Its currents after one step must be those
+    of the scalar operator classes on the same particles (1e-13: the V projector sums in another order), and a
+    multi-step run with the sort must keep going (the particle count is conserved: every leaver returns)."""
+    orc, ref = libs
+    n, cell, dt = (8, 8, 8), (0.07, 0.07, 0.07), 0.038
+    g = ol.make_grid(n, 2, cell, dt)
+    rng = np.random.default_rng(77)
+    F = ol.random_fields(g, rng, scale=1e-2)
+    N = 8 ** 3 * 12
+    P = ol.random_particles(g, rng, N, p_scale=0.3)
+    keys = orc.cell_keys(g, P["x"], P["y"], P["z"])
+    first, perm = orc.counting_sort_perm(keys, 9 ** 3)
+    S = {k: np.ascontiguousarray(v[perm]) for k, v in P.items()}
+    names = ("Jx", "Jy", "Jz")
+    dims = [ol.field_dims(g, k) for k in names]
+    Jv = np.zeros(sum(int(np.prod(d)) for d in dims))
+    ref.time_dynamics_V(g, 0, 1.0, F, S, first, 1, 1, 1, with_sort=True, J_out=Jv)
+    R = {k: v.copy() for k, v in S.items()}
+    E, B, iold, delta = ref.interp(g, 2, F, R["x"], R["y"], R["z"])
+    ref.push(g, 0, 1.0, R["x"], R["y"], R["z"], R["px"], R["py"], R["pz"], R["q"], E, B)
+    J = {k: np.zeros(ol.field_dims(g, k)) for k in names}
+    ref.project(g, 2, J, R["x"], R["y"], R["z"], R["q"], R["w"], iold, delta)
+    off = 0
+    for k, d in zip(names, dims):
+        m = int(np.prod(d))
+        a = Jv[off:off + m].reshape(d)
+        off += m
+        assert np.abs(a - J[k]).max() <= 1e-13 * np.abs(J[k]).max(), k
+    t, _ = ref.time_dynamics_V(g, 0, 1.0, F, S, first, 2, 5, 2, with_sort=True)
+    assert t > 0
