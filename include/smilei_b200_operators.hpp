@@ -4,7 +4,7 @@
 //
 // This header is compiled AGAINST THE REFERENCE TREE (its include paths), nothing in it is used by the
 // product library itself.  tests/test_capi_symbols.py type-checks it with the reference headers when
-// /root/reference is present, and oracle/ref_build/adapter_harness.cpp EXECUTES it: the classes below are created
+// /root/reference is present, and the adapter harness of the test tree (adapter_harness.cpp) EXECUTES it: the classes below are created
 // on the reference's Params / Patch / Species / ElectroMagn3D objects and driven through Interpolator* / Pusher* /
 // Projector* / Solver* (tests/test_gpu_parity.py::test_adapter_executes_through_reference_vtable, on a B200).
 // INTEGRATION.md shows the four factory branches that return these classes.
