@@ -1155,6 +1155,7 @@ constexpr int REC = 26;                                  // doubles per record: 
 // lane quads of the consumer read slots 16 apart, which would otherwise all sit in the same banks
 __device__ __forceinline__ int rec_off( int L ) { return L*REC + 2*( L >> 4 ); }
 constexpr int RECBUF = GROUP*REC + 2*( GROUP/16 );       // doubles per group
+constexpr int DIRECT_PPC = 6;                            // a group with fewer particles per cell on average deposits lane by lane (see the kernel)
 constexpr int XQ2 = 8;                                   // crosser queue entries per producer warp
 constexpr int XQD2 = 9*XQ2 + XQ2/2;
 constexpr int XSCR2 = 4*CGDim<2>::XSCR;                  // cross_pass scratch per producer warp (4 octets)
@@ -1214,6 +1215,35 @@ __device__ __forceinline__ int2 xtab_entry( int m, int it )
         off = ( 2+f )*st[comp] + ( up ? 4 : 0 )*st[d] + ( 1+kk )*st[bdim];
     } else valid = 0;
     return make_int2( iC | ( iP << 5 ) | ( iQ << 10 ) | ( iB << 15 ) | ( isb << 20 ) | ( valid << 21 ), comp*T::JBOX + off );
+}
+// sparse group (see k_dynamics_o2): the lane that wrote a record adds its sums to the J box itself, one current component
+// after the other.  Kept out of line: it is the rare path and must not weigh on the register allocation of the main one.
+__device__ __noinline__ void self_consume( const double *rec, jbox_t *jcell )
+{
+#pragma unroll 1
+    for( int cc=0; cc<3; cc++ ) {
+        const int da = cc == 0 ? 1 : 0, db = cc == 2 ? 1 : 2;
+        const int sf_ = cc == 0 ? T::JY*T::JZ : ( cc == 1 ? T::JZ : 1 );
+        const int sa_ = cc == 0 ? T::JZ : T::JY*T::JZ;
+        const int sb_ = cc == 2 ? T::JZ : 1;
+        const double2 *qa = reinterpret_cast<const double2 *>( rec + 6*da );
+        const double2 *qb = reinterpret_cast<const double2 *>( rec + 6*db );
+        const double2 a0 = qa[0], a1 = qa[1], a2 = qa[2], b0 = qb[0], b1 = qb[1], b2 = qb[2];
+        const double2 cf = *reinterpret_cast<const double2 *>( rec + 18 + 2*cc );
+        const double Ma[NW] = { a0.x, a0.y, a1.x }, Da[NW] = { a1.y, a2.x, a2.y };
+        const double Mb[NW] = { b0.x, b0.y, b1.x }, Db[NW] = { b1.y, b2.x, b2.y };
+        jbox_t *jb = jcell + cc*T::JBOX + 2*sf_ + sa_ + sb_;
+        if( cf.x != 0. || cf.y != 0. ) {
+#pragma unroll
+            for( int j=0; j<NW; j++ )
+#pragma unroll
+                for( int k_=0; k_<NW; k_++ ) {
+                    const double W = fma( Ma[j], Mb[k_], Da[j]*Db[k_] );
+                    jadd_scaled( jb + j*sa_ + k_*sb_, cf.x*W );
+                    jadd_scaled( jb + sf_ + j*sa_ + k_*sb_, cf.y*W );
+                }
+        }
+    }
 }
 }
 
@@ -1304,6 +1334,16 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
         const int base[3] = { g.begin[0] + g.o[0] + c0[0], g.begin[1] + g.o[1] + c0[1], g.begin[2] + g.o[2] + c0[2] };
         int qh = 0, qn = 0, bad = 0;
         int ws = 0, q0 = 0, we = 0, q1 = 0;
+        // SPARSE group (fewer than DIRECT_PPC particles per cell on average, e.g. the 1-per-cell plasma of a laser
+        // wake): windows of whole cells would leave most lanes idle, so the windows are plain stretches of GROUP
+        // particles whatever their cells, and every lane adds the sums of ITS OWN record to the J box (no consumer,
+        // no hand-off; with so few particles per cell there is nothing to accumulate in registers anyway)
+        const bool direct = total < DIRECT_PPC*GCELLS;
+        auto window = [&]( int &ws_, int &q0_, int &we_, int &q1_ ) -> bool {
+            if( !direct ) return next_window( coff, total, lane, ws_, q0_, we_, q1_ );
+            we_ = min( ws_ + GROUP, total ); q1_ = q0_;
+            return ws_ < total;
+        };
         // slot (in the sorted order) and source index (through the pending sort order) of this lane's particle in a
         // window; looked up one window ahead so that the dependent load of the sort order is off the critical path
         auto locate = [&]( int ws_, int q0_, int we_, int &row_, int &ip_, int &is_ ) {
@@ -1311,13 +1351,17 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
             row_ = q0_ >> 3;                                            // the window's cells lie in at most two rows
             ip_ = -1; is_ = -1;
             if( s_ < we_ ) {
-                row_ += s_ >= coff[T::TZ*( row_+1 )];
+                if( direct ) {
+                    row_ = 0;
+#pragma unroll
+                    for( int k_=1; k_<ROWS; k_++ ) row_ += s_ >= coff[T::TZ*k_];
+                } else row_ += s_ >= coff[T::TZ*( row_+1 )];
                 ip_ = cell_first[GCELLS*grp + T::TZ*row_] + ( s_ - coff[T::TZ*row_] );
                 is_ = a.perm ? a.perm[ip_] : ip_;
             }
         };
         double pos[3] = { 0., 0., 0. };
-        bool more = next_window( coff, total, lane, ws, q0, we, q1 );
+        bool more = window( ws, q0, we, q1 );
         int row = 0, ipi = -1, isi = -1;
         if( more ) locate( ws, q0, we, row, ipi, isi );
         if( isi >= 0 ) { pos[0] = a.in[0][isi]; pos[1] = a.in[1][isi]; pos[2] = a.in[2][isi]; }
@@ -1325,7 +1369,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
 #pragma unroll 1
         for( int r = 0; more; r++ ) {
             int nws = we, nq0 = q1, nwe = 0, nq1 = 0, nrow = 0, nip = -1, nis = -1;
-            const bool nmore = next_window( coff, total, lane, nws, nq0, nwe, nq1 );
+            const bool nmore = window( nws, nq0, nwe, nq1 );
             if( nmore ) locate( nws, nq0, nwe, nrow, nip, nis );
             const bool active = ipi >= 0;
             double S0[3][NW], dl1[3] = { 0., 0., 0. }, cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
@@ -1415,7 +1459,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
             // ---------------- the positions of the next window's particle: in flight during the rest of this round
             if( nis >= 0 ) { pos[0] = a.in[0][nis]; pos[1] = a.in[1][nis]; pos[2] = a.in[2][nis]; }
             // ---------------- the consumer must have finished with the records of the previous round
-            if( r > 0 ) tma_wait( &empty_bar[grp], ( r-1 ) & 1 );
+            if( r > 0 && !direct ) tma_wait( &empty_bar[grp], ( r-1 ) & 1 );
             // ---------------- part B: new shape, the record of the deposit.  Per dimension M[3], DS[3]/sqrt(12) on
             //                  the HOME nodes (the 3 nodes of S0) and the flux coefficients at the 2 home flux
             //                  points.  A particle that moved to the next node along a dimension has S1 shifted by
@@ -1453,7 +1497,11 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                 *reinterpret_cast<double2 *>( rec + 24 ) = make_double2( xe, xc );
             }
             __syncwarp();
-            if( lane == 0 ) mbar_arrive( &full_bar[grp] );
+            if( !direct ) {
+                if( lane == 0 ) mbar_arrive( &full_bar[grp] );
+            } else if( active ) {
+                o2::self_consume( rec, sJ + zj + ( ( cellt >> 5 )*T::JY + ( ( cellt >> 3 ) & 3 ) )*T::JZ + ( cellt & 7 ) );
+            }
             // ---------------- particles that moved to the next node in ONE dimension: the 21 values outside the
             //                  home window, one particle per 8-lane octet, 3 passes of 8 table items
             const bool one = active && nx == 1;
@@ -1560,19 +1608,25 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
             asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.qin + lo ) );
         }
         int ws = 0, q0 = 0, we, q1;
+        const bool direct = total < DIRECT_PPC*GCELLS;        // sparse group: the producers deposit themselves
 #pragma unroll 1
-        for( int r = 0; next_window( coff, total, lane, ws, q0, we, q1 ); r++, ws = we, q0 = q1 ) {
-            // this lane's cell of the window: the one with z = c among q0 .. q1-1 (the cell q0 alone when the window is a piece of it)
-            const int q = q0 + ( ( c - q0 ) & 7 );
-            const bool has = wk && q < max( q1, q0+1 );
+        for( int r = 0; !direct && next_window( coff, total, lane, ws, q0, we, q1 ); r++, ws = we, q0 = q1 ) {
+            // The window holds m <= 8 whole cells (or a piece of one).  A lane quad takes one cell; when the cells are
+            // dense (m <= 4) 2, 4 or 8 quads SHARE a cell, each taking every 2nd / 4th / 8th of its records, so that
+            // the walk stays ~GROUP/8 records long whatever the number of particles per cell.  The sums go to the
+            // J box at the end of every window.
+            const int m = max( q1 - q0, 1 );
+            const int sh = m > 4 ? 0 : ( m > 2 ? 1 : ( m > 1 ? 2 : 3 ) );
+            const int idx = c >> sh;
+            const int q = q0 + idx;
+            const bool has = wk && idx < m;
             int s = 0, hi = 0;
-            bool fin = false;
             if( has ) {
-                const int chi = coff[q+1];
-                s = max( coff[q], ws ) - ws;
-                hi = min( chi, we ) - ws;
-                fin = chi <= we && hi > s;                     // the cell ends in this window: its sums go to the J box
+                s = max( coff[q], ws ) - ws + ( c & ( ( 1 << sh ) - 1 ) );
+                hi = min( coff[q+1], we ) - ws;
             }
+            const int step = 1 << sh;
+            const bool fin = s < hi;
             tma_wait( &full_bar[grp], r & 1 );
             // software pipeline: the record of the next particle is loaded while the sums of this one are formed (its 28
             // registers are free as soon as the nine W are known)
@@ -1597,7 +1651,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                         for( int k=0; k<NW; k++ ) W[j][k] = fma( Ma[j], Mb[k], Da[j]*Db[k] );
                 }
                 const double c0_ = s < hi ? cf.x : 0., c1_ = s < hi ? cf.y : 0.;     // a lane past its cell adds nothing
-                s++;
+                s += step;
                 if( s < hi ) {
                     const double *rc = recbuf + rec_off( s );
                     const double2 *qa = reinterpret_cast<const double2 *>( rc + oa );
@@ -1617,7 +1671,7 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
             if( lane == 0 ) mbar_arrive( &empty_bar[grp] );    // the producers may write the records of the next window
             if( fin ) {
                 const int row = q >> 3;
-                jbox_t *jb = sJ + zj + ( ( 2*grp + ( row >> 2 ) )*T::JY + ( row & 3 ) )*T::JZ + c + jo_;
+                jbox_t *jb = sJ + zj + ( ( 2*grp + ( row >> 2 ) )*T::JY + ( row & 3 ) )*T::JZ + ( q & 7 ) + jo_;
 #pragma unroll
                 for( int f=0; f<2; f++ )
 #pragma unroll
@@ -1802,24 +1856,34 @@ __global__ void __launch_bounds__( o4::NTHR, 1 ) k_dynamics_o4( const GridDev g,
         const int base[3] = { g.begin[0] + g.o[0] + c0[0], g.begin[1] + g.o[1] + c0[1], g.begin[2] + g.o[2] + c0[2] };
         int qh = 0, qn = 0, bad = 0;
         int ws = 0, q0 = 0, we = 0, q1 = 0;
+        const bool direct = total < o2::DIRECT_PPC*GCELLS;       // sparse group: see k_dynamics_o2
+        auto window = [&]( int &ws_, int &q0_, int &we_, int &q1_ ) -> bool {
+            if( !direct ) return next_window( coff, total, lane, ws_, q0_, we_, q1_ );
+            we_ = min( ws_ + GROUP, total ); q1_ = q0_;
+            return ws_ < total;
+        };
         auto locate = [&]( int ws_, int q0_, int we_, int &row_, int &ip_, int &is_ ) {
             const int s_ = ws_ + L;
             row_ = q0_ >> 3;
             ip_ = -1; is_ = -1;
             if( s_ < we_ ) {
-                row_ += s_ >= coff[T::TZ*( row_+1 )];
+                if( direct ) {
+                    row_ = 0;
+#pragma unroll
+                    for( int k_=1; k_<8; k_++ ) row_ += s_ >= coff[T::TZ*k_];
+                } else row_ += s_ >= coff[T::TZ*( row_+1 )];
                 ip_ = cell_first[GCELLS*grp + T::TZ*row_] + ( s_ - coff[T::TZ*row_] );
                 is_ = a.perm ? a.perm[ip_] : ip_;
             }
         };
-        bool more = next_window( coff, total, lane, ws, q0, we, q1 );
+        bool more = window( ws, q0, we, q1 );
         int row = 0, ipi = -1, isi = -1;
         if( more ) locate( ws, q0, we, row, ipi, isi );
 
 #pragma unroll 1
         for( int r = 0; more; r++ ) {
             int nws = we, nq0 = q1, nwe = 0, nq1 = 0, nrow = 0, nip = -1, nis = -1;
-            const bool nmore = next_window( coff, total, lane, nws, nq0, nwe, nq1 );
+            const bool nmore = window( nws, nq0, nwe, nq1 );
             if( nmore ) locate( nws, nq0, nwe, nrow, nip, nis );
             const bool active = ipi >= 0;
             double dl1[3] = { 0., 0., 0. }, cr[3] = { 0., 0., 0. }, xdelta[3] = { 0., 0., 0. }, xnpos[3] = { 0., 0., 0. };
@@ -1909,7 +1973,7 @@ __global__ void __launch_bounds__( o4::NTHR, 1 ) k_dynamics_o4( const GridDev g,
                 a.key[ip] = key;
             }
             // ---------------- the consumers must have finished with the records of the previous round
-            if( r > 0 ) tma_wait( &empty_bar[grp], ( r-1 ) & 1 );
+            if( r > 0 && !direct ) tma_wait( &empty_bar[grp], ( r-1 ) & 1 );
             // ---------------- part B: new shape, the record of the deposit (see k_dynamics_o2), 5 home nodes per dimension
             int xmeta = 0;
             if( active ) {
@@ -1957,7 +2021,31 @@ __global__ void __launch_bounds__( o4::NTHR, 1 ) k_dynamics_o4( const GridDev g,
                 rec[SEO] = xe; rec[XCO] = xc;
             }
             __syncwarp();
-            if( lane == 0 ) mbar_arrive( &full_bar[grp] );
+            if( !direct ) {
+                if( lane == 0 ) mbar_arrive( &full_bar[grp] );
+            } else if( active ) {
+                // sparse group: this lane is the consumer of its own record, one (component, row) after the other
+                jbox_t *jcell = sJ + zj + ( ( cellt >> 5 )*T::JY + ( ( cellt >> 3 ) & 3 ) )*T::JZ + ( cellt & 7 );
+#pragma unroll 1
+                for( int cj=0; cj<3*NW; cj++ ) {
+                    const int cc = cj / NW, j = cj - NW*cc;
+                    const int da = cc == 0 ? 1 : 0, db = cc == 2 ? 1 : 2;
+                    const int sf_ = cc == 0 ? T::JY*T::JZ : ( cc == 1 ? T::JZ : 1 );
+                    const int sa_ = cc == 0 ? T::JZ : T::JY*T::JZ;
+                    const int sb_ = cc == 2 ? T::JZ : 1;
+                    const double ma = rec[2*NW*da + j], dj = rec[2*NW*da + NW + j];
+                    const double *rb = rec + 2*NW*db, *rcf = rec + CFO + NF*cc;
+                    jbox_t *jb = jcell + cc*T::JBOX + 2*sf_ + ( 1+j )*sa_ + sb_;
+                    if( rcf[0] != 0. || rcf[NF-1] != 0. ) {
+#pragma unroll
+                        for( int k_=0; k_<NW; k_++ ) {
+                            const double W = fma( ma, rb[k_], dj*rb[NW+k_] );
+#pragma unroll
+                            for( int f=0; f<NF; f++ ) jadd_scaled( jb + f*sf_ + k_*sb_, rcf[f]*W );
+                        }
+                    }
+                }
+            }
             // ---------------- one-dimension movers: the 65 values outside the home window, one particle per octet
             const bool one = active && nx == 1;
             const unsigned rem = __ballot_sync( 0xffffffffu, one );
@@ -2059,18 +2147,24 @@ __global__ void __launch_bounds__( o4::NTHR, 1 ) k_dynamics_o4( const GridDev g,
             asm volatile( "prefetch.global.L2 [%0];" :: "l"( a.qin + lo ) );
         }
         int ws = 0, q0 = 0, we, q1;
+        const bool direct = total < o2::DIRECT_PPC*GCELLS;
 #pragma unroll 1
         for( int r = 0; next_window( coff, total, lane, ws, q0, we, q1 ); r++, ws = we, q0 = q1 ) {
-            const int q = q0 + ( ( c - q0 ) & 7 );
-            const bool has = wk && q < max( q1, q0+1 );
+            if( direct ) break;                                // sparse group: the producers deposit themselves
+            // m <= 8 whole cells (or a piece of one) in the window; dense cells are shared by 2, 4 or 8 cell slots, each
+            // taking every 2nd / 4th / 8th record (see k_dynamics_o2); the sums go to the J box at the end of every window
+            const int m = max( q1 - q0, 1 );
+            const int sh = m > 4 ? 0 : ( m > 2 ? 1 : ( m > 1 ? 2 : 3 ) );
+            const int idx = c >> sh;
+            const int q = q0 + idx;
+            const bool has = wk && idx < m;
             int s = 0, hi = 0;
-            bool fin = false;
             if( has ) {
-                const int chi = coff[q+1];
-                s = max( coff[q], ws ) - ws;
-                hi = min( chi, we ) - ws;
-                fin = chi <= we && hi > s;
+                s = max( coff[q], ws ) - ws + ( c & ( ( 1 << sh ) - 1 ) );
+                hi = min( coff[q+1], we ) - ws;
             }
+            const int step = 1 << sh;
+            const bool fin = s < hi;
             tma_wait( &full_bar[grp], r & 1 );
 #pragma unroll 1
             while( __any_sync( 0xffffffffu, s < hi ) ) {
@@ -2090,13 +2184,13 @@ __global__ void __launch_bounds__( o4::NTHR, 1 ) k_dynamics_o4( const GridDev g,
                         for( int f=0; f<NF; f++ ) acc[f][k] = fma( cf[f], W, acc[f][k] );
                     }
                 }
-                s++;
+                s += step;
             }
             __syncwarp();
             if( lane == 0 ) mbar_arrive( &empty_bar[grp] );
             if( fin ) {
                 const int row = q >> 3;
-                jbox_t *jb = sJ + zj + ( ( 2*grp + ( row >> 2 ) )*T::JY + ( row & 3 ) )*T::JZ + c + jo_;
+                jbox_t *jb = sJ + zj + ( ( 2*grp + ( row >> 2 ) )*T::JY + ( row & 3 ) )*T::JZ + ( q & 7 ) + jo_;
 #pragma unroll
                 for( int f=0; f<NF; f++ )
 #pragma unroll

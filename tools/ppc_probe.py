@@ -2,7 +2,7 @@
 
     python tools/ppc_probe.py            (on a B200)
 
-Thermal plasma as in bench.py, created on the device at ppc = 8, 16, 32, 64 with the box sized to ~2 x 134 M particles;
+Thermal plasma as in bench.py, created on the device at ppc = 1, 2, 4, 8, 16, 32, 64 with the box sized to 2 x 64..134 M particles;
 5 warm-up steps, 5 timed steps (CUDA events), plus the time of the sort alone.  Prints one JSON line per case.
 """
 import json
@@ -19,7 +19,7 @@ if __name__ == "__main__":
     from smilei_b200 import namelist
     from smilei_b200.simulation import Simulation
     T, dx, dt = bench.plasma_constants()
-    cases = (((2, 2, 2), 256), ((4, 2, 2), 200), ((4, 4, 2), 160), ((4, 4, 4), 128))
+    cases = (((1, 1, 1), 400), ((2, 1, 1), 320), ((2, 2, 1), 256), ((2, 2, 2), 256), ((4, 2, 2), 200), ((4, 4, 2), 160), ((4, 4, 4), 128))
     if len(sys.argv) > 2:                  # one case: ppc as a,b,c and cells per dimension (e.g. under ncu)
         cases = ((tuple(int(v) for v in sys.argv[1].split(",")), int(sys.argv[2])),)
     for ppc, ncell in cases:
