@@ -334,6 +334,93 @@ def multi_gpu_parity(world, rank, local, grid, steps=6, nloc=24, ppc=8):
     return out
 
 
+LASER_WAKE_SRC = """
+dx, dtrans, dt = 0.2, 3., 0.19
+Main(geometry="3Dcartesian", interpolation_order=2, timestep=dt, number_of_timesteps=1000000,
+     cell_length=[dx, dtrans, dtrans], number_of_cells={gsize!r}, number_of_patches=[{npx}, 1, 1],
+     EM_boundary_conditions=[["silver-muller"]],
+     EM_boundary_conditions_k=[[1., 0., 0.], [-1., 0., 0.], [1., 0.005, 0.], [1., -0.005, 0.], [1., 0., 0.005], [1., 0., -0.005]],
+     solve_poisson=False)
+MovingWindow(time_start={tstart!r}, velocity_x=0.9997)
+Species(name="electron", position_initialization="regular", momentum_initialization="cold", particles_per_cell=1,
+        mass=1.0, charge=-1.0, charge_density=0.000494, pusher="vay", boundary_conditions=[["remove", "remove"]]*3)
+LaserGaussian3D(box_side="xmin", a0=2., focus=[0., {gsize[1]}*dtrans/2., {gsize[2]}*dtrans/2.], waist=10.,
+                time_envelope=tgaussian(center=2**0.5*19.80, fwhm=19.80))
+"""
+
+
+def laser_wake_run(args, world, rank, local):
+    """BASELINE.json configs[3] scaled (benchmarks/tst3d_s_o2_laser_wake_yee_vay.py: Vay pusher, cold plasma at
+    1 particle per cell, Gaussian laser through the Silver-Mueller xmin side with the benchmark's oblique absorption
+    vectors, `remove` particles, moving window sliding by one 8-cell patch): ncell^3 cells per GPU on the same rank
+    grids as the thermal workload.  Warm-up in the fixed box, then K timed steps WHILE THE WINDOW MOVES (field slide,
+    particles handed to the -x neighbour, new particles created on the last rank along x, re-sort)."""
+    import torch
+    import torch.distributed as dist
+    from smilei_b200 import capi, namelist
+    from smilei_b200.simulation import Simulation
+    grid = rank_grid_for(world)
+    n = args.ncell
+    gsize = [n * g for g in grid]
+    dt = 0.19
+    warm = max(args.warmup, 3)
+    params = namelist.load_namelist(LASER_WAKE_SRC.format(gsize=gsize, npx=gsize[0] // 8, tstart=(warm + 0.25) * dt),
+                                    is_source=True)
+    sim = Simulation(params, rank_grid=grid, rank=rank, device=f"cuda:{local}")
+    sim.create_particles()
+    npart = float(sum(sim.n_particles()))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    sim.run(warm)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    sim.run(args.steps)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = max(e0.elapsed_time(e1), 0.)
+    t = torch.tensor([ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0].item())
+    clocks = sampler.stop() if rank == 0 else None
+    uk, ue = sim.scalars()
+    npart_end = float(sum(sim.n_particles()))
+    line = {
+        "metric": METRIC, "value": npart * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"laser wake (BASELINE.json configs[3] scaled): {n}^3 cells per GPU, 1 ppc cold electrons, "
+                               f"Vay, order 2, Silver-Mueller + laser at xmin, remove, moving window (stride 8 cells), "
+                               f"rank grid {grid[0]}x{grid[1]}x{grid[2]}",
+                   "cells_per_gpu": n ** 3, "particles_total": int(npart), "particles_at_end": int(npart_end),
+                   "window_cells_moved": int(sim.simWindow.n_moved),
+                   "l2": "fields of 13 x 150 MB and particle columns larger than L2; no flush needed"},
+        "wall_ms_per_step": float(t[1].item()) / args.steps,
+        "yee_cell_updates_per_s_incl_everything": n ** 3 * world * args.steps / (ms * 1e-3),
+        "energies": {"Ukin": [float(v) for v in uk], "Uelm": ue},
+        "gpu_launches": int(capi.launch_count() - launches0),
+    }
+    if clocks is not None:
+        line["clocks"] = clocks
+    if rank == 0:
+        emit(line)
+    sim.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,6 +433,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--workload", default="thermal", choices=["thermal", "laser_wake"],
+                    help="thermal = BASELINE.json configs[1]/[4] (the bench contract); laser_wake = configs[3] scaled")
     ap.add_argument("--no-order4", action="store_true", help="skip the order-4 sub-measurement (configs[2])")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-rank vs 1-rank parity run at N > 1")
     args = ap.parse_args()
@@ -368,6 +457,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.workload == "laser_wake":
+        return laser_wake_run(args, world, rank, local)
     grid = rank_grid_for(world)
     nloc = args.ncell
     gsize = [nloc * g for g in grid]

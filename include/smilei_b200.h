@@ -171,6 +171,15 @@ int  sb200_apply_SM( sb200_patch *p, int i_boundary, const double k[3], const in
  * the last ncells real planes AFTER it.  The caller then appends the particles of the cells uncovered at the
  * right end of the box (sb200_species_append) and sorts. */
 int  sb200_window_shift( sb200_patch *p, int ncells );
+/* ParticleCreator on the DEVICE for position_initialization "regular" + momentum_initialization "cold"
+ * (src/Particles/ParticleCreator.cpp:627-667, 840-851) with the same count in every kept cell — what a moving window
+ * creates every shift in the laser-wake benchmarks (SimWindow.cpp:372-392).  `cells` = flat indices (x slowest) of the
+ * kept cells inside `box` cells starting at position `origin`; weight / charge per particle of each kept cell (the
+ * density and charge profiles are evaluated by the caller); regular_inv = 1/regular_number or 1/pow(nppc,1/3) as the
+ * reference computes it.  Appends ncells * prod(regular_number) particles; the species becomes unsorted. */
+int  sb200_species_append_regular( sb200_patch *p, int ispec, const double origin[3], const int box[3],
+                                   const int regular_number[3], const double regular_inv[3],
+                                   const int *cells, const double *weight, const short *charge, size_t ncells );
 /* HOST -> device append of n particles at the end of a species (ParticleCreator::create on the cells a moving
  * window uncovers, SimWindow.cpp:372-392); the species becomes unsorted. */
 int  sb200_species_append( sb200_patch *p, int ispec,

@@ -48,6 +48,7 @@ SYMBOLS = (
     "sb200_debug_flags", "sb200_species_init_thermal", "sb200_launch_count",
     "sb200_species_set_bc", "sb200_species_lost_energy", "sb200_apply_SM", "sb200_window_shift", "sb200_species_append",
     "sb200_hilbert_index3d", "sb200_create_particles_ref", "sb200_species_diag_fields", "sb200_compute_total_rhoJ",
+    "sb200_species_append_regular",
 )
 
 
@@ -238,6 +239,19 @@ class Patch:
         q = np.ascontiguousarray(q, dtype=np.int16)
         _check(lib().sb200_species_append(self._h, ispec, *[_p(a, np.float64) for a in cols], _p(q, np.int16),
                                           C.c_size_t(n)), "sb200_species_append")
+
+    def species_append_regular(self, ispec, origin, box, regular_number, regular_inv, cells, weight, charge):
+        """Device-side ParticleCreator (regular positions, cold): see sb200_species_append_regular."""
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        weight = np.ascontiguousarray(weight, dtype=np.float64)
+        charge = np.ascontiguousarray(charge, dtype=np.int16)
+        if len(cells) == 0:
+            return
+        _check(lib().sb200_species_append_regular(
+            self._h, ispec, (C.c_double * 3)(*[float(v) for v in origin]), (C.c_int * 3)(*[int(v) for v in box]),
+            (C.c_int * 3)(*[int(v) for v in regular_number]), (C.c_double * 3)(*[float(v) for v in regular_inv]),
+            _p(cells, np.int32), _p(weight, np.float64), _p(charge, np.int16), C.c_size_t(len(cells))),
+            "sb200_species_append_regular")
 
     def window_shift(self, ncells):
         _check(lib().sb200_window_shift(self._h, int(ncells)), "sb200_window_shift")

@@ -357,6 +357,76 @@ int sb200_species_append( sb200_patch *p, int ispec,
     return 0;
 }
 
+// ParticleCreator for the common laser-wake case, on the device: position_initialization "regular"
+// (ParticleCreator.cpp:627-667: x = x_cell + dx*0.975*(0.5 + i%c)/c per dimension), momentum_initialization "cold",
+// the same number of particles in every kept cell.  The profiles (density, charge) are the caller's business: it
+// hands the flat index of every kept cell inside `box`, its weight per particle and its charge.  The arithmetic is
+// written without contraction in the order of the host creator of this repository, so both produce the same doubles.
+__global__ void __launch_bounds__( 256 ) k_create_regular( double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
+        double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz, double *__restrict__ w, short *__restrict__ q,
+        int *__restrict__ key, const int *__restrict__ cells, const double *__restrict__ wcell, const short *__restrict__ qcell,
+        size_t ntot, int nppc, int b1, int b2, double o0, double o1, double o2, double d0, double d1, double d2,
+        int c0, int c1, int c2, double f0, double f1, double f2 )
+{
+    for( size_t t = blockIdx.x*( size_t )blockDim.x + threadIdx.x; t < ntot; t += ( size_t )gridDim.x*blockDim.x ) {
+        const size_t ic = t / ( size_t )nppc;
+        int i = ( int )( t - ic*( size_t )nppc );
+        const int cell = cells[ic];
+        const int k2 = cell % b2, k1 = ( cell / b2 ) % b1, k0 = cell / ( b2*b1 );
+        // origin + ci*cell_length + (cell_length*0.975*inv)*(0.5 + i % c)
+        x[t] = __dadd_rn( __dadd_rn( o0, __dmul_rn( ( double )k0, d0 ) ), __dmul_rn( f0, __dadd_rn( 0.5, ( double )( i % c0 ) ) ) );
+        i /= c0;
+        y[t] = __dadd_rn( __dadd_rn( o1, __dmul_rn( ( double )k1, d1 ) ), __dmul_rn( f1, __dadd_rn( 0.5, ( double )( i % c1 ) ) ) );
+        i /= c1;
+        z[t] = __dadd_rn( __dadd_rn( o2, __dmul_rn( ( double )k2, d2 ) ), __dmul_rn( f2, __dadd_rn( 0.5, ( double )( i % c2 ) ) ) );
+        px[t] = 0.; py[t] = 0.; pz[t] = 0.;
+        w[t] = wcell[ic];
+        q[t] = qcell[ic];
+        key[t] = 0;
+    }
+}
+
+int sb200_species_append_regular( sb200_patch *p, int ispec, const double origin[3], const int box[3], const int regular_number[3],
+                                  const double regular_inv[3], const int *cells, const double *weight, const short *charge, size_t ncells )
+{
+    SB200_CHECK( p && ispec >= 0 && ispec < p->nspec && origin && box && regular_number && regular_inv, "sb200_species_append_regular: bad arguments" );
+    if( ncells == 0 ) return 0;
+    SB200_CHECK( cells && weight && charge, "sb200_species_append_regular: null cell list" );
+    const int nppc = regular_number[0]*regular_number[1]*regular_number[2];
+    SB200_CHECK( nppc > 0, "sb200_species_append_regular: regular_number must be positive" );
+    SB200_CUDA( cudaSetDevice( p->device ) );
+    if( materialize( p, ispec ) ) return 1;
+    SpeciesDev &s = p->sp[ispec];
+    const size_t n = ncells*( size_t )nppc;
+    if( grow_species( p, ispec, s.n + n ) ) return 1;
+    // the three per-cell lists travel through the staging buffer: ints | doubles | shorts
+    const size_t need = ( ncells*sizeof( int ) + 7 )/8 + ncells + ( ncells*sizeof( short ) + 7 )/8 + 8;
+    if( ensure_stage( p, need ) ) return 1;
+    int *d_cells = reinterpret_cast<int *>( p->stage );
+    double *d_w = p->stage + ( ncells*sizeof( int ) + 7 )/8;
+    short *d_q = reinterpret_cast<short *>( d_w + ncells );
+    SB200_CUDA( cudaMemcpyAsync( d_cells, cells, ncells*sizeof( int ), cudaMemcpyHostToDevice, p->stream ) );
+    SB200_CUDA( cudaMemcpyAsync( d_w, weight, ncells*sizeof( double ), cudaMemcpyHostToDevice, p->stream ) );
+    SB200_CUDA( cudaMemcpyAsync( d_q, charge, ncells*sizeof( short ), cudaMemcpyHostToDevice, p->stream ) );
+    const GridDev &g = p->gd;
+    double f[3];
+    for( int d=0; d<3; d++ ) f[d] = g.cell[d]*0.975*regular_inv[d];          // left to right, as the host creator
+    const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*8 ? ( n + 255 )/256 : 148*8 );
+    k_create_regular<<<blocks, 256, 0, p->stream>>>( s.col[0] + s.n, s.col[1] + s.n, s.col[2] + s.n, s.col[3] + s.n, s.col[4] + s.n,
+            s.col[5] + s.n, s.col[6] + s.n, s.q + s.n, s.key + s.n, d_cells, d_w, d_q, n, nppc, box[1], box[2],
+            origin[0], origin[1], origin[2], g.cell[0], g.cell[1], g.cell[2],
+            regular_number[0], regular_number[1], regular_number[2], f[0], f[1], f[2] );
+    sb200::g_launches++;
+    SB200_CUDA( cudaGetLastError() );
+    const size_t n0 = s.n;
+    s.n += n;
+    s.sorted = false;
+    s.count_valid = false;
+    if( update_qwmax( p, ispec, n0, n ) ) return 1;
+    SB200_CUDA( cudaStreamSynchronize( p->stream ) );       // the host lists may be reused by the caller
+    return 0;
+}
+
 // particles the window leaves behind: dropped on the patch at the left end of the box, tagged for the -x neighbour
 // (and listed, as the dynamics kernel lists its leavers) elsewhere
 __global__ void __launch_bounds__( 256 ) k_window_tag( const double *__restrict__ x, int *__restrict__ key, size_t n, double xmin_new,

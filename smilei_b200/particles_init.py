@@ -154,6 +154,44 @@ def create_reference_streams(params, species, n, pcoord):
     return created
 
 
+def regular_cold_cells(params, sp, n, pcoord, origin_cells=None):
+    """What the device-side creator (sb200_species_append_regular) needs for species `sp` in a box of `n` cells, or None
+    when the species is not of that kind: position_initialization "regular", momentum_initialization "cold", zero mean
+    velocity and the same particles_per_cell in every kept cell.  Returns (origin, cells, weight, charge,
+    regular_number, regular_inv): the profiles are evaluated here exactly as `create` does."""
+    if sp.position_initialization != "regular" or sp.momentum_initialization != "cold":
+        return None
+    if any(abs(v) > 0 for v in sp.mean_velocity):
+        return None
+    cell = params.cell_length
+    if origin_cells is None:
+        origin = [pcoord[d] * n[d] * cell[d] for d in range(3)]
+    else:
+        origin = [origin_cells[d] * cell[d] for d in range(3)]
+    ic, jc, kc = np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(n[2]), indexing="ij")
+    X = origin[0] + (ic + 0.5) * cell[0]
+    Y = origin[1] + (jc + 0.5) * cell[1]
+    Z = origin[2] + (kc + 0.5) * cell[2]
+    nppc = _profile(sp.particles_per_cell, X, Y, Z).astype(int)
+    charge = _profile(sp.charge, X, Y, Z)
+    if sp.charge_density is not None:
+        dens = _profile(sp.charge_density, X, Y, Z)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dens = np.where(charge != 0, np.abs(dens / charge), 0.)
+    else:
+        dens = np.abs(_profile(sp.number_density, X, Y, Z))
+    dens = dens * params.cell_volume
+    keep = (dens > 0) & (nppc > 0)
+    cells = np.flatnonzero(keep.ravel())
+    npc = nppc.ravel()[cells]
+    if len(cells) == 0:
+        return origin, cells.astype(np.int32), np.zeros(0), np.zeros(0, dtype=np.int16), [1, 1, 1], [1., 1., 1.]
+    if npc.min() != npc.max():
+        return None
+    c, inv = _regular_counts(int(npc[0]), sp.regular_number)
+    return origin, cells.astype(np.int32), dens.ravel()[cells] / npc, charge.ravel()[cells].astype(np.int16), c, inv
+
+
 def create(params, sp, n, pcoord, seed, rank, positions=None, origin_cells=None):
     """Arrays (x,y,z,px,py,pz,w,q) of species `sp` inside the patch at `pcoord` with `n` cells, or — with
     `origin_cells` — inside the box of `n` cells that starts at that global cell (the cells a moving window

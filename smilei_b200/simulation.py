@@ -178,6 +178,17 @@ class Simulation:
         seed = self.params.random_seed if seed is None else seed
         created = {}
         for sp in self.vecSpecies:
+            dev = particles_init.regular_cold_cells(self.params, sp.sparams, self.n, self.pcoord) \
+                if hasattr(self.patch, "species_append_regular") else None
+            if dev is not None:
+                # regular positions, cold: created on the device (the same doubles as the host creator)
+                origin, cells, weight, charge, c, inv = dev
+                n = len(cells) * c[0] * c[1] * c[2]
+                self.patch.species_config(sp.ispec, sp.mass_, sp.pusher, int(max(n * self.capacity_factor, n + 4096)))
+                self._set_species_bc(sp.ispec)
+                self.patch.species_append_regular(sp.ispec, origin, self.n, c, inv, cells, weight, charge)
+                self.patch.sort(sp.ispec)
+                continue
             src = created.get(sp.sparams.position_initialization)
             arrays = particles_init.create(self.params, sp.sparams, self.n, self.pcoord, seed, self.rank,
                                            positions=None if src is None else (src["x"], src["y"], src["z"]))
@@ -285,6 +296,13 @@ class Simulation:
                 first_new = self.params.global_size[0] + w.n_moved - S
                 box = (S, self.n[1], self.n[2])
                 origin = (first_new, self.pcoord[1] * self.n[1], self.pcoord[2] * self.n[2])
+                dev = particles_init.regular_cold_cells(self.params, sp.sparams, box, self.pcoord, origin_cells=origin) \
+                    if hasattr(self.patch, "species_append_regular") else None
+                if dev is not None:
+                    o_, cells, weight, charge, c, inv = dev
+                    self.patch.species_append_regular(sp.ispec, o_, box, c, inv, cells, weight, charge)
+                    self.patch.sort(sp.ispec)
+                    continue
                 src = created.get(sp.sparams.position_initialization)
                 arrays = particles_init.create(self.params, sp.sparams, box, self.pcoord, self.params.random_seed + w.n_moved,
                                                self.rank, positions=None if src is None else (src["x"], src["y"], src["z"]),

@@ -793,3 +793,37 @@ def test_species_grows_on_demand_and_empty_rank_forwards_corner_particles(sb, or
     for c in allp:
         assert np.array_equal(after[c], allp[c][perm]), c
     p.close()
+
+
+def test_device_creator_regular_cold_equals_host_creator(sb):
+    """sb200_species_append_regular (the moving window's particle creation on the device, SimWindow.cpp:372-392 /
+    ParticleCreator.cpp:627-667) gives the doubles of the host creator: positions, weights, charges, zero momenta —
+    with a density profile that leaves some cells empty and with 1 and 8 particles per cell."""
+    from smilei_b200 import namelist, particles_init
+    for nppc in (1, 8):
+        src = f"""
+Main(geometry="3Dcartesian", interpolation_order=2, timestep=0.09, number_of_timesteps=1, cell_length=[0.1, 0.3, 0.25],
+     number_of_cells=[16, 12, 8], number_of_patches=[4, 1, 1], EM_boundary_conditions=[["silver-muller"]])
+Species(name="electron", position_initialization="regular", momentum_initialization="cold", particles_per_cell={nppc},
+        mass=1.0, charge=-1.0, number_density=lambda x, y, z: 0.003*(x > 0.65)*(1. + 0.1*y),
+        pusher="vay", boundary_conditions=[["remove"]])
+"""
+        params = namelist.load_namelist(src, is_source=True)
+        sp = params.species[0]
+        box, origin_cells = (8, 12, 8), (4, 0, 0)
+        host = particles_init.create(params, sp, box, (0, 0, 0), 0, 0, origin_cells=origin_cells)
+        dev = particles_init.regular_cold_cells(params, sp, box, (0, 0, 0), origin_cells=origin_cells)
+        assert dev is not None
+        origin, cells, weight, charge, c, inv = dev
+        assert 0 < len(cells) < 8 * 12 * 8                      # the vacuum cells are skipped
+        p = sb.Patch((16, 12, 8), (0.1, 0.3, 0.25), 0.09, interp_order=2, n_species=1)
+        p.species_config(0, 1.0, "vay", 16)                      # grows on demand
+        p.species_append_regular(0, origin, box, c, inv, cells, weight, charge)
+        assert p.species_count(0) == len(host["x"]) == len(cells) * nppc
+        p.sort(0)
+        got = p.species_get(0)
+        order = np.lexsort((host["z"], host["y"], host["x"]))
+        gorder = np.lexsort((got["z"], got["y"], got["x"]))
+        for k in ("x", "y", "z", "px", "py", "pz", "w", "q"):
+            assert np.array_equal(got[k][gorder], host[k][order]), (nppc, k)
+        p.close()
