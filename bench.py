@@ -252,11 +252,7 @@ def order4_run(args, local):
             sp.dynamics(sim.EMfields, sim.smpi)
             b.record()
             dyn_ev.append((a, b))
-        sim.exchanger.exchange_particles(2)
-        sim.exchanger.sum_J()
-        sim.EMfields.MaxwellAmpereSolver_(sim.EMfields)
-        sim.EMfields.MaxwellFaradaySolver_(sim.EMfields)
-        sim.exchanger.exchange_B()
+        sim.exchange_and_solve()
         for sp in sim.vecSpecies:
             sim.patch.sort(sp.ispec)
         sim.EMfields.centerMagneticFields()
@@ -499,15 +495,9 @@ def main():
             sp.dynamics(sim.EMfields, sim.smpi)
             b.record()
             dyn_ev.append((a, b))
-        sim.exchanger.exchange_particles(2)
-        sim.exchanger.sum_J()
         a, b = ev(), ev()
-        a.record()
-        sim.EMfields.MaxwellAmpereSolver_(sim.EMfields)
-        sim.EMfields.MaxwellFaradaySolver_(sim.EMfields)
-        b.record()
+        sim.exchange_and_solve(maxwell_events=(a, b))     # particle exchange (overlapped at N > 1), J sum, Yee, B exchange
         mw_ev.append((a, b))
-        sim.exchanger.exchange_B()
         for sp in sim.vecSpecies:
             p.sort(sp.ispec)
         a, b = ev(), ev()

@@ -100,18 +100,20 @@ class Exchanger:
         for w in dist.batch_isend_irecv(p2p):
             w.wait()
 
-    def _exchange_slabs(self, dim, to_lo, to_hi, size_from_lo=None, size_from_hi=None):
+    def _exchange_slabs(self, dim, to_lo, to_hi, size_from_lo=None, size_from_hi=None, tag=""):
         """Send `to_lo` to the -dim neighbour and `to_hi` to the +dim one; returns (from_lo, from_hi) = what
         those neighbours sent to me.  By default the exchange is symmetric (I receive from a side as much as
-        I send to it); for particle records the incoming sizes are given."""
+        I send to it); for particle records the incoming sizes are given.  `tag` names the caller's own set of
+        staging buffers: the particle exchange runs on a side stream concurrently with the J sum and the B exchange
+        (Simulation.exchange_and_solve), so the three must not share send / receive buffers."""
         lo, hi = self.nbr[dim]
         n_lo, n_hi = to_lo.numel(), to_hi.numel()
         m_lo = n_hi if size_from_lo is None else size_from_lo     # the -dim neighbour sends me ITS to_hi block
         m_hi = n_lo if size_from_hi is None else size_from_hi
         if lo is None or hi is None:
             # box side without neighbour: nothing goes or comes that way (callers skip that side's unpack)
-            from_lo = self._buf(("rl", dim), m_lo)[:0 if lo is None else m_lo]
-            from_hi = self._buf(("rh", dim), m_hi)[:0 if hi is None else m_hi]
+            from_lo = self._buf((tag + "rl", dim), m_lo)[:0 if lo is None else m_lo]
+            from_hi = self._buf((tag + "rh", dim), m_hi)[:0 if hi is None else m_hi]
             ops = []
             if lo is not None:
                 ops.append((lo, to_lo, from_lo))
@@ -122,15 +124,15 @@ class Exchanger:
             return from_lo, from_hi
         if lo == hi:
             # one peer on both sides: [payload for its +side | payload for its -side] in one message
-            send = self._buf(("s2", dim), n_lo + n_hi)[:n_lo + n_hi]
+            send = self._buf((tag + "s2", dim), n_lo + n_hi)[:n_lo + n_hi]
             send[:n_lo].copy_(to_lo)
             send[n_lo:].copy_(to_hi)
-            recv = self._buf(("r2", dim), m_hi + m_lo)[:m_hi + m_lo]
+            recv = self._buf((tag + "r2", dim), m_hi + m_lo)[:m_hi + m_lo]
             self._sendrecv([(lo, send, recv)])
             # the peer's first block was meant for its -dim neighbour's +side = my +side
             return recv[m_hi:], recv[:m_hi]
-        from_lo = self._buf(("rl", dim), m_lo)[:m_lo]
-        from_hi = self._buf(("rh", dim), m_hi)[:m_hi]
+        from_lo = self._buf((tag + "rl", dim), m_lo)[:m_lo]
+        from_hi = self._buf((tag + "rh", dim), m_hi)[:m_hi]
         self._sendrecv([(lo, to_lo, from_lo), (hi, to_hi, from_hi)])
         return from_lo, from_hi
 
@@ -159,7 +161,7 @@ class Exchanger:
                 p.halo_pack(f, dim, self.n[dim], g, to_hi[off:off + s].data_ptr())  # my planes [n,n+gsp)
                 off += s
             self._sync_patch_stream()
-            from_lo, from_hi = self._exchange_slabs(dim, to_lo, to_hi)
+            from_lo, from_hi = self._exchange_slabs(dim, to_lo, to_hi, tag="J")
             off = 0
             for f, g, s in zip(fields, gsp, sizes):
                 # the -dim neighbour's [n,n+gsp) planes are my [0,gsp); the +dim one's [0,gsp) are my [n,n+gsp)
@@ -232,7 +234,7 @@ class Exchanger:
             has_lo, has_hi = self.nbr[dim][0] is not None, self.nbr[dim][1] is not None
             cnt_lo = torch.tensor([float(v) for v in c_lo], dtype=torch.float64, device=self.device)
             cnt_hi = torch.tensor([float(v) for v in c_hi], dtype=torch.float64, device=self.device)
-            r_lo, r_hi = self._exchange_slabs(dim, cnt_lo, cnt_hi)
+            r_lo, r_hi = self._exchange_slabs(dim, cnt_lo, cnt_hi, tag="C")
             n_from_lo = [int(v) for v in r_lo.cpu().tolist()] if has_lo else [0] * n_species
             n_from_hi = [int(v) for v in r_hi.cpu().tolist()] if has_hi else [0] * n_species
             # per direction, every species block is padded to the largest count of that direction, which both
@@ -246,7 +248,7 @@ class Exchanger:
                 pack(s, dim, 1, wrap_hi, to_hi[RECORD * pad_to_hi * s:].data_ptr(), pad_to_hi, c_hi[s])
             self._sync_patch_stream()
             from_lo, from_hi = self._exchange_slabs(dim, to_lo, to_hi, RECORD * pad_from_lo * n_species,
-                                                    RECORD * pad_from_hi * n_species)
+                                                    RECORD * pad_from_hi * n_species, tag="P")
             for s in range(n_species):
                 # arrivals from the -dim neighbour first, then from the +dim one (deterministic order)
                 if has_lo:

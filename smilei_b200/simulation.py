@@ -114,7 +114,7 @@ class Simulation:
     of the namelist is split evenly, one patch per rank, periodic."""
 
     def __init__(self, params, rank_grid=(1, 1, 1), rank=0, patch_factory=None, device=None, group=None,
-                 capacity_factor=1.25):
+                 capacity_factor=1.25, overlap_exchange=True):
         params.check_hot_path()
         self.params = params
         self.rank_grid = tuple(int(v) for v in rank_grid)
@@ -139,9 +139,11 @@ class Simulation:
         self.patch = patch_factory(n=self.n, cell_length=tuple(params.cell_length), dt=params.timestep,
                                    interp_order=params.interpolation_order, n_species=len(params.species),
                                    pcoord=self.pcoord, npatch=self.rank_grid, oversize=tuple(params.oversize))
+        self.overlap_exchange = overlap_exchange
         if self.device.type == "cuda" and hasattr(self.patch, "bind_stream"):
             # the library's kernels and torch.distributed's collectives share ONE stream: torch's current one
             self.patch.bind_stream(torch.cuda.current_stream(self.device).cuda_stream)
+            self._side_stream = torch.cuda.Stream(self.device)      # the particle exchange overlaps the field part on it
         self.EMfields = ElectroMagn(params, self.patch)
         self.vecSpecies = [Species(params, sp, self.patch, i) for i, sp in enumerate(params.species)]
         self.smpi = _Smpi()
@@ -247,22 +249,7 @@ class Simulation:
         self.EMfields.restartRhoJ()                                   # VectorPatch.cpp:4779
         for sp in self.vecSpecies:
             sp.dynamics(self.EMfields, self.smpi, diag_flag)          # VectorPatch.cpp:4821
-        # ---- initExchParticles .. finalizeExchParticles (Smilei.cpp:528,637)
-        self.exchanger.exchange_particles(len(self.vecSpecies))
-        # ---- sumDensities (Smilei.cpp:531; VectorPatch.cpp:905-963).  On a diag step the totals first receive the
-        #      species' own arrays (computeTotalRhoJ), rho is summed with J (sumRhoJ), and so are the species' arrays
-        #      (sumRhoJs) so that a field diagnostic reads complete values on the shared planes
-        if diag_flag:
-            self.EMfields.computeTotalRhoJ()
-            self.exchanger.sum_J(fields=J_FIELDS + ("rho",))
-            for ispec, names in getattr(self.EMfields, "species_fields", {}).items():
-                self.exchanger.sum_J(fields=tuple((n, ispec) for n in names))
-        else:
-            self.exchanger.sum_J()
-        # ---- solveMaxwell (Smilei.cpp:547): saveMagneticFields, Ampere, Faraday, exchangeB
-        self.EMfields.MaxwellAmpereSolver_(self.EMfields)
-        self.EMfields.MaxwellFaradaySolver_(self.EMfields)
-        self.exchanger.exchange_B()
+        self.exchange_and_solve(diag_flag)
         # ---- importAndSortParticles (Smilei.cpp:637)
         for sp in self.vecSpecies:
             p.sort(sp.ispec)
@@ -276,6 +263,53 @@ class Simulation:
         if moving:
             self.moveWindow(time_dual)
         self.itime += 1
+
+    def exchange_and_solve(self, diag_flag=False, maxwell_events=None):
+        """The middle of a time step: particle exchange, density sum, Maxwell solve, B exchange (Smilei.cpp:528-547,637).
+        `maxwell_events`: a pair of CUDA events recorded around the two solver calls (bench.py)."""
+        p = self.patch
+        # ---- initExchParticles (Smilei.cpp:528) .. sumDensities (:531) .. solveMaxwell (:547) .. finalizeExchParticles
+        #      (:637).  The reference starts the particle exchange, sums the densities and solves Maxwell while the
+        #      particles travel, and completes the exchange before the sort.  Across ranks on the GPU the same overlap:
+        #      the field part is enqueued on the main stream, the particle exchange (pack kernels, NCCL messages,
+        #      unpack kernels: they touch no field array and none of the field scratch) runs on a side stream that
+        #      only waits for the dynamics kernels, and the sort waits for both.
+        overlap = self.overlap_exchange and self.world > 1 and self.device.type == "cuda" and hasattr(p, "bind_stream")
+        if overlap:
+            main = torch.cuda.current_stream(self.device)
+            after_dynamics = torch.cuda.Event()
+            after_dynamics.record(main)
+        else:
+            self.exchanger.exchange_particles(len(self.vecSpecies))
+        # ---- sumDensities (Smilei.cpp:531; VectorPatch.cpp:905-963).  On a diag step the totals first receive the
+        #      species' own arrays (computeTotalRhoJ), rho is summed with J (sumRhoJ), and so are the species' arrays
+        #      (sumRhoJs) so that a field diagnostic reads complete values on the shared planes
+        if diag_flag:
+            self.EMfields.computeTotalRhoJ()
+            self.exchanger.sum_J(fields=J_FIELDS + ("rho",))
+            for ispec, names in getattr(self.EMfields, "species_fields", {}).items():
+                self.exchanger.sum_J(fields=tuple((n, ispec) for n in names))
+        else:
+            self.exchanger.sum_J()
+        # ---- solveMaxwell (Smilei.cpp:547): saveMagneticFields, Ampere, Faraday, exchangeB
+        if maxwell_events is not None:
+            maxwell_events[0].record()
+        self.EMfields.MaxwellAmpereSolver_(self.EMfields)
+        self.EMfields.MaxwellFaradaySolver_(self.EMfields)
+        if maxwell_events is not None:
+            maxwell_events[1].record()
+        self.exchanger.exchange_B()
+        if overlap:
+            with torch.cuda.stream(self._side_stream):
+                self._side_stream.wait_event(after_dynamics)
+                p.bind_stream(self._side_stream.cuda_stream)
+                try:
+                    self.exchanger.exchange_particles(len(self.vecSpecies))
+                finally:
+                    p.bind_stream(main.cuda_stream)
+                exchanged = torch.cuda.Event()
+                exchanged.record(self._side_stream)
+            main.wait_event(exchanged)
 
     def moveWindow(self, time_dual):
         """SimWindow::shift (SimWindow.cpp:98-550) for one patch spanning the box along x."""
