@@ -250,7 +250,8 @@ Main(geometry="3Dcartesian", interpolation_order={order}, timestep=dt, simulatio
      EM_boundary_conditions_k={kvec}, solve_poisson=False)
 MovingWindow(time_start=Main.grid_length[0], velocity_x=0.9997)
 Species(name="electron", position_initialization="regular", momentum_initialization="cold", particles_per_cell=1,
-        mass=1.0, charge=-1.0, charge_density=0.000494, pusher="{pusher}", boundary_conditions=[["remove", "remove"]]*3)
+        mass=1.0, charge=-1.0, charge_density=0.000494, mean_velocity=[0., 0., 0.], temperature=[0.0],
+        pusher="{pusher}", boundary_conditions=[["remove", "remove"]]*3)
 LaserGaussian3D(box_side="xmin", a0=2., focus=[0., Main.grid_length[1]/2., Main.grid_length[2]/2.], waist=10.,
                 time_envelope=tgaussian(center=2**0.5*19.80, fwhm=19.80))
 """
