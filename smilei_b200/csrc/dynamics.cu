@@ -62,7 +62,10 @@ template<int ORDER, int TX_ = 4, int TY_ = 4, int TZ_ = 8> struct Tile {
     static constexpr int FX = TX+2*H+1, FY = TY+2*H+1, FZ = ( TZ+2*H+2 + 1 )/2*2;
     // J accumulation box; along z it may start one element early so that the TMA reduction of the box into
     // HBM begins on a 16-B boundary (needed when oversize-H-1 is odd), hence the spare and the even extent
-    static constexpr int JX = TX+2*H+2, JY = TY+2*H+2, JZ = ( TZ+2*H+2 + ( ( ORDER-H-1 ) & 1 ) + 1 )/2*2;
+    // At order 4 the even extent would be 16 doubles = 32 banks: the five rows j of a consumer's (cell, component)
+    // lanes would add into the SAME bank (measured: 13 wavefronts per ATOMS instead of 1).  Two spare elements
+    // (rows 36 words apart) spread them; the TMA reduction adds the two zero columns or clips them at the array edge.
+    static constexpr int JX = TX+2*H+2, JY = TY+2*H+2, JZ = ( TZ+2*H+2 + ( ( ORDER-H-1 ) & 1 ) + 1 )/2*2 + ( ORDER == 4 ? 2 : 0 );
     static constexpr int FVOL = FX*FY*FZ, JVOL = JX*JY*JZ;
     static constexpr int FBOX = ( FVOL + 15 )/16*16;          // box strides in shared memory: 128-B aligned (TMA source / destination)
     static constexpr int JBOX = ( JVOL + 15 )/16*16;
