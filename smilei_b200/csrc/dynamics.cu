@@ -1380,9 +1380,6 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
             // ---------------- part A: gather, push, tag, key
             if( active ) {
                 const size_t ip = ( size_t )ipi, is = ( size_t )isi;
-                double px = a.in[3][is], py = a.in[4][is], pz = a.in[5][is];
-                const short charge = a.qin[is];
-
                 double cd[3][NW];
                 int sp[3], sd[3], cl[3];
 #pragma unroll
@@ -1413,6 +1410,12 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                 const double Ex = gather<T>( sF+0*T::FBOX, cd[0], S0[1], S0[2], sd[0], sp[1], sp[2] );
                 const double Ey = gather<T>( sF+1*T::FBOX, S0[0], cd[1], S0[2], sp[0], sd[1], sp[2] );
                 const double Ez = gather<T>( sF+2*T::FBOX, S0[0], S0[1], cd[2], sp[0], sp[1], sd[2] );
+                // the momenta are not needed before the push: their loads are issued here, after the electric field, so that
+                // they do not hold registers during the first half of the gather (the empty asm ties the index to Ez)
+                size_t isl = is;
+                asm volatile( "" : "+l"( isl ) : "d"( Ez ) );
+                double px = a.in[3][isl], py = a.in[4][isl], pz = a.in[5][isl];
+                const short charge = a.qin[isl];
                 const double Bx = gather<T>( sF+3*T::FBOX, S0[0], cd[1], cd[2], sp[0], sd[1], sd[2] );
                 const double By = gather<T>( sF+4*T::FBOX, cd[0], S0[1], cd[2], sd[0], sp[1], sd[2] );
                 const double Bz = gather<T>( sF+5*T::FBOX, cd[0], cd[1], S0[2], sd[0], sd[1], sp[2] );
