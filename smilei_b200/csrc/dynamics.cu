@@ -1157,6 +1157,13 @@ constexpr int REC = 26;                                  // doubles per record: 
 // slot L of a group's record buffer; one 16-byte skew every 16 slots: with exactly 16 particles per cell the 8
 // lane quads of the consumer read slots 16 apart, which would otherwise all sit in the same banks
 __device__ __forceinline__ int rec_off( int L ) { return L*REC + 2*( L >> 4 ); }
+__device__ __forceinline__ unsigned rec_byte( int L ) { return ( unsigned )( L*( REC*8 ) + ( ( L >> 4 ) << 4 ) ); }     // 8*rec_off(L)
+// predicated 16-byte shared-memory load (no branch: the compiler keeps it where it is written; a lane that is switched
+// off keeps the old value and asks nothing of the shared-memory pipe)
+__device__ __forceinline__ void lds_v2( double2 &v, unsigned addr, int on )
+{
+    asm volatile( "{\n .reg .pred p;\n setp.ne.s32 p, %3, 0;\n @p ld.shared.v2.f64 {%0, %1}, [%2];\n}" : "+d"( v.x ), "+d"( v.y ) : "r"( addr ), "r"( on ) );
+}
 constexpr int RECBUF = GROUP*REC + 2*( GROUP/16 );       // doubles per group
 constexpr int DIRECT_PPC = 6;                            // a group with fewer particles per cell on average deposits lane by lane (see the kernel)
 constexpr int XQ2 = 8;                                   // crosser queue entries per producer warp
@@ -1581,6 +1588,8 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
         const int cc = wk ? ( lane & 3 ) : 0;                  // current component
         const int da = cc == 0 ? 1 : 0, db = cc == 2 ? 1 : 2;  // its transverse dimensions
         const int oa = 6*da, ob = 6*db, oc = 18 + 2*cc;
+        unsigned pa = smem_u32( recbuf + oa ), pb = smem_u32( recbuf + ob ), pc = smem_u32( recbuf + oc );   // this lane's three pieces of record 0
+        asm volatile( "" : "+r"( pa ), "+r"( pb ), "+r"( pc ) );      // kept in registers: the compiler would rebuild them from the thread index in every turn
         // J-box strides of the flux index and of the two transverse indices, and the offset of (f,j,k) = (0,0,0)
         const int sf_ = cc == 0 ? T::JY*T::JZ : ( cc == 1 ? T::JZ : 1 );
         const int sa_ = cc == 0 ? T::JZ : T::JY*T::JZ;
@@ -1635,15 +1644,18 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
             const bool fin = s < hi;
             tma_wait( &full_bar[grp], r & 1 );
             // software pipeline: the record of the next particle is loaded while the sums of this one are formed (its 28
-            // registers are free as soon as the nine W are known)
+            // registers are free as soon as the nine W are known).  The loads are predicated instructions on shared-memory
+            // addresses kept in registers: as a branch around plain loads the compiler put them AFTER the 18 accumulations
+            // and rebuilt the three lane offsets from the thread index in every turn (83 instructions per record where the
+            // arithmetic needs 36).
             double2 a0, a1, a2, b0, b1, b2, cf;
             a0 = a1 = a2 = b0 = b1 = b2 = cf = make_double2( 0., 0. );
-            if( s < hi ) {
-                const double *rc = recbuf + rec_off( s );
-                const double2 *qa = reinterpret_cast<const double2 *>( rc + oa );
-                const double2 *qb = reinterpret_cast<const double2 *>( rc + ob );
-                a0 = qa[0]; a1 = qa[1]; a2 = qa[2]; b0 = qb[0]; b1 = qb[1]; b2 = qb[2];
-                cf = *reinterpret_cast<const double2 *>( rc + oc );
+            {
+                const unsigned o = rec_byte( s );
+                const int on = s < hi;
+                lds_v2( a0, pa + o, on ); lds_v2( a1, pa + o + 16, on ); lds_v2( a2, pa + o + 32, on );
+                lds_v2( b0, pb + o, on ); lds_v2( b1, pb + o + 16, on ); lds_v2( b2, pb + o + 32, on );
+                lds_v2( cf, pc + o, on );
             }
 #pragma unroll 1
             while( __any_sync( 0xffffffffu, s < hi ) ) {
@@ -1658,12 +1670,12 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
                 }
                 const double c0_ = s < hi ? cf.x : 0., c1_ = s < hi ? cf.y : 0.;     // a lane past its cell adds nothing
                 s += step;
-                if( s < hi ) {
-                    const double *rc = recbuf + rec_off( s );
-                    const double2 *qa = reinterpret_cast<const double2 *>( rc + oa );
-                    const double2 *qb = reinterpret_cast<const double2 *>( rc + ob );
-                    a0 = qa[0]; a1 = qa[1]; a2 = qa[2]; b0 = qb[0]; b1 = qb[1]; b2 = qb[2];
-                    cf = *reinterpret_cast<const double2 *>( rc + oc );
+                {
+                    const unsigned o = rec_byte( s );
+                    const int on = s < hi;
+                    lds_v2( a0, pa + o, on ); lds_v2( a1, pa + o + 16, on ); lds_v2( a2, pa + o + 32, on );
+                    lds_v2( b0, pb + o, on ); lds_v2( b1, pb + o + 16, on ); lds_v2( b2, pb + o + 32, on );
+                    lds_v2( cf, pc + o, on );
                 }
 #pragma unroll
                 for( int j=0; j<NW; j++ )
