@@ -1480,7 +1480,27 @@ __global__ void __launch_bounds__( o2::NTHR, 2 ) k_dynamics_o2( const GridDev g,
             //                  node just outside; the flux running sum (Projector3D2Order.cpp:215-228) starts one
             //                  node earlier when the shift is negative.
             int xmeta = 0;
-            if( active ) {
+            if( __all_sync( 0xffffffffu, shifts == 0x15 ) ) {
+                // no particle of the warp changed node (nearly every warp of a slow species): S1 sits on the home nodes,
+                // none of the selections of the general case below
+                if( active ) {
+#pragma unroll
+                    for( int d=0; d<3; d++ ) {
+                        double w1[NW], s0[NW];
+                        shape2( dl1[d], w1 );
+                        shape2( xdelta[d], s0 );
+                        const double ds0 = w1[0] - s0[0], ds1 = w1[1] - s0[1], ds2 = w1[2] - s0[2];
+                        double2 *r2 = reinterpret_cast<double2 *>( rec + 6*d );
+                        r2[0] = make_double2( fma( 0.5, ds0, s0[0] ), fma( 0.5, ds1, s0[1] ) );
+                        r2[1] = make_double2( fma( 0.5, ds2, s0[2] ), ds0*K12 );
+                        r2[2] = make_double2( ds1*K12, ds2*K12 );
+                        const double cf0 = -cr[d]*( 0. + ds0 );
+                        const double cf1 = fma( -cr[d], ds1, cf0 );
+                        *reinterpret_cast<double2 *>( rec + 18 + 2*d ) = make_double2( cf0, cf1 );
+                    }
+                    *reinterpret_cast<double2 *>( rec + 24 ) = make_double2( 0., 0. );
+                }
+            } else if( active ) {
                 const bool home = nx <= 1;           // the consumer deposits the home part; movers in 2+ dimensions go to the queue whole
                 double xe = 0., xc = 0.;
 #pragma unroll
