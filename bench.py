@@ -547,7 +547,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_dynamics (gather+push+BC+deposit, one species)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dyn_bytes, "ms_per_launch": dyn_ms,
-                     "note": "FP64-issue / latency bound, not HBM bound (DESIGN.md §4.2, profiles/r2_final_dynamics_256.txt); "
+                     "note": "bound by the shared-memory pipe (66 / 78 % of its wavefront peak) and FP64 latency, not by HBM (DESIGN.md §4.2, profiles/r2_final_dynamics_256.txt, r2_lds_pattern.txt); "
                              "traffic = DRAM bytes per launch from the ncu --set full capture recorded in profiles/r2_traffic.json"},
         "energies": {"Ukin": [float(v) for v in uk], "Uelm": ue},
         "gpu_launches": int(launches),
