@@ -131,16 +131,23 @@ __global__ void __launch_bounds__( 256 ) k_scatter_idx( const int *__restrict__ 
     const size_t per = ( nblk + nwarp - 1 )/nwarp;
     const size_t b0 = ( blockIdx.x*( size_t )( blockDim.x >> 5 ) + ( threadIdx.x >> 5 ) )*per;
     const size_t b1 = b0 + per < nblk ? b0 + per : nblk;
+    // the keys of the next two stretches are already in flight while the atomic of this one makes its round trip (the walk
+    // of a warp is a chain of dependent latencies: key load, atomic, store)
+    int kn1 = b0 < b1 && b0*32 + lane < n ? key[b0*32 + lane] : -1;
+    int kn2 = b0 + 1 < b1 && ( b0+1 )*32 + lane < n ? key[( b0+1 )*32 + lane] : -1;
     for( size_t b = b0; b < b1; b++ ) {
         const size_t i = b*32 + lane;
-        const int k = i < n ? key[i] : -1;
+        const int k = kn1;
+        kn1 = kn2;
+        kn2 = b + 2 < b1 && ( b+2 )*32 + lane < n ? key[( b+2 )*32 + lane] : -1;
+        const int f = k >= 0 ? first[k] : 0;                  // independent of the atomic: issued before it returns
         const unsigned peers = __match_any_sync( 0xffffffffu, k );
         const int leader = __ffs( peers ) - 1;
         const int rank = __popc( peers & ( ( 1u << lane ) - 1u ) );
         int base = 0;
         if( lane == leader && k >= 0 ) base = atomicAdd( &cursor[k], __popc( peers ) );
         base = __shfl_sync( 0xffffffffu, base, leader );
-        if( k >= 0 ) perm[first[k] + base + rank] = ( int )i;
+        if( k >= 0 ) perm[f + base + rank] = ( int )i;
     }
 }
 
