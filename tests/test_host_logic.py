@@ -513,3 +513,28 @@ def test_moving_window_options_outside_the_path_are_rejected():
     one = WINDOW_NAMELIST.replace("number_of_patches=[12, 1, 1]", "number_of_patches=[1, 1, 1]")
     with pytest.raises(namelist.NamelistError):
         namelist.load_namelist(one, is_source=True).check_hot_path()
+
+
+def test_regular_cold_cells_uniform_branch_matches_the_general_one():
+    """particles_init.regular_cold_cells: a uniform plasma (every profile a number) takes a branch without per-cell
+    arrays — the slab a moving window uncovers asks for it every few steps; it must return exactly what the general
+    branch returns for the same plasma written as a profile."""
+    from smilei_b200 import namelist, particles_init as pi
+    src = '''
+Main(geometry="3Dcartesian", interpolation_order=2, timestep=0.19, simulation_time=1.9, cell_length=[0.2,3.,3.],
+     grid_length=[6.4,48.,48.], number_of_patches=[4,4,4], EM_boundary_conditions=[["silver-muller"]])
+Species(name="electron", position_initialization="regular", momentum_initialization="cold", particles_per_cell=%s, mass=1.0,
+        charge=-1.0, charge_density=%s, mean_velocity=[0.,0.,0.], temperature=[0.], pusher="vay",
+        boundary_conditions=[["remove","remove"]]*3)
+'''
+    for ppc in ("1", "8"):
+        p1 = namelist.load_namelist(src % (ppc, "0.000494"), is_source=True)
+        p2 = namelist.load_namelist(src % (ppc, "lambda x,y,z: 0.000494 + 0*x"), is_source=True)
+        for n, oc in (((8, 16, 16), (40, 0, 0)), ((32, 16, 16), None), ((8, 16, 16), (48, 0, 0))):
+            a = pi.regular_cold_cells(p1, p1.species[0], n, (0, 0, 0), origin_cells=oc)
+            b = pi.regular_cold_cells(p2, p2.species[0], n, (0, 0, 0), origin_cells=oc)
+            assert a[0] == b[0] and a[4] == b[4] and a[5] == b[5]
+            for x, y in zip(a[1:4], b[1:4]):
+                assert x.dtype == y.dtype and np.array_equal(x, y)
+    p0 = namelist.load_namelist(src % ("1", "0."), is_source=True)
+    assert len(pi.regular_cold_cells(p0, p0.species[0], (8, 16, 16), (0, 0, 0))[1]) == 0
