@@ -101,6 +101,17 @@ __global__ void __launch_bounds__( 256 ) k_faraday_center( GridDev g,
         const double2 ey = *reinterpret_cast<const double2 *>( Ey+idx );
         const double2 ez = *reinterpret_cast<const double2 *>( Ez+idx );
         const double exm = k > 0 ? Ex[idx-1] : 0., eym = k > 0 ? Ey[idx-1] : 0.;
+        // every operand of the three updates is asked for here, before the first of them is used (the index of a
+        // neighbour that does not exist is replaced by the point's own: loaded, never used): behind the conditions of
+        // the updates the loads formed three dependent groups per point, each one waiting for a DRAM round trip
+        const long long oy = j >= 1 ? g.sy : 0, ox = i >= 1 ? g.sx : 0;
+        const double2 ezj = *reinterpret_cast<const double2 *>( Ez+idx-oy );
+        const double2 ezi = *reinterpret_cast<const double2 *>( Ez+idx-ox );
+        const double2 eyi = *reinterpret_cast<const double2 *>( Ey+idx-ox );
+        const double2 exj = *reinterpret_cast<const double2 *>( Ex+idx-oy );
+        const double2 bx0 = *reinterpret_cast<const double2 *>( Bx+idx );
+        const double2 by0 = *reinterpret_cast<const double2 *>( By+idx );
+        const double2 bz0 = *reinterpret_cast<const double2 *>( Bz+idx );
         bool kint[2], ksh[2], kp[2];
         for( int s=0; s<2; s++ ) {
             kint[s] = ( k+s ) >= 1 && ( k+s ) < g.d[2]-1;
@@ -110,10 +121,9 @@ __global__ void __launch_bounds__( 256 ) k_faraday_center( GridDev g,
         const bool kd1 = k+1 < g.d[2];
         // Bx^(p,d,d):  Bx += -dt/dy*(Ez-Ez[j-1]) + dt/dz*(Ey-Ey[k-1]),  j in [1,d1-1), k in [1,d2-1)
         if( ip ) {
-            double2 b = *reinterpret_cast<double2 *>( Bx+idx );
+            double2 b = bx0;
             const double2 old = b;
             if( j_int ) {
-                const double2 ezj = *reinterpret_cast<const double2 *>( Ez+idx-g.sy );
                 if( kint[0] ) b.x = __dadd_rn( b.x, __dadd_rn( -__dmul_rn( ddy, __dadd_rn( ez.x, -ezj.x ) ), __dmul_rn( ddz, __dadd_rn( ey.x, -eym ) ) ) );
                 if( kint[1] ) b.y = __dadd_rn( b.y, __dadd_rn( -__dmul_rn( ddy, __dadd_rn( ez.y, -ezj.y ) ), __dmul_rn( ddz, __dadd_rn( ey.y, -ey.x ) ) ) );
                 *reinterpret_cast<double2 *>( Bx+idx ) = b;
@@ -126,10 +136,9 @@ __global__ void __launch_bounds__( 256 ) k_faraday_center( GridDev g,
         }
         // By^(d,p,d):  By += -dt/dz*(Ex-Ex[k-1]) + dt/dx*(Ez-Ez[i-1]),  i in [1,d0-1), k in [1,d2-1)
         if( jp ) {
-            double2 b = *reinterpret_cast<double2 *>( By+idx );
+            double2 b = by0;
             const double2 old = b;
             if( i_int ) {
-                const double2 ezi = *reinterpret_cast<const double2 *>( Ez+idx-g.sx );
                 if( kint[0] ) b.x = __dadd_rn( b.x, __dadd_rn( -__dmul_rn( ddz, __dadd_rn( ex.x, -exm ) ), __dmul_rn( ddx, __dadd_rn( ez.x, -ezi.x ) ) ) );
                 if( kint[1] ) b.y = __dadd_rn( b.y, __dadd_rn( -__dmul_rn( ddz, __dadd_rn( ex.y, -ex.x ) ), __dmul_rn( ddx, __dadd_rn( ez.y, -ezi.y ) ) ) );
                 *reinterpret_cast<double2 *>( By+idx ) = b;
@@ -142,11 +151,9 @@ __global__ void __launch_bounds__( 256 ) k_faraday_center( GridDev g,
         }
         // Bz^(d,d,p):  Bz += -dt/dx*(Ey-Ey[i-1]) + dt/dy*(Ex-Ex[j-1]),  i in [1,d0-1), j in [1,d1-1), k in [0,p2)
         if( kp[0] ) {
-            double2 b = *reinterpret_cast<double2 *>( Bz+idx );
+            double2 b = bz0;
             const double2 old = b;
             if( i_int && j_int ) {
-                const double2 eyi = *reinterpret_cast<const double2 *>( Ey+idx-g.sx );
-                const double2 exj = *reinterpret_cast<const double2 *>( Ex+idx-g.sy );
                 b.x = __dadd_rn( b.x, __dadd_rn( -__dmul_rn( ddx, __dadd_rn( ey.x, -eyi.x ) ), __dmul_rn( ddy, __dadd_rn( ex.x, -exj.x ) ) ) );
                 if( kp[1] ) b.y = __dadd_rn( b.y, __dadd_rn( -__dmul_rn( ddx, __dadd_rn( ey.y, -eyi.y ) ), __dmul_rn( ddy, __dadd_rn( ex.y, -exj.y ) ) ) );
                 *reinterpret_cast<double2 *>( Bz+idx ) = b;
