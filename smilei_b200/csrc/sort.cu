@@ -131,23 +131,37 @@ __global__ void __launch_bounds__( 256 ) k_scatter_idx( const int *__restrict__ 
     const size_t per = ( nblk + nwarp - 1 )/nwarp;
     const size_t b0 = ( blockIdx.x*( size_t )( blockDim.x >> 5 ) + ( threadIdx.x >> 5 ) )*per;
     const size_t b1 = b0 + per < nblk ? b0 + per : nblk;
-    // the keys of the next two stretches are already in flight while the atomic of this one makes its round trip (the walk
-    // of a warp is a chain of dependent latencies: key load, atomic, store)
-    int kn1 = b0 < b1 && b0*32 + lane < n ? key[b0*32 + lane] : -1;
-    int kn2 = b0 + 1 < b1 && ( b0+1 )*32 + lane < n ? key[( b0+1 )*32 + lane] : -1;
-    for( size_t b = b0; b < b1; b++ ) {
-        const size_t i = b*32 + lane;
-        const int k = kn1;
-        kn1 = kn2;
-        kn2 = b + 2 < b1 && ( b+2 )*32 + lane < n ? key[( b+2 )*32 + lane] : -1;
-        const int f = k >= 0 ? first[k] : 0;                  // independent of the atomic: issued before it returns
-        const unsigned peers = __match_any_sync( 0xffffffffu, k );
-        const int leader = __ffs( peers ) - 1;
-        const int rank = __popc( peers & ( ( 1u << lane ) - 1u ) );
-        int base = 0;
-        if( lane == leader && k >= 0 ) base = atomicAdd( &cursor[k], __popc( peers ) );
-        base = __shfl_sync( 0xffffffffu, base, leader );
-        if( k >= 0 ) perm[f + base + rank] = ( int )i;
+    // A warp's walk is a chain of dependent latencies (key load, atomic round trip, store).  Four stretches are taken per
+    // turn, their atomics in flight together, and the keys of the next turn are loaded before this one's atomics are
+    // issued.  (Atomics of one warp on one cursor leave the SM in program order; should two ever be served the other
+    // way round, k_cell_sort repairs the run like any other.)
+    auto load = [&]( size_t b ) -> int { const size_t i = b*32 + lane; return b < b1 && i < n ? key[i] : -1; };
+    constexpr int U = 4;                                   // stretches per turn
+    int kn[U];
+#pragma unroll
+    for( int u=0; u<U; u++ ) kn[u] = load( b0 + u );
+    const unsigned below = ( 1u << lane ) - 1u;
+    for( size_t b = b0; b < b1; b += U ) {
+        int k[U], f[U], base[U], lead[U];
+        unsigned peers[U];
+#pragma unroll
+        for( int u=0; u<U; u++ ) { k[u] = kn[u]; kn[u] = load( b + U + u ); }
+#pragma unroll
+        for( int u=0; u<U; u++ ) {
+            f[u] = k[u] >= 0 ? first[k[u]] : 0;           // independent of the atomics
+            peers[u] = __match_any_sync( 0xffffffffu, k[u] );
+            lead[u] = __ffs( peers[u] ) - 1;
+        }
+#pragma unroll
+        for( int u=0; u<U; u++ ) {
+            base[u] = 0;
+            if( lane == lead[u] && k[u] >= 0 ) base[u] = atomicAdd( &cursor[k[u]], __popc( peers[u] ) );
+        }
+#pragma unroll
+        for( int u=0; u<U; u++ ) {
+            base[u] = __shfl_sync( 0xffffffffu, base[u], lead[u] );
+            if( k[u] >= 0 ) perm[f[u] + base[u] + __popc( peers[u] & below )] = ( int )( ( b+u )*32 + lane );
+        }
     }
 }
 
