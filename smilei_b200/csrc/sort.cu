@@ -224,9 +224,12 @@ __global__ void __launch_bounds__( 256 ) k_cell_sort( const int *__restrict__ fi
         if( ( bad >> lane ) & 1u ) {
             if( staged ) {
                 const int b0 = cb - base, e0 = ce - base;
+                int prev = sm[b0 + ( b0 >> 4 )];                       // the largest entry so far = the one just before i
                 for( int i = b0+1; i < e0; i++ ) {
                     const int v = sm[i + ( i >> 4 )];
-                    int j = i-1;
+                    if( v > prev ) { prev = v; continue; }             // in order (the common case): nothing to move
+                    sm[i + ( i >> 4 )] = prev;
+                    int j = i-2;
                     while( j >= b0 ) {
                         const int u = sm[j + ( j >> 4 )];
                         if( u <= v ) break;
