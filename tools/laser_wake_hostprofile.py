@@ -1,5 +1,7 @@
+"""Host-side profile (cProfile) of 20 steps of the laser-wake workload of bench.py on one GPU: where the host thread waits
+or works between the kernels.  python tools/laser_wake_hostprofile.py   (on a B200)"""
 import sys, os, time, cProfile, pstats
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 from smilei_b200 import namelist
 from smilei_b200.simulation import Simulation
