@@ -12,10 +12,11 @@
 // Design: one CTA per tile of 4 x 4 x 8 primal-node cells.  Because the particles are
 // sorted by cell key (z fastest), the tile's particles are 16 contiguous runs.  The CTA receives the E and
 // B_m stencil boxes of the tile by TMA (cp.async.bulk.tensor), keeps a private fixed-point J box in shared
-// memory and hands it to the TMA unit once (cp.reduce.async.bulk.tensor .add).  Order 2: k_dynamics_o2
-// (producer warps walk the particle stream, consumer warps form the per-cell current sums); order 4:
-// k_dynamics_cg (8-lane cell groups, shuffle transpose-reduction).  k_dynamics (one thread per particle, full
-// Esirkepov window) is compiled only with -DSB200_AB_KERNELS, for A/B checks.  Particle traffic is the
+// memory and hands it to the TMA unit once (cp.reduce.async.bulk.tensor .add).  Order 2: k_dynamics_o2,
+// order 4: k_dynamics_o4 (producer warps walk the particle stream, consumer warps form the per-cell current
+// sums).  k_dynamics_cg (8-lane cell groups, shuffle transpose-reduction: round 1's order-4 kernel) and k_dynamics
+// (one thread per particle, full Esirkepov window) are compiled only with -DSB200_AB_KERNELS, for A/B checks.
+// Particle traffic is the
 // algorithmic 110 B: read 7 doubles + 1 short, write 6 doubles + 1 int; Epart/Bpart/iold/deltaold/invgf
 // never exist in HBM unless SB200_DYN_KEEP_SCRATCH asks for them.
 #include "common.cuh"
