@@ -212,6 +212,19 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def other_ceilings(args):
+    """What the committed ncu capture of the dominant kernel says about the units that bind it instead of HBM (shared-memory
+    wavefronts, FP64 pipe, issue slots); reported next to the HBM roofline, never re-measured here."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            t = json.load(f)["k_dynamics_o2"]
+        if t["config"]["ncell"] == args.ncell and t["config"]["order"] == args.order:
+            return t.get("other_ceilings_from_the_same_capture")
+    except Exception:
+        pass
+    return None
+
+
 def measured_traffic(args):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture, when this run is the captured
     configuration (it is not re-measured here: a number taken under a profiler is never a bench value)."""
@@ -545,7 +558,7 @@ def main():
         "yee_roofline_frac": (192. * ncell_local / ((mw_ms + ctr_ms) * 1e-3) / 1e9) / peak,
         "yee_ms": {"ampere_faraday_center": mw_ms, "center_shell": ctr_ms},
         "roofline": {"bound": "hbm", "kernel": "k_dynamics (gather+push+BC+deposit, one species)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args), "peak_source": peak_src,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args), "other_ceilings": other_ceilings(args), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dyn_bytes, "ms_per_launch": dyn_ms,
                      "note": "bound by the shared-memory pipe (66 / 78 % of its wavefront peak) and FP64 latency, not by HBM (DESIGN.md §4.2, profiles/r2_final_dynamics_256.txt, r2_lds_pattern.txt); "
                              "traffic = DRAM bytes per launch from the ncu --set full capture recorded in profiles/r2_traffic.json"},
