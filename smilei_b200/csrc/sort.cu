@@ -403,7 +403,7 @@ int launch_sort( sb200_patch *p, int ispec )
     SB200_CUDA( cudaMemcpyAsync( &kept, s.first + p->ncells, sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
     SB200_CUDA( cudaMemcpyAsync( flags, p->iflags, 8*sizeof( int ), cudaMemcpyDeviceToHost, p->stream ) );
     if( n > 0 ) {
-        const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*16 ? ( n + 255 )/256 : 148*16 );
+        const unsigned blocks = ( unsigned )( ( n + 255 )/256 < 148*8 ? ( n + 255 )/256 : 148*8 );
         k_scatter_idx<<<blocks, 256, 0, p->stream>>>( s.key, s.first, p->cursor, s.perm, n );
         sb200::g_launches++;
         SB200_CUDA( cudaGetLastError() );
