@@ -195,6 +195,8 @@ def regular_cold_cells(params, sp, n, pcoord, origin_cells=None):
                 c, inv = _regular_counts(nppc1, sp.regular_number)
                 hit = (sig, (np.arange(ncell, dtype=np.int32), np.full(ncell, dens1 / nppc1),
                              np.full(ncell, charge1).astype(np.int16), c, inv))
+            for arr in hit[1][:3]:
+                arr.setflags(write=False)              # handed out again on the next call: nobody may write into them
             _UNIFORM_CACHE.clear()
             _UNIFORM_CACHE[key] = hit
         cells, weight, charge_i, c, inv = hit[1]
